@@ -1,0 +1,228 @@
+"""Validated launchers: torch tensors in, torch tensors out, straight through the C ABI.
+
+These are the moral equivalents of the reference's host functions `rasterize_cuda`,
+`render_cuda[_backward]`, `interpolate_cuda[_backward]`, `edge_grad_estimator_cuda_backward`
+(reference `src/*/..._kernel.cu`), including their argument checks and error messages
+(`TORCH_CHECK` -> RuntimeError with the same `rasterize(): ...` style prefixes).  PyTorch is
+used for device memory, the caching allocator and the current stream only.
+"""
+import torch
+
+from . import _lib
+
+
+def _chk(cond, msg):
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _f32(t, who, name):
+    _chk(t.is_floating_point(), f"{who}(): expected {name} to have floating point type, but {name} has {t.dtype}")
+    if t.dtype != torch.float32:
+        if t.dtype in (torch.float16, torch.bfloat16) and torch.is_autocast_enabled():
+            return t.float()  # what the reference's Autocast kernels do (cached_cast to fp32)
+        raise RuntimeError(
+            f"{who}(): drtk_b200 computes in float32 only, but {name} has {t.dtype}; cast it to float32"
+        )
+    return t
+
+
+# ------------------------------------------------------------------------------------------
+def rasterize(v, vi, height, width, wireframe=False, algo=0):
+    """-> (depth_img f32 [N,H,W], index_img i32 [N,H,W]); checks of src/rasterize/rasterize_kernel.cu:423-468."""
+    _chk(isinstance(v, torch.Tensor) and isinstance(vi, torch.Tensor), "rasterize(): expected all inputs to be defined")
+    _chk(v.device == vi.device and v.is_cuda, "rasterize(): expected all inputs to be on same cuda device")
+    v = _f32(v, "rasterize", "v")
+    _chk(vi.dtype == torch.int32, f"rasterize(): expected vi to have int32 type, but vi has {vi.dtype}")
+    _chk(v.layout == torch.strided and vi.layout == torch.strided, "rasterize(): expected all inputs to have torch.strided layout")
+    _chk(v.dim() == 3 and vi.dim() == 3,
+         f"rasterize(): expected v.ndim == 3, vi.ndim == 3, but got v with sizes {tuple(v.shape)} and vi with sizes {tuple(vi.shape)}")
+    _chk(v.size(2) == 3 and vi.size(2) == 3,
+         "rasterize(): expected third dim of v to be of size 3, and last dim of vi to be of size 3, but got "
+         f"{v.size(2)} in the third dim of v, and {vi.size(2)} in the last dim of vi")
+    _chk(vi.size(0) == v.size(0),
+         f"rasterize(): expected first dim of vi to match first dim of v, but got {v.size(0)} in first dim of v, and {vi.size(0)} in the first dim of vi")
+    _chk(v.size(1) < 0x10000000, f"rasterize(): expected second dim of v to be less or eual to 268435456, but got {v.size(1)}")
+    _chk(height > 0 and width > 0,
+         f"rasterize(): both height and width have to be greater than zero, but got height: {height}, and width: {width}")
+    if wireframe:
+        raise NotImplementedError("rasterize(): wireframe mode is not implemented in drtk_b200 yet")
+    lib = _lib.load()
+    N, V, F = v.size(0), v.size(1), vi.size(1)
+    H, W = int(height), int(width)
+    with torch.cuda.device(v.device):
+        depth = torch.empty((N, H, W), dtype=torch.float32, device=v.device)
+        index = torch.empty((N, H, W), dtype=torch.int32, device=v.device)
+        nbytes = lib.drtk_b200_rasterize_workspace_bytes(N, F, H, W, algo)
+        ws = torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=v.device)
+        rc = lib.drtk_b200_rasterize(
+            _lib.ptr(v), _lib.strides(v), _lib.ptr(vi), _lib.strides(vi), N, V, F, H, W,
+            int(bool(wireframe)), int(algo), _lib.ptr(depth), _lib.ptr(index), _lib.ptr(ws), ws.numel(),
+            _stream(v.device))
+    _lib.check(rc, "rasterize()")
+    return depth, index
+
+
+# ------------------------------------------------------------------------------------------
+def _check_render(v, vi, index_img):
+    _chk(v.device == vi.device and v.device == index_img.device and v.is_cuda,
+         "render(): expected all inputs to be on same cuda device")
+    _chk(vi.dtype == torch.int32, f"render(): expected vi to have int32 type, but vi has {vi.dtype}")
+    _chk(index_img.dtype == torch.int32, f"render(): expected index_img to have int32 type, but index_img has {index_img.dtype}")
+    _chk(v.dim() == 3 and vi.dim() == 3 and index_img.dim() == 3,
+         "render(): expected v.ndim == 3, vi.ndim == 3, index_img.ndim == 3, but got v with sizes "
+         f"{tuple(v.shape)} and vi with sizes {tuple(vi.shape)} and index_img with sizes {tuple(index_img.shape)}")
+    _chk(v.size(0) == index_img.size(0),
+         f"render(): expected v and index_img to have same batch size, but got v with sizes {tuple(v.shape)} and index_img with sizes {tuple(index_img.shape)}")
+    _chk(vi.size(0) == v.size(0),
+         f"rasterize(): expected first dim of vi to match first dim of v but got {v.size(0)} in first dim of v, and {vi.size(0)} in the first dim of vi")
+    _chk(v.size(2) == 3 and vi.size(2) == 3,
+         f"render(): expected third dim of v to be of size 3, and third dim of vi to be of size 3, but got {v.size(2)} in the third dim of v, and {vi.size(2)} in the third dim of vi")
+
+
+def render_forward(v, vi, index_img):
+    """-> (depth_img [N,H,W], bary_img [N,3,H,W]); checks of src/render/render_kernel.cu:285-336."""
+    v = _f32(v, "render", "v")
+    _check_render(v, vi, index_img)
+    lib = _lib.load()
+    N, V, F = v.size(0), v.size(1), vi.size(1)
+    H, W = index_img.size(1), index_img.size(2)
+    with torch.cuda.device(v.device):
+        depth = torch.empty((N, H, W), dtype=torch.float32, device=v.device)
+        bary = torch.empty((N, 3, H, W), dtype=torch.float32, device=v.device)
+        rc = lib.drtk_b200_render_forward(
+            _lib.ptr(v), _lib.strides(v), _lib.ptr(vi), _lib.strides(vi), _lib.ptr(index_img),
+            _lib.strides(index_img), N, V, F, H, W, _lib.ptr(depth), _lib.ptr(bary), _stream(v.device))
+    _lib.check(rc, "render()")
+    return depth, bary
+
+
+def render_backward(v, vi, index_img, grad_depth, grad_bary):
+    """-> grad_v [N,V,3] (src/render/render_kernel.cu:382-436). grad_* may be None (= zeros)."""
+    lib = _lib.load()
+    N, V, F = v.size(0), v.size(1), vi.size(1)
+    H, W = index_img.size(1), index_img.size(2)
+    if grad_depth is not None:
+        grad_depth = _f32(grad_depth, "render", "grad_depth_img")
+    if grad_bary is not None:
+        grad_bary = _f32(grad_bary, "render", "grad_bary_img")
+    with torch.cuda.device(v.device):
+        grad_v = torch.empty((N, V, 3), dtype=torch.float32, device=v.device)
+        rc = lib.drtk_b200_render_backward(
+            _lib.ptr(v), _lib.strides(v), _lib.ptr(vi), _lib.strides(vi), _lib.ptr(index_img),
+            _lib.strides(index_img), _lib.ptr(grad_depth),
+            None if grad_depth is None else _lib.strides(grad_depth), _lib.ptr(grad_bary),
+            None if grad_bary is None else _lib.strides(grad_bary), N, V, F, H, W, _lib.ptr(grad_v),
+            _stream(v.device))
+    _lib.check(rc, "render() backward")
+    return grad_v
+
+
+# ------------------------------------------------------------------------------------------
+def _check_interp(attr, vi, index_img, bary_img):
+    _chk(attr.device == vi.device and attr.device == index_img.device and attr.device == bary_img.device,
+         "interpolate(): expected all inputs to be on same device")
+    _chk(attr.is_cuda, "interpolate(): drtk_b200 has no CPU path; expected all inputs to be on a cuda device")
+    _chk(attr.dtype == bary_img.dtype,
+         f"interpolate(): expected vert_attributes and bary_img to have same dtype, but vert_attributes has {attr.dtype} and bary_img has {bary_img.dtype}")
+    _chk(vi.dtype == torch.int32, f"interpolate(): expected vi to have int32 type, but vi has {vi.dtype}")
+    _chk(index_img.dtype == torch.int32, f"interpolate(): expected index_img to have int32 type, but index_img has {index_img.dtype}")
+    _chk(attr.dim() == 3 and vi.dim() == 3 and index_img.dim() == 3 and bary_img.dim() == 4,
+         "interpolate(): expected vert_attributes.ndim == 3, vi.ndim == 3, index_img.ndim == 3, bary_img.ndim == 4, "
+         f"but got vert_attributes with sizes {tuple(attr.shape)} and vi with sizes {tuple(vi.shape)} and index_img with sizes {tuple(index_img.shape)} and bary_img with sizes {tuple(bary_img.shape)}")
+    _chk(attr.size(0) == index_img.size(0) and attr.size(0) == bary_img.size(0),
+         "interpolate(): expected vert_attributes, index_img and bary_img to have same batch size, "
+         f"but got vert_attributes with sizes {tuple(attr.shape)} and index_img with sizes {tuple(index_img.shape)} and bary_img with sizes {tuple(bary_img.shape)}")
+    _chk(vi.size(2) == 3 and bary_img.size(1) == 3,
+         f"interpolate(): expected last dim of vi to be of size 3, and second dim of bary_img to be of size 3, but got {vi.size(2)} in the last dim of vi, and {bary_img.size(1)} in the second dim of bary_img")
+    _chk(vi.size(0) == attr.size(0),
+         f"interpolate(): expected vi to have same first dimension as vert_atrributes, but got {vi.size(0)} in the first dim of vi, and {attr.size(0)} in the first dim of vert_attributes")
+    _chk(index_img.size(1) == bary_img.size(2) and index_img.size(2) == bary_img.size(3),
+         "interpolate(): expected H and W dims of index_img and bary_img to match")
+
+
+def interpolate_forward(attr, vi, index_img, bary_img):
+    """-> out [N,C,H,W]; checks of src/interpolate/interpolate_kernel.cu:459-526."""
+    _chk(attr.is_floating_point(), f"interpolate(): expected vert_attributes to have floating point type, but v has {attr.dtype}")
+    if torch.is_autocast_enabled():
+        attr = attr.float() if attr.dtype != torch.float32 else attr
+        bary_img = bary_img.float() if bary_img.dtype != torch.float32 else bary_img
+    _check_interp(attr, vi, index_img, bary_img)
+    attr = _f32(attr, "interpolate", "vert_attributes")
+    lib = _lib.load()
+    N, V, C = attr.shape
+    F = vi.size(1)
+    H, W = bary_img.size(2), bary_img.size(3)
+    with torch.cuda.device(attr.device):
+        out = torch.empty((N, C, H, W), dtype=torch.float32, device=attr.device)
+        rc = lib.drtk_b200_interpolate_forward(
+            _lib.ptr(attr), _lib.strides(attr), _lib.ptr(vi), _lib.strides(vi), _lib.ptr(index_img),
+            _lib.strides(index_img), _lib.ptr(bary_img), _lib.strides(bary_img), N, V, F, C, H, W,
+            _lib.ptr(out), _stream(attr.device))
+    _lib.check(rc, "interpolate()")
+    return out
+
+
+def interpolate_backward(grad_out, attr, vi, index_img, bary_img, need_attr_grad, need_bary_grad):
+    """-> (vert_attributes_grad [N,V,C] | None, bary_img_grad [N,3,H,W] | None)
+    (src/interpolate/interpolate_kernel.cu:642-697)."""
+    lib = _lib.load()
+    N, V, C = attr.shape
+    F = vi.size(1)
+    H, W = bary_img.size(2), bary_img.size(3)
+    grad_out = _f32(grad_out, "interpolate", "grad_out")
+    with torch.cuda.device(attr.device):
+        ga = torch.empty((N, V, C), dtype=torch.float32, device=attr.device) if need_attr_grad else None
+        gb = torch.empty((N, 3, H, W), dtype=torch.float32, device=attr.device) if need_bary_grad else None
+        rc = lib.drtk_b200_interpolate_backward(
+            _lib.ptr(grad_out), _lib.strides(grad_out), _lib.ptr(attr), _lib.strides(attr), _lib.ptr(vi),
+            _lib.strides(vi), _lib.ptr(index_img), _lib.strides(index_img), _lib.ptr(bary_img),
+            _lib.strides(bary_img), N, V, F, C, H, W, _lib.ptr(ga), _lib.ptr(gb), _stream(attr.device))
+    _lib.check(rc, "interpolate() backward")
+    return ga, gb
+
+
+# ------------------------------------------------------------------------------------------
+def check_edge_grad(v_pix, v_pix_img, vi, img, index_img):
+    """Argument checks of edge_grad_estimator_fwd (src/edge_grad/edge_grad_module.cpp:30-112)."""
+    who = "edge_grad_estimator()"
+    _chk(v_pix.device == v_pix_img.device and v_pix.device == vi.device and v_pix.device == img.device
+         and v_pix.device == index_img.device and v_pix.is_cuda, f"{who}: expected all inputs to be on same cuda device")
+    _chk(v_pix.is_floating_point() and v_pix_img.is_floating_point() and img.is_floating_point(),
+         f"{who}: expected v_pix, v_pix_img, and img to have floating point type, but v_pix has {v_pix.dtype} v_pix has {v_pix_img.dtype} img has {img.dtype}")
+    _chk(vi.dtype == torch.int32, f"{who}: expected vi to have int32 type, but vi has {vi.dtype}")
+    _chk(index_img.dtype == torch.int32, f"{who}: expected index_img to have int32 type, but index_img has {index_img.dtype}")
+    _chk(v_pix.dim() == 3 and v_pix_img.dim() == 4 and vi.dim() == 3 and img.dim() == 4 and index_img.dim() == 3,
+         f"{who}: expected v_pix.ndim == 3, v_pix_img.ndim == 4, vi.ndim == 3, img.ndim == 4, index_img.ndim == 3, "
+         f"but got v_pix with sizes {tuple(v_pix.shape)} and v_pix_img with sizes {tuple(v_pix_img.shape)} and vi with sizes {tuple(vi.shape)} and img with sizes {tuple(img.shape)} and index_img with sizes {tuple(index_img.shape)}")
+    _chk(v_pix.size(0) == v_pix_img.size(0) and v_pix.size(0) == img.size(0) and v_pix.size(0) == index_img.size(0),
+         f"{who}: expected v and index_img to have same batch size, but got v_pix with sizes {tuple(v_pix.shape)}, v_pix_img with sizes {tuple(v_pix_img.shape)}, img with sizes {tuple(img.shape)} and index_img with sizes {tuple(index_img.shape)}")
+    _chk(v_pix.size(2) == 3 and v_pix_img.size(1) == 3 and vi.size(2) == 3,
+         f"{who}: expected third dim of v_pix to be of size 3, and third dim of vi to be of size 3, but got {v_pix.size(2)} in the third dim of v_pix, and {v_pix_img.size(1)} in the second dim of v_pix_img, and {vi.size(2)} in the third dim of vi")
+    _chk(v_pix_img.size(3) == img.size(3) and v_pix_img.size(3) == index_img.size(2)
+         and v_pix_img.size(2) == img.size(2) and v_pix_img.size(2) == index_img.size(1),
+         f"{who}: expected width and height of v_pix_img, img, and index_img to match, but got size of v_pix_img: {tuple(v_pix_img.shape)}, size of img: {tuple(img.shape)}, size of index_img: {tuple(index_img.shape)}")
+
+
+def edge_grad_backward(v_pix, img, index_img, vi, grad_output, max_dp_dr):
+    """-> grad_v_pix_img [N,3,H,W] (src/edge_grad/edge_grad_kernel.cu:475-506)."""
+    lib = _lib.load()
+    v_pix = _f32(v_pix, "edge_grad_estimator", "v_pix")
+    img = _f32(img, "edge_grad_estimator", "img")
+    grad_output = _f32(grad_output, "edge_grad_estimator", "grad_output")
+    N, V = v_pix.size(0), v_pix.size(1)
+    F = vi.size(1)
+    C, H, W = img.size(1), img.size(2), img.size(3)
+    with torch.cuda.device(v_pix.device):
+        out = torch.empty((N, 3, H, W), dtype=torch.float32, device=v_pix.device)
+        rc = lib.drtk_b200_edge_grad_backward(
+            _lib.ptr(v_pix), _lib.strides(v_pix), _lib.ptr(img), _lib.strides(img), _lib.ptr(index_img),
+            _lib.strides(index_img), _lib.ptr(vi), _lib.strides(vi), _lib.ptr(grad_output),
+            _lib.strides(grad_output), N, V, F, C, H, W, float(max_dp_dr), _lib.ptr(out),
+            _stream(v_pix.device))
+    _lib.check(rc, "edge_grad_estimator() backward")
+    return out

@@ -1,0 +1,445 @@
+// rasterize.cu -- z-buffered triangle coverage for sm_100a.
+//
+// Contract (bit-exact with the reference CUDA build): src/rasterize/rasterize_kernel.cu:42-168
+// (+ unpack :402-415, memset :484-488) of facebookresearch/DRTK.  Per (triangle, pixel)
+// sample the arithmetic below reproduces the reference's compiled sm_100 SASS
+// (--use_fast_math: FTZ, MUFU.RCP, one specific FMA contraction per expression) with
+// explicit intrinsics, so that the packed (depth_bits << 32 | triangle_id) minimum -- an
+// order-independent quantity -- comes out identical however the work is organised.
+//
+// Organisation (NOT the reference's thread-per-triangle + 64-bit global atomics + memset +
+// unpack): triangles are binned to 32x32-pixel screen tiles; one CTA per tile keeps the packed
+// z-buffer of its tile in shared memory, resolves it there and writes index_img / depth_img
+// once with coalesced 128-bit stores.  Global traffic: the 8 B/px outputs plus the bin lists.
+//
+//   bin_count  -> scan_offsets -> bin_fill -> raster_tiles
+//
+// A triangle whose clamped bounding box spans at most 2x2 tiles ("small") is appended to
+// those tiles' lists (<= 4 entries, so the list storage is bounded by 4*N*F and the call needs
+// no device->host sync to size anything).  Everything else ("large") goes to one per-image
+// list that every tile of that image walks cooperatively (all threads of the CTA split the
+// pixels of the clipped bounding box).
+#include "common.cuh"
+
+namespace drtk {
+namespace {
+
+constexpr int kTileLog = 5;
+constexpr int kTile = 1 << kTileLog;        // 32 x 32 pixels
+constexpr int kTilePix = kTile * kTile;     // 1024
+constexpr int kRasterThreads = 128;
+
+struct RasterArgs {
+  const float* v;
+  Strides3 vs;
+  const int32_t* vi;
+  Strides3 vis;
+  int N, V, F, H, W;
+  int tilesX, tilesY;
+};
+
+// Everything a sample test needs, derived once per triangle.
+struct TriSetup {
+  // canonical edges k = 0,1,2  <->  (v1,v2), (v2,v0), (v0,v1); origin = endpoint with the lower
+  // vertex index (src/rasterize/rasterize_kernel.cu:29-40)
+  float ox[3], oy[3], abx[3], aby[3], sg[3];
+  float d0, d1, d2;  // MUFU.RCP(epsclamp(z_k))
+  float rden;        // MUFU.RCP(|den|)
+  bool tl[3];
+  int bx0, by0, bx1, by1;  // clamped pixel bounding box (inclusive); may be empty
+};
+
+__device__ __forceinline__ void canon_edge_setup(int ia, int ib, float ax, float ay, float bx,
+                                                 float by, float sgn, float& ox, float& oy,
+                                                 float& abx, float& aby, float& sg) {
+  if (ia <= ib) {
+    ox = ax; oy = ay; abx = sub_rn(bx, ax); aby = sub_rn(by, ay); sg = sgn;
+  } else {
+    ox = bx; oy = by; abx = sub_rn(ax, bx); aby = sub_rn(ay, by); sg = -sgn;
+  }
+}
+
+// Loads triangle f of image n, applies the reference's rejection rules (:81, :96-100, :107) and
+// fills the setup.  Returns false when the triangle produces no samples.
+__device__ __forceinline__ bool tri_setup(const RasterArgs& a, int n, int f, TriSetup& s) {
+  const int32_t* vip = a.vi + (int64_t)n * a.vis.s0 + (int64_t)f * a.vis.s1;
+  const int i0 = (int)(((uint32_t)vip[0]) & 0x0FFFFFFFu);  // top nibble reserved (:74)
+  const int i1 = vip[a.vis.s2];
+  const int i2 = vip[2 * a.vis.s2];
+  if (i0 == i1 && i1 == i2) return false;  // padding triangles (:81)
+
+  const float* vp = a.v + (int64_t)n * a.vs.s0;
+  const float* q0 = vp + (int64_t)i0 * a.vs.s1;
+  const float* q1 = vp + (int64_t)i1 * a.vs.s1;
+  const float* q2 = vp + (int64_t)i2 * a.vs.s1;
+  const float p0x = q0[0], p0y = q0[a.vs.s2], z0 = q0[2 * a.vs.s2];
+  const float p1x = q1[0], p1y = q1[a.vs.s2], z1 = q1[2 * a.vs.s2];
+  const float p2x = q2[0], p2y = q2[a.vs.s2], z2 = q2[2 * a.vs.s2];
+
+  if (!(z0 > 1e-8f && z1 > 1e-8f && z2 > 1e-8f)) return false;  // (:96)
+  const float mnx = fminf(fminf(p0x, p1x), p2x), mny = fminf(fminf(p0y, p1y), p2y);
+  const float mxx = fmaxf(fmaxf(p0x, p1x), p2x), mxy = fmaxf(fmaxf(p0y, p1y), p2y);
+  if (!(mnx <= (float)(a.W - 1) && mny <= (float)(a.H - 1) && mxx > 0.f && mxy > 0.f))
+    return false;  // (:97-98)
+
+  const float v01x = sub_rn(p1x, p0x), v01y = sub_rn(p1y, p0y);
+  const float v02x = sub_rn(p2x, p0x), v02y = sub_rn(p2y, p0y);
+  const float v12x = sub_rn(p2x, p1x), v12y = sub_rn(p2y, p1y);
+  const float den = diff_of_products(v01x, v02y, v01y, v02x);  // (:105) FMUL + FFMA as compiled
+  if (den == 0.f) return false;                                   // (:107)
+
+  // bounding box with the reference's truncation and +1 border (:109-113)
+  s.bx0 = max(0, __float2int_rz(mnx));
+  s.by0 = max(0, __float2int_rz(mny));
+  s.bx1 = min(a.W - 1, (int)((unsigned)__float2int_rz(mxx) + 1u));
+  s.by1 = min(a.H - 1, (int)((unsigned)__float2int_rz(mxy) + 1u));
+
+  const float sgn = den > 0.f ? 1.f : -1.f;  // sign(den), den != 0 (:125)
+  canon_edge_setup(i1, i2, p1x, p1y, p2x, p2y, sgn, s.ox[0], s.oy[0], s.abx[0], s.aby[0], s.sg[0]);
+  canon_edge_setup(i2, i0, p2x, p2y, p0x, p0y, sgn, s.ox[1], s.oy[1], s.abx[1], s.aby[1], s.sg[1]);
+  canon_edge_setup(i0, i1, p0x, p0y, p1x, p1y, sgn, s.ox[2], s.oy[2], s.abx[2], s.aby[2], s.sg[2]);
+
+  if (den > 0.f) {  // top-left classification (:133-141)
+    s.tl[0] = (v12y < 0.f) || (v12y == 0.f && v12x > 0.f);
+    s.tl[1] = (v02y > 0.f) || (v02y == 0.f && v02x < 0.f);
+    s.tl[2] = (v01y < 0.f) || (v01y == 0.f && v01x > 0.f);
+  } else {
+    s.tl[0] = (v12y > 0.f) || (v12y == 0.f && v12x < 0.f);
+    s.tl[1] = (v02y < 0.f) || (v02y == 0.f && v02x > 0.f);
+    s.tl[2] = (v01y > 0.f) || (v01y == 0.f && v01x < 0.f);
+  }
+  s.rden = rcp_approx(fabsf(den));  // (:148) under fast-math: bary * MUFU.RCP(|den|)
+  s.d0 = rcp_approx(epsclamp(z0));  // (:151)
+  s.d1 = rcp_approx(epsclamp(z1));
+  s.d2 = rcp_approx(epsclamp(z2));
+  return true;
+}
+
+// One (triangle, pixel) sample.  Returns true and the depth bits when the pixel centre (x, y)
+// is covered under the top-left rule (:118-153).
+__device__ __forceinline__ bool sample(const TriSetup& s, float px, const float (&row)[3],
+                                       const float (&apy)[3], uint32_t& depth_bits) {
+  (void)apy;
+  // e_k = fma(-ab.y, p.x - o.x, rn((p.y - o.y) * ab.x)); the product is per-row (hoisted by the
+  // reference compiler as well; same value either way)
+  const float b0 = mul_rn(fma_rn(-s.aby[0], sub_rn(px, s.ox[0]), row[0]), s.sg[0]);
+  const float b1 = mul_rn(fma_rn(-s.aby[1], sub_rn(px, s.ox[1]), row[1]), s.sg[1]);
+  const float b2 = mul_rn(fma_rn(-s.aby[2], sub_rn(px, s.ox[2]), row[2]), s.sg[2]);
+  if (!(b0 >= 0.f && b1 >= 0.f && b2 >= 0.f)) return false;
+  if ((b0 == 0.f && !s.tl[0]) || (b1 == 0.f && !s.tl[1]) || (b2 == 0.f && !s.tl[2])) return false;
+  const float c0 = mul_rn(b0, s.rden), c1 = mul_rn(b1, s.rden), c2 = mul_rn(b2, s.rden);
+  // dot(d_inv, bary) as compiled: FMUL(b1,d1) -> FFMA(b0,d0,.) -> FFMA(b2,d2,.)
+  const float inv = fma_rn(c2, s.d2, fma_rn(c0, s.d0, mul_rn(c1, s.d1)));
+  depth_bits = __float_as_uint(rcp_approx(epsclamp(inv)));
+  return true;
+}
+
+__device__ __forceinline__ void row_terms(const TriSetup& s, float py, float (&row)[3]) {
+  row[0] = mul_rn(sub_rn(py, s.oy[0]), s.abx[0]);
+  row[1] = mul_rn(sub_rn(py, s.oy[1]), s.abx[1]);
+  row[2] = mul_rn(sub_rn(py, s.oy[2]), s.abx[2]);
+}
+
+// ------------------------------------------------------------------------------------------
+// binning
+// ------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(256) bin_kernel(RasterArgs a, int64_t total, uint32_t* tile_count,
+                                                  const uint32_t* tile_offset, uint32_t* tile_list,
+                                                  uint32_t* large_count, uint32_t* large_list) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int n = (int)(idx / a.F);
+  const int f = (int)(idx - (int64_t)n * a.F);
+  TriSetup s;
+  if (!tri_setup(a, n, f, s)) return;
+  if (s.bx0 > s.bx1 || s.by0 > s.by1) return;
+  const int tx0 = s.bx0 >> kTileLog, tx1 = s.bx1 >> kTileLog;
+  const int ty0 = s.by0 >> kTileLog, ty1 = s.by1 >> kTileLog;
+  const int64_t tbase = (int64_t)n * a.tilesX * a.tilesY;
+  if (tx1 - tx0 <= 1 && ty1 - ty0 <= 1) {
+    for (int ty = ty0; ty <= ty1; ++ty)
+      for (int tx = tx0; tx <= tx1; ++tx) {
+        const int64_t t = tbase + (int64_t)ty * a.tilesX + tx;
+        const uint32_t k = atomicAdd(&tile_count[t], 1u);
+        if (FILL) tile_list[tile_offset[t] + k] = (uint32_t)f;
+      }
+  } else if (FILL) {
+    const uint32_t k = atomicAdd(&large_count[n], 1u);
+    large_list[(int64_t)n * a.F + k] = (uint32_t)f;
+  }
+}
+
+// exclusive scan of `count[0..M)` into `offset[0..M)`, zeroing `count` so that bin_kernel<true>
+// can reuse it as the per-tile cursor.  One CTA; M is #tiles * N (1e5 .. 1e6 at most).
+__global__ void __launch_bounds__(1024) scan_kernel(uint32_t* count, uint32_t* offset, int64_t M) {
+  __shared__ uint32_t warp_sums[32];
+  const int tid = threadIdx.x;
+  const int64_t chunk = (M + 1023) / 1024;
+  const int64_t b = tid * chunk, e = min(M, b + chunk);
+  uint32_t sum = 0;
+  for (int64_t i = b; i < e; ++i) sum += count[i];
+  // block exclusive scan of `sum`
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((tid & 31) >= o) inc += t;
+  }
+  if ((tid & 31) == 31) warp_sums[tid >> 5] = inc;
+  __syncthreads();
+  if (tid < 32) {
+    uint32_t w = warp_sums[tid];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+      if (tid >= o) w += t;
+    }
+    warp_sums[tid] = w;
+  }
+  __syncthreads();
+  uint32_t run = inc - sum + ((tid >> 5) ? warp_sums[(tid >> 5) - 1] : 0u);
+  for (int64_t i = b; i < e; ++i) {
+    const uint32_t c = count[i];
+    offset[i] = run;
+    count[i] = 0u;
+    run += c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-tile resolve
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRasterThreads) raster_tiles_kernel(
+    RasterArgs a, const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_offset,
+    const uint32_t* __restrict__ tile_list, const uint32_t* __restrict__ large_count,
+    const uint32_t* __restrict__ large_list, float* __restrict__ depth_img,
+    int32_t* __restrict__ index_img) {
+  __shared__ unsigned long long zbuf[kTilePix];
+  const int tid = threadIdx.x;
+  const int64_t t = blockIdx.x;
+  const int tiles_per_img = a.tilesX * a.tilesY;
+  const int n = (int)(t / tiles_per_img);
+  const int tl = (int)(t - (int64_t)n * tiles_per_img);
+  const int tile_y = tl / a.tilesX, tile_x = tl - tile_y * a.tilesX;
+  const int x_lo = tile_x << kTileLog, y_lo = tile_y << kTileLog;
+  const int x_hi = min(x_lo + kTile - 1, a.W - 1), y_hi = min(y_lo + kTile - 1, a.H - 1);
+
+  for (int i = tid; i < kTilePix; i += kRasterThreads) zbuf[i] = ~0ull;  // (:484-488)
+  __syncthreads();
+
+  // (1) small triangles: one thread per list entry, serial walk of the clipped bounding box
+  const uint32_t cnt = tile_count[t];
+  const uint32_t* list = tile_list + tile_offset[t];
+  for (uint32_t i = tid; i < cnt; i += kRasterThreads) {
+    const int f = (int)list[i];
+    TriSetup s;
+    if (!tri_setup(a, n, f, s)) continue;
+    const int bx0 = max(s.bx0, x_lo), bx1 = min(s.bx1, x_hi);
+    const int by0 = max(s.by0, y_lo), by1 = min(s.by1, y_hi);
+    for (int y = by0; y <= by1; ++y) {
+      float row[3];
+      row_terms(s, (float)y, row);
+      for (int x = bx0; x <= bx1; ++x) {
+        uint32_t db;
+        if (sample(s, (float)x, row, row, db)) {
+          const unsigned long long packed = ((unsigned long long)db << 32) | (uint32_t)f;  // (:155-157)
+          atomicMin(&zbuf[((y - y_lo) << kTileLog) + (x - x_lo)], packed);
+        }
+      }
+    }
+  }
+
+  // (2) large triangles of this image: whole CTA cooperates on each one
+  const uint32_t nlarge = large_count[n];
+  const uint32_t* llist = large_list + (int64_t)n * a.F;
+  for (uint32_t j = 0; j < nlarge; ++j) {
+    const int f = (int)llist[j];
+    TriSetup s;
+    if (!tri_setup(a, n, f, s)) continue;  // uniform across the CTA
+    const int bx0 = max(s.bx0, x_lo), bx1 = min(s.bx1, x_hi);
+    const int by0 = max(s.by0, y_lo), by1 = min(s.by1, y_hi);
+    if (bx0 > bx1 || by0 > by1) continue;
+    const int bw = bx1 - bx0 + 1, npx = bw * (by1 - by0 + 1);
+    for (int p = tid; p < npx; p += kRasterThreads) {
+      const int yy = p / bw, xx = p - yy * bw;
+      const int x = bx0 + xx, y = by0 + yy;
+      float row[3];
+      row_terms(s, (float)y, row);
+      uint32_t db;
+      if (sample(s, (float)x, row, row, db)) {
+        const unsigned long long packed = ((unsigned long long)db << 32) | (uint32_t)f;
+        atomicMin(&zbuf[((y - y_lo) << kTileLog) + (x - x_lo)], packed);
+      }
+    }
+  }
+  __syncthreads();
+
+  // (3) resolve + store (:402-415): empty -> index -1 (low word all ones), depth 0
+  const int64_t img_base = (int64_t)n * a.H * a.W;
+  if ((a.W & 3) == 0) {
+    for (int q = tid; q < kTilePix / 4; q += kRasterThreads) {
+      const int ly = q >> 3, lx = (q & 7) << 2;
+      const int x = x_lo + lx, y = y_lo + ly;
+      if (x > x_hi || y > y_hi) continue;  // W % 4 == 0 -> the whole quad is inside or outside
+      int4 id;
+      float4 dp;
+      const unsigned long long z0 = zbuf[(ly << kTileLog) + lx], z1 = zbuf[(ly << kTileLog) + lx + 1],
+                               z2 = zbuf[(ly << kTileLog) + lx + 2], z3 = zbuf[(ly << kTileLog) + lx + 3];
+      id.x = (int)(uint32_t)z0; id.y = (int)(uint32_t)z1; id.z = (int)(uint32_t)z2; id.w = (int)(uint32_t)z3;
+      const uint32_t d0 = (uint32_t)(z0 >> 32), d1 = (uint32_t)(z1 >> 32), d2 = (uint32_t)(z2 >> 32),
+                     d3 = (uint32_t)(z3 >> 32);
+      dp.x = d0 == 0xFFFFFFFFu ? 0.f : __uint_as_float(d0);
+      dp.y = d1 == 0xFFFFFFFFu ? 0.f : __uint_as_float(d1);
+      dp.z = d2 == 0xFFFFFFFFu ? 0.f : __uint_as_float(d2);
+      dp.w = d3 == 0xFFFFFFFFu ? 0.f : __uint_as_float(d3);
+      const int64_t o = img_base + (int64_t)y * a.W + x;
+      stg_stream_i4(index_img + o, id);
+      stg_stream_f4(depth_img + o, dp);
+    }
+  } else {
+    for (int q = tid; q < kTilePix; q += kRasterThreads) {
+      const int ly = q >> kTileLog, lx = q & (kTile - 1);
+      const int x = x_lo + lx, y = y_lo + ly;
+      if (x > x_hi || y > y_hi) continue;
+      const unsigned long long z = zbuf[q];
+      const uint32_t d = (uint32_t)(z >> 32);
+      const int64_t o = img_base + (int64_t)y * a.W + x;
+      index_img[o] = (int)(uint32_t)z;
+      depth_img[o] = d == 0xFFFFFFFFu ? 0.f : __uint_as_float(d);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// validation path (algo 1): triangle-parallel walk with 64-bit global atomicMin + unpack.
+// Same per-sample arithmetic, the reference's work organisation; used by the tests to
+// cross-check the tiled path and as a second opinion against the oracle.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) raster_atomic_kernel(RasterArgs a, int64_t total,
+                                                            unsigned long long* packed_img) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int n = (int)(idx / a.F);
+  const int f = (int)(idx - (int64_t)n * a.F);
+  TriSetup s;
+  if (!tri_setup(a, n, f, s)) return;
+  unsigned long long* img = packed_img + (int64_t)n * a.H * a.W;
+  for (int y = s.by0; y <= s.by1; ++y) {
+    float row[3];
+    row_terms(s, (float)y, row);
+    for (int x = s.bx0; x <= s.bx1; ++x) {
+      uint32_t db;
+      if (sample(s, (float)x, row, row, db))
+        atomicMin(img + (int64_t)y * a.W + x, ((unsigned long long)db << 32) | (uint32_t)f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) unpack_kernel(const unsigned long long* __restrict__ packed,
+                                                     int64_t count, float* __restrict__ depth_img,
+                                                     int32_t* __restrict__ index_img) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const unsigned long long z = packed[i];
+  const uint32_t d = (uint32_t)(z >> 32);
+  index_img[i] = (int)(uint32_t)z;
+  depth_img[i] = d == 0xFFFFFFFFu ? 0.f : __uint_as_float(d);
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct TiledWorkspace {
+  size_t off_count, off_offset, off_large_count, off_large_list, off_tile_list, total;
+  int64_t M;
+};
+
+inline TiledWorkspace tiled_layout(int64_t N, int64_t F, int64_t H, int64_t W) {
+  TiledWorkspace w;
+  const int64_t tilesX = (W + kTile - 1) >> kTileLog, tilesY = (H + kTile - 1) >> kTileLog;
+  w.M = N * tilesX * tilesY;
+  size_t o = 0;
+  w.off_count = o;       o = align_up(o + sizeof(uint32_t) * (size_t)w.M, 256);
+  w.off_large_count = o; o = align_up(o + sizeof(uint32_t) * (size_t)N, 256);
+  const size_t zero_end = o;  // [0, zero_end) is memset to 0 per call
+  (void)zero_end;
+  w.off_offset = o;      o = align_up(o + sizeof(uint32_t) * (size_t)w.M, 256);
+  w.off_large_list = o;  o = align_up(o + sizeof(uint32_t) * (size_t)(N * F), 256);
+  w.off_tile_list = o;   o = align_up(o + sizeof(uint32_t) * (size_t)(4 * N * F), 256);
+  w.total = o;
+  return w;
+}
+
+}  // namespace
+}  // namespace drtk
+
+using namespace drtk;
+
+extern "C" size_t drtk_b200_rasterize_workspace_bytes(int64_t N, int64_t F, int64_t H, int64_t W,
+                                                       int algo) {
+  if (N <= 0 || H <= 0 || W <= 0 || F < 0) return 0;
+  if (algo == 1) return sizeof(unsigned long long) * (size_t)(N * H * W) + 256;
+  return tiled_layout(N, F, H, W).total + 256;
+}
+
+extern "C" int drtk_b200_rasterize(const float* v, const int64_t* v_strides, const int32_t* vi,
+                                   const int64_t* vi_strides, int64_t N, int64_t V, int64_t F,
+                                   int64_t H, int64_t W, int wireframe, int algo, float* depth_img,
+                                   int32_t* index_img, void* workspace, size_t workspace_bytes,
+                                   void* stream_) {
+  if (wireframe) return DRTK_B200_EUNSUPPORTED;
+  if (N < 0 || F < 0 || V < 0 || H <= 0 || W <= 0) return DRTK_B200_EINVAL;
+  if (N == 0) return 0;
+  if (!depth_img || !index_img || !v_strides || !vi_strides) return DRTK_B200_EINVAL;
+  if ((F > 0 && (!v || !vi))) return DRTK_B200_EINVAL;
+  if (H > (1 << 30) || W > (1 << 30) || N * F > (int64_t)0x1FFFFFFF || V >= 0x10000000LL)
+    return DRTK_B200_EUNSUPPORTED;
+  if (workspace_bytes < drtk_b200_rasterize_workspace_bytes(N, F, H, W, algo) || !workspace)
+    return DRTK_B200_EWORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+  RasterArgs a;
+  a.v = v; a.vs = make3(v_strides); a.vi = vi; a.vis = make3(vi_strides);
+  a.N = (int)N; a.V = (int)V; a.F = (int)F; a.H = (int)H; a.W = (int)W;
+  a.tilesX = (int)((W + kTile - 1) >> kTileLog);
+  a.tilesY = (int)((H + kTile - 1) >> kTileLog);
+  const int64_t total = N * F;
+  char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+
+  if (algo == 1) {
+    unsigned long long* packed = reinterpret_cast<unsigned long long*>(ws);
+    const int64_t npx = N * H * W;
+    DRTK_CUDA(cudaMemsetAsync(packed, 0xFF, sizeof(unsigned long long) * (size_t)npx, stream));
+    if (total > 0) {
+      raster_atomic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a, total, packed);
+      DRTK_CHECK_LAUNCH();
+    }
+    unpack_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, stream>>>(packed, npx, depth_img, index_img);
+    DRTK_CHECK_LAUNCH();
+    return 0;
+  }
+
+  const TiledWorkspace w = tiled_layout(N, F, H, W);
+  if (w.M > 0x7FFFFFFFLL) return DRTK_B200_EUNSUPPORTED;
+  uint32_t* tile_count = reinterpret_cast<uint32_t*>(ws + w.off_count);
+  uint32_t* large_count = reinterpret_cast<uint32_t*>(ws + w.off_large_count);
+  uint32_t* tile_offset = reinterpret_cast<uint32_t*>(ws + w.off_offset);
+  uint32_t* large_list = reinterpret_cast<uint32_t*>(ws + w.off_large_list);
+  uint32_t* tile_list = reinterpret_cast<uint32_t*>(ws + w.off_tile_list);
+
+  DRTK_CUDA(cudaMemsetAsync(ws, 0, w.off_offset, stream));  // tile_count + large_count
+  if (total > 0) {
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    bin_kernel<false><<<blocks, 256, 0, stream>>>(a, total, tile_count, nullptr, nullptr, nullptr, nullptr);
+    DRTK_CHECK_LAUNCH();
+    scan_kernel<<<1, 1024, 0, stream>>>(tile_count, tile_offset, w.M);
+    DRTK_CHECK_LAUNCH();
+    bin_kernel<true><<<blocks, 256, 0, stream>>>(a, total, tile_count, tile_offset, tile_list,
+                                                 large_count, large_list);
+    DRTK_CHECK_LAUNCH();
+  }
+  raster_tiles_kernel<<<(unsigned)w.M, kRasterThreads, 0, stream>>>(
+      a, tile_count, tile_offset, tile_list, large_count, large_list, depth_img, index_img);
+  DRTK_CHECK_LAUNCH();
+  return 0;
+}

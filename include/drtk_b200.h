@@ -1,0 +1,132 @@
+/*
+ * drtk_b200.h -- C ABI of libdrtk_b200.so: the B200 (sm_100a) rasterisation hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one host launcher of the
+ * reference (facebookresearch/DRTK) that sits behind a TORCH_LIBRARY op; the reference
+ * interface each one stands in for is cited as path:line relative to the reference root.
+ * The signatures carry only plain pointers, sizes, element strides and a CUDA stream --
+ * no torch types -- so the library can be bound from ctypes (drtk_b200/_lib.py), from a
+ * TORCH_LIBRARY shim or from any other host.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers on the current CUDA device; fp32 / int32 only
+ *   - `*_strides` are HOST arrays of element strides (as torch.Tensor.stride()), so
+ *     expanded (stride 0) and non-contiguous inputs are accepted exactly like the
+ *     reference kernels accept them (TensorInfo strides, e.g. src/render/render_kernel.cu:36-55)
+ *   - outputs are dense, freshly allocated by the caller, fully written by the callee
+ *     (no pre-zeroing needed, also not for the gradient accumulators)
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously,
+ *     nothing synchronises the device
+ *   - return value: 0 on success, otherwise a cudaError_t value (>0) or a DRTK_B200_E*
+ *     code (<0); drtk_b200_error_string() turns either into text.  No CPU fallback exists.
+ */
+#ifndef DRTK_B200_H_
+#define DRTK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRTK_B200_ABI_VERSION 1
+
+#define DRTK_B200_EINVAL (-1)     /* bad argument (null pointer, non-positive size, ...) */
+#define DRTK_B200_EWORKSPACE (-2) /* workspace too small */
+#define DRTK_B200_EUNSUPPORTED (-3)
+
+int drtk_b200_abi_version(void);
+const char* drtk_b200_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------
+ * rasterize  -- replaces rasterize_cuda (src/rasterize/rasterize_kernel.cu:417-563), i.e.
+ * the op `rasterize_ext::rasterize(Tensor v, Tensor vi, int height, int width,
+ * bool wireframe) -> Tensor[]` (src/rasterize/rasterize_module.cpp:77-79).
+ *
+ *   v          [N,V,3] f32, strides v_strides[3]
+ *   vi         [N,F,3] i32, strides vi_strides[3] (batch stride 0 for a shared topology)
+ *   depth_img  [N,H,W] f32 out (0 where empty);  index_img [N,H,W] i32 out (-1 where empty)
+ *   workspace  scratch of at least drtk_b200_rasterize_workspace_bytes(...) bytes
+ *   algo       0 = tile-binned, shared-memory z-buffer (default)
+ *              1 = triangle-parallel 64-bit global atomicMin (validation path; same bits)
+ * Bit-exact contract: depth_img / index_img equal the reference CUDA kernels' output.
+ * ------------------------------------------------------------------------------------- */
+size_t drtk_b200_rasterize_workspace_bytes(int64_t N, int64_t F, int64_t H, int64_t W, int algo);
+
+int drtk_b200_rasterize(const float* v, const int64_t* v_strides, const int32_t* vi,
+                        const int64_t* vi_strides, int64_t N, int64_t V, int64_t F, int64_t H,
+                        int64_t W, int wireframe, int algo, float* depth_img, int32_t* index_img,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * render forward -- replaces render_cuda (src/render/render_kernel.cu:283-380), op
+ * `render_ext::render(Tensor v, Tensor vi, Tensor index_img) -> Tensor[]`
+ * (src/render/render_module.cpp:89-91).
+ *   index_img [N,H,W] i32 (strides index_strides[3])
+ *   depth_img [N,H,W] f32 out;  bary_img [N,3,H,W] f32 out (planar)
+ * ------------------------------------------------------------------------------------- */
+int drtk_b200_render_forward(const float* v, const int64_t* v_strides, const int32_t* vi,
+                             const int64_t* vi_strides, const int32_t* index_img,
+                             const int64_t* index_strides, int64_t N, int64_t V, int64_t F,
+                             int64_t H, int64_t W, float* depth_img, float* bary_img,
+                             void* stream);
+
+/* render backward -- replaces render_cuda_backward (src/render/render_kernel.cu:382-436).
+ *   grad_depth [N,H,W] (may be NULL = zeros), grad_bary [N,3,H,W] (may be NULL = zeros)
+ *   grad_v     [N,V,3] f32 out, dense; zero-filled by the callee, then accumulated      */
+int drtk_b200_render_backward(const float* v, const int64_t* v_strides, const int32_t* vi,
+                              const int64_t* vi_strides, const int32_t* index_img,
+                              const int64_t* index_strides, const float* grad_depth,
+                              const int64_t* grad_depth_strides, const float* grad_bary,
+                              const int64_t* grad_bary_strides, int64_t N, int64_t V, int64_t F,
+                              int64_t H, int64_t W, float* grad_v, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * interpolate forward -- replaces interpolate_cuda
+ * (src/interpolate/interpolate_kernel.cu:454-570), op `interpolate_ext::interpolate(Tensor
+ * vert_attributes, Tensor vi, Tensor index_img, Tensor bary_img) -> Tensor`
+ * (src/interpolate/interpolate_module.cpp:632-634).
+ *   vert_attributes [N,V,C] f32;  bary_img [N,3,H,W] f32;  out [N,C,H,W] f32 (planar)
+ * ------------------------------------------------------------------------------------- */
+int drtk_b200_interpolate_forward(const float* vert_attributes, const int64_t* attr_strides,
+                                  const int32_t* vi, const int64_t* vi_strides,
+                                  const int32_t* index_img, const int64_t* index_strides,
+                                  const float* bary_img, const int64_t* bary_strides, int64_t N,
+                                  int64_t V, int64_t F, int64_t C, int64_t H, int64_t W,
+                                  float* out, void* stream);
+
+/* interpolate backward -- replaces interpolate_cuda_backward
+ * (src/interpolate/interpolate_kernel.cu:642-697).
+ *   grad_out [N,C,H,W] (strides grad_out_strides[4])
+ *   vert_attributes_grad [N,V,C] out or NULL (zero-filled by the callee, then accumulated)
+ *   bary_img_grad        [N,3,H,W] out or NULL (every pixel written)                      */
+int drtk_b200_interpolate_backward(const float* grad_out, const int64_t* grad_out_strides,
+                                   const float* vert_attributes, const int64_t* attr_strides,
+                                   const int32_t* vi, const int64_t* vi_strides,
+                                   const int32_t* index_img, const int64_t* index_strides,
+                                   const float* bary_img, const int64_t* bary_strides, int64_t N,
+                                   int64_t V, int64_t F, int64_t C, int64_t H, int64_t W,
+                                   float* vert_attributes_grad, float* bary_img_grad,
+                                   void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * edge_grad backward -- replaces edge_grad_estimator_cuda_backward
+ * (src/edge_grad/edge_grad_kernel.cu:475-506), the backward of op
+ * `edge_grad_ext::edge_grad_estimator(...)` (src/edge_grad/edge_grad_module.cpp:205-208;
+ * its forward is the identity on `img`, :118-137, and needs no kernel).
+ *   v_pix [N,V,3]; img [N,C,H,W]; grad_output [N,C,H,W]; grad_v_pix_img [N,3,H,W] out
+ *   (every pixel written: gather formulation, no zero-fill, no atomics, deterministic)
+ * ------------------------------------------------------------------------------------- */
+int drtk_b200_edge_grad_backward(const float* v_pix, const int64_t* v_strides, const float* img,
+                                 const int64_t* img_strides, const int32_t* index_img,
+                                 const int64_t* index_strides, const int32_t* vi,
+                                 const int64_t* vi_strides, const float* grad_output,
+                                 const int64_t* grad_output_strides, int64_t N, int64_t V,
+                                 int64_t F, int64_t C, int64_t H, int64_t W, float max_dp_dr,
+                                 float* grad_v_pix_img, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRTK_B200_H_ */

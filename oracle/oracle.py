@@ -1,0 +1,151 @@
+"""ctypes/numpy front-end of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY.  May be imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline leg -- never by drtk_b200/.  Each function restates the reference
+algorithm cited in drtk_oracle_impl.h; see that file for the file:line map.
+
+All arrays are numpy, C-contiguous; `vi` may be [F,3] (shared) or [N,F,3].
+dtype float32 -> *_f32 build, float64 -> *_f64 build.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("drtk_oracle.c", "drtk_oracle_impl.h")]
+    stale = (not os.path.exists(so)) or any(
+        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(so) for s in srcs
+    )
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _sfx(dt):
+    if dt == np.float32:
+        return "_f32"
+    if dt == np.float64:
+        return "_f64"
+    raise TypeError(f"oracle: unsupported dtype {dt}")
+
+
+def _prep_vi(vi, N):
+    vi = np.ascontiguousarray(vi, dtype=np.int32)
+    if vi.ndim == 2:
+        return vi, 0, vi.shape[0]
+    assert vi.shape[0] == N
+    return vi, 1, vi.shape[1]
+
+
+def _c(a, dt=None):
+    return np.ascontiguousarray(a if dt is None else a.astype(dt, copy=False))
+
+
+I64 = ctypes.c_int64
+
+
+def rasterize(v, vi, H, W, mode=0, with_margin=False):
+    """-> (depth_img f32 [N,H,W], index_img i32 [N,H,W][, margin u32 [N,H,W]])."""
+    v = _c(v)
+    N, V, _ = v.shape
+    vi, vb, F = _prep_vi(vi, N)
+    depth = np.empty((N, H, W), np.float32)
+    index = np.empty((N, H, W), np.int32)
+    margin = np.empty((N, H, W), np.uint32) if with_margin else None
+    fn = getattr(lib(), "oracle_rasterize" + _sfx(v.dtype))
+    fn(_p(v), _p(vi), I64(N), I64(V), I64(F), I64(H), I64(W), ctypes.c_int(vb), ctypes.c_int(mode),
+       _p(depth), _p(index), _p(margin))
+    return (depth, index, margin) if with_margin else (depth, index)
+
+
+def render_fwd(v, vi, index_img):
+    v = _c(v)
+    N, V, _ = v.shape
+    vi, vb, F = _prep_vi(vi, N)
+    index_img = _c(index_img, np.int32)
+    _, H, W = index_img.shape
+    depth = np.empty((N, H, W), v.dtype)
+    bary = np.empty((N, 3, H, W), v.dtype)
+    fn = getattr(lib(), "oracle_render_fwd" + _sfx(v.dtype))
+    fn(_p(v), _p(vi), _p(index_img), I64(N), I64(V), I64(F), I64(H), I64(W), ctypes.c_int(vb),
+       _p(depth), _p(bary))
+    return depth, bary
+
+
+def render_bwd(v, vi, index_img, grad_depth, grad_bary):
+    v = _c(v)
+    N, V, _ = v.shape
+    vi, vb, F = _prep_vi(vi, N)
+    index_img = _c(index_img, np.int32)
+    _, H, W = index_img.shape
+    gd = None if grad_depth is None else _c(grad_depth, v.dtype)
+    gb = None if grad_bary is None else _c(grad_bary, v.dtype)
+    grad_v = np.empty((N, V, 3), v.dtype)
+    fn = getattr(lib(), "oracle_render_bwd" + _sfx(v.dtype))
+    fn(_p(v), _p(vi), _p(index_img), _p(gd), _p(gb), I64(N), I64(V), I64(F), I64(H), I64(W),
+       ctypes.c_int(vb), _p(grad_v))
+    return grad_v
+
+
+def interpolate_fwd(attr, vi, index_img, bary_img):
+    attr = _c(attr)
+    N, V, C = attr.shape
+    vi, vb, F = _prep_vi(vi, N)
+    index_img = _c(index_img, np.int32)
+    bary_img = _c(bary_img, attr.dtype)
+    _, H, W = index_img.shape
+    out = np.empty((N, C, H, W), attr.dtype)
+    fn = getattr(lib(), "oracle_interpolate_fwd" + _sfx(attr.dtype))
+    fn(_p(attr), _p(vi), _p(index_img), _p(bary_img), I64(N), I64(V), I64(F), I64(C), I64(H), I64(W),
+       ctypes.c_int(vb), _p(out))
+    return out
+
+
+def interpolate_bwd(grad_out, attr, vi, index_img, bary_img, need_attr=True, need_bary=True):
+    attr = _c(attr)
+    N, V, C = attr.shape
+    vi, vb, F = _prep_vi(vi, N)
+    index_img = _c(index_img, np.int32)
+    bary_img = _c(bary_img, attr.dtype)
+    grad_out = _c(grad_out, attr.dtype)
+    _, H, W = index_img.shape
+    ga = np.empty((N, V, C), attr.dtype) if need_attr else None
+    gb = np.empty((N, 3, H, W), attr.dtype) if need_bary else None
+    fn = getattr(lib(), "oracle_interpolate_bwd" + _sfx(attr.dtype))
+    fn(_p(grad_out), _p(attr), _p(vi), _p(index_img), _p(bary_img), I64(N), I64(V), I64(F), I64(C),
+       I64(H), I64(W), ctypes.c_int(vb), _p(ga), _p(gb))
+    return ga, gb
+
+
+def edge_grad_bwd(v_pix, img, index_img, vi, grad_output, max_dp_dr=1e4):
+    v_pix = _c(v_pix)
+    N, V, _ = v_pix.shape
+    vi, vb, F = _prep_vi(vi, N)
+    index_img = _c(index_img, np.int32)
+    img = _c(img, v_pix.dtype)
+    grad_output = _c(grad_output, v_pix.dtype)
+    _, C, H, W = img.shape
+    out = np.empty((N, 3, H, W), v_pix.dtype)
+    real = ctypes.c_float if v_pix.dtype == np.float32 else ctypes.c_double
+    fn = getattr(lib(), "oracle_edge_grad_bwd" + _sfx(v_pix.dtype))
+    fn(_p(v_pix), _p(img), _p(index_img), _p(vi), _p(grad_output), I64(N), I64(V), I64(F), I64(C),
+       I64(H), I64(W), ctypes.c_int(vb), real(max_dp_dr), _p(out))
+    return out
