@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- the DRTK rasterisation hot path on B200: Mpixels/s, forward + backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl new|reference] [--config 4]
+
+One step = one pass of the hot path over one batch of synthetic input (BASELINE.json):
+
+    index = rasterize(v_pix, vi, H, W); depth, bary = render(v_pix, vi, index)
+    img = interpolate(attr, vi, index, bary); img = edge_grad_estimator(v_pix, vi, bary, img, index)
+    loss = (img * w).sum(); loss.backward()          # v_pix and attr require grad
+
+Default workload: BASELINE config 4 -- 100 352 triangles, 2048x2048, batch 8, 16 vertex
+attributes (the configuration the metric is quoted on).  Prints ONE JSON line (rank 0).
+
+  value          whole-job Mpix/s with inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e            same metric through the public API with HOST (pinned) inputs: every step copies
+                 v_pix / attr / vi to the device and reads loss + both gradients back
+  roofline       the dominant kernel of the step: algorithmic bytes / its event-timed duration,
+                 against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline   the reference's own CPU kernels (oracle/_ref, built from the unmodified reference
+                 sources) on a bounded sample of the same workload, on the host cores of the box
+  --impl reference   times that CPU implementation as its own arm (rank 0 only under torchrun)
+
+N > 1 (torchrun, one process per GPU, NCCL): the batch is sharded -- every rank runs the same
+per-GPU workload on its own items (weak scaling, no data-path collective) and the gradients of the
+shared mesh / attribute table are summed over the local batch and all-reduced once per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch as th
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from drtk_b200 import scenes  # noqa: E402
+
+METRIC = "Mpixels/s fwd+bwd (rasterize+render+interpolate+edge_grad), 100k-tri@2048^2 b8"
+C_ATTR = 16
+
+# algorithmic (compulsory) HBM bytes per pixel of each of OUR ops at fp32, C = attribute channels;
+# vertex / index tables are L2 resident and excluded (DESIGN.md "Kernels")
+ALGO_BYTES_PER_PX = {
+    "rasterize": lambda C: 8,                       # index + depth written
+    "render_fwd": lambda C: 20,                     # index read; depth + 3 bary written
+    "interpolate_fwd": lambda C: 16 + 4 * C,        # index + bary read; C planes written
+    "edge_grad_bwd": lambda C: 4 + 8 * C + 12,      # index, img, grad_out read; 3 planes written
+    "interpolate_bwd_vpix": lambda C: 16 + 12,      # C=3 conduit: index + bary + 3 grad planes read
+    "interpolate_bwd": lambda C: 16 + 4 * C + 12,   # index + bary + C grad planes read; bary grad written
+    "render_bwd": lambda C: 4 + 12,                 # index + grad_bary read (grad_depth undefined here)
+}
+# CUDA kernels launched by libdrtk_b200.so per op call (memsets are driver operations, not counted)
+KERNELS = {"rasterize": 4, "render_fwd": 1, "interpolate_fwd": 1, "edge_grad_bwd": 1,
+           "interpolate_bwd_vpix": 1, "interpolate_bwd": 1, "render_bwd": 1}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(cfg, device, seed_offset=0):
+    c = scenes.CONFIGS[cfg]
+    v, vi = scenes.grid_mesh(c["nx"], c["ny"], c["H"], c["W"], c["N"], seed=1000 * cfg + seed_offset)
+    attr = scenes.vertex_attributes(c["N"], v.shape[1], C_ATTR, seed=1000 * cfg + 1 + seed_offset)
+    return v, vi, attr, c
+
+
+def pipeline(api, v_pix, vi, attr, w, H, W):
+    index = api.rasterize(v_pix, vi, H, W)
+    _, bary = api.render(v_pix, vi, index)
+    img = api.interpolate(attr, vi, index, bary)
+    img = api.edge_grad_estimator(v_pix, vi, bary, img, index)
+    loss = (img * w).sum()
+    loss.backward()
+    return loss
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference_cpu(cfg, steps, warmup, sample_items=1):
+    """The reference's CPU implementation of the path (oracle/_ref when present, else the oracle
+    port) on a bounded sample: `sample_items` batch items of the workload per step."""
+    c = scenes.CONFIGS[cfg]
+    v, vi = scenes.grid_mesh(c["nx"], c["ny"], c["H"], c["W"], sample_items, seed=1000 * cfg)
+    attr = scenes.vertex_attributes(sample_items, v.shape[1], C_ATTR, seed=1000 * cfg + 1)
+    w = th.rand((sample_items, C_ATTR, c["H"], c["W"]), generator=th.Generator().manual_seed(1000 * cfg + 2))
+    from oracle import ref as R
+    kind = "reference" if R.available() else "port"
+    cores = th.get_num_threads()
+    if kind == "reference":
+        def step():
+            vv, aa = v.clone().requires_grad_(True), attr.clone().requires_grad_(True)
+            pipeline(R, vv, vi, aa, w, c["H"], c["W"])
+    else:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        vn, vin, an, wn = v.numpy(), vi.numpy(), attr.numpy(), w.numpy()
+
+        def step():
+            _, idx = O.rasterize(vn, vin, c["H"], c["W"], mode=0)
+            _, bary = O.render_fwd(vn, vin, idx)
+            img = O.interpolate_fwd(an, vin, idx, bary)
+            gpix = O.edge_grad_bwd(vn, img, idx, vin, wn, 1e4)
+            O.interpolate_bwd(gpix, vn, vin, idx, bary, True, False)
+            _, gb = O.interpolate_bwd(wn, an, vin, idx, bary, True, True)
+            O.render_bwd(vn, vin, idx, None, gb)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    px = sample_items * c["H"] * c["W"]
+    return {"value": px / dt / 1e6, "unit": "Mpix/s", "cores": cores, "kind": kind,
+            "sample": f"{sample_items} of {c['N']} batch items of config {cfg} per step ({px / 1e6:.2f} Mpix), {steps} steps, {warmup} warm-up",
+            "ms_per_step": dt * 1e3}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="new", choices=["new", "reference"])
+    ap.add_argument("--config", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = args.config
+    c = scenes.CONFIGS[cfg]
+    workload = (f"BASELINE config {cfg}: {2 * (c['nx'] - 1) * (c['ny'] - 1)} triangles, {c['W']}x{c['H']}, "
+                f"batch {c['N']} per GPU, {C_ATTR} vertex attributes + edge_grad, synthetic jittered grid mesh")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = run_reference_cpu(cfg, max(args.steps, 1), args.warmup)
+        line = {"metric": METRIC, "value": r["value"], "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+                "config": {"workload": workload, "note": "reference CPU kernels on the host cores, bounded sample"},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    assert th.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    th.cuda.set_device(local_rank)
+    dev = th.device("cuda", local_rank)
+    import drtk_b200
+    from drtk_b200 import _ops
+    from drtk_b200 import dist as ddist
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- inputs: pinned host copies (e2e) and device-resident copies (value) ----
+    v_h, vi_h, attr_h, _ = make_inputs(cfg, dev, seed_offset=100 * rank)
+    v_h, vi_h, attr_h = v_h.pin_memory(), vi_h.pin_memory(), attr_h.pin_memory()
+    H, W, N = c["H"], c["W"], c["N"]
+    npx_rank = N * H * W
+    v_d = v_h.to(dev).requires_grad_(True)
+    attr_d = attr_h.to(dev).requires_grad_(True)
+    vi_d = vi_h.to(dev)
+    w = th.rand((N, C_ATTR, H, W), device=dev, generator=th.Generator(device=dev).manual_seed(1000 * cfg + 2))
+
+    # per-op CUDA-event timing hooks (events on the launching stream, inside the timed region)
+    op_events = {k: [] for k in KERNELS}
+    orig = {}
+
+    def wrap(name, key_fn):
+        fn = getattr(_ops, name)
+        orig[name] = fn
+
+        def timed(*a, **kw):
+            key = key_fn(*a, **kw)
+            e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **kw)
+            e1.record()
+            if timing_on[0]:
+                op_events[key].append((e0, e1))
+            return out
+        setattr(_ops, name, timed)
+
+    timing_on = [False]
+    wrap("rasterize", lambda *a, **k: "rasterize")
+    wrap("render_forward", lambda *a, **k: "render_fwd")
+    wrap("render_backward", lambda *a, **k: "render_bwd")
+    wrap("interpolate_forward", lambda *a, **k: "interpolate_fwd")
+    wrap("interpolate_backward", lambda g, attr, *a, **k: "interpolate_bwd_vpix" if attr.shape[2] == 3 else "interpolate_bwd")
+    wrap("edge_grad_backward", lambda *a, **k: "edge_grad_bwd")
+
+    def step_device():
+        v_d.grad = None
+        attr_d.grad = None
+        loss = pipeline(drtk_b200, v_d, vi_d, attr_d, w, H, W)
+        if world > 1:  # shared-parameter gradient exchange: one bucketed NCCL all-reduce
+            ddist.allreduce_shared_grads([v_d.grad, attr_d.grad])
+        return loss
+
+    loss_h = th.empty((), dtype=th.float32).pin_memory()
+    gv_h = th.empty_like(v_h).pin_memory()
+    ga_h = th.empty_like(attr_h).pin_memory()
+    h2d = v_h.numel() * 4 + attr_h.numel() * 4 + vi_h.numel() * 4
+    d2h = 4 + gv_h.numel() * 4 + ga_h.numel() * 4
+
+    def step_e2e():
+        v = v_h.to(dev, non_blocking=True).requires_grad_(True)
+        a = attr_h.to(dev, non_blocking=True).requires_grad_(True)
+        vi = vi_h.to(dev, non_blocking=True)
+        loss = pipeline(drtk_b200, v, vi, a, w, H, W)
+        gv, ga = v.grad, a.grad
+        if world > 1:
+            (gvs, gas), _ = ddist.allreduce_shared_grads([gv, ga])
+        loss_h.copy_(loss.detach(), non_blocking=True)
+        gv_h.copy_(gv, non_blocking=True)
+        ga_h.copy_(ga, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        th.cuda.synchronize()
+
+    def timed_region(step_fn, steps):
+        barrier()
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step_fn()
+        e1.record()
+        barrier()
+        ms = th.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    timing_on[0] = True
+    ms_step = timed_region(step_device, args.steps)
+    timing_on[0] = False
+    clocks = sampler.stop() if sampler else None
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed_region(step_e2e, args.steps)
+
+    total_px = npx_rank * world
+    value = total_px / (ms_step * 1e-3) / 1e6
+    e2e_value = total_px / (ms_e2e * 1e-3) / 1e6
+
+    # ---- per-op breakdown and the roofline of the dominant kernel (rank 0) ----
+    per_op = {}
+    for k, evs in op_events.items():
+        if evs:
+            per_op[k] = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    peak, peak_src = load_peaks()
+    roofline, breakdown = None, {}
+    if per_op:
+        for k, ms in per_op.items():
+            gb = ALGO_BYTES_PER_PX[k](C_ATTR) * npx_rank / 1e9
+            breakdown[k] = {"ms": round(ms, 4), "algo_GB": round(gb, 4), "GBps": round(gb / (ms * 1e-3), 1),
+                            "frac_of_peak": round(gb / (ms * 1e-3) / peak, 4)}
+        dom = max(per_op, key=per_op.get)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(dom)
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": breakdown[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": breakdown[dom]["frac_of_peak"], "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX[dom](C_ATTR) * npx_rank}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "new",
+        "config": {"workload": workload, "global_batch": N * world, "parallelism": f"dp{world} (batch sharded, shared-grad allreduce)",
+                   "l2": "per-step working set ~10 GB >> 126 MB L2 (inputs larger than L2, no explicit flush)",
+                   "loss": "(img * w).sum() in torch, inside the timed step"},
+        "e2e": {"value": e2e_value, "unit": "Mpix/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "pinned host v_pix/attr/vi copied in, loss + grad_v + grad_attr copied out, every step"},
+        "gpu_launches": sum(KERNELS.values()) * args.steps,
+        "clocks": clocks, "roofline": roofline, "per_op": breakdown,
+        "pipeline_algorithmic_GB_per_step": round(sum(ALGO_BYTES_PER_PX[k](C_ATTR) for k in KERNELS) * npx_rank / 1e9, 3),
+    }
+
+    # ---- reference CUDA kernels on the same tensors (context for the >=4x target; not the arm) ----
+    if world == 1 and not args.no_ref_cuda:
+        try:
+            from oracle import ref as R
+            if R.available():
+                def step_ref():
+                    v_d.grad = None; attr_d.grad = None
+                    pipeline(R, v_d, vi_d, attr_d, w, H, W)
+                for _ in range(3):
+                    step_ref()
+                ms_ref = timed_region(step_ref, args.steps)
+                line["reference_cuda"] = {"value": total_px / (ms_ref * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": ms_ref,
+                                          "note": "unmodified reference CUDA kernels (oracle/_ref, sm_100 build), same tensors, same loss"}
+        except Exception as ex:  # noqa: BLE001
+            line["reference_cuda"] = {"unavailable": repr(ex)[:200]}
+
+    if world == 1 and not args.no_cpu_baseline:
+        r = run_reference_cpu(cfg, steps=3, warmup=1)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,58 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/drtk_b200.h declares.
+No compute calls (no GPU here) -- only loading, symbol resolution and argument-error paths."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from tests.util import ROOT
+
+HEADER = os.path.join(ROOT, "include", "drtk_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(drtk_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_path():
+    names = declared_functions()
+    for need in ("drtk_b200_rasterize", "drtk_b200_render_forward", "drtk_b200_render_backward",
+                 "drtk_b200_interpolate_forward", "drtk_b200_interpolate_backward",
+                 "drtk_b200_edge_grad_backward"):
+        assert need in names
+
+
+def test_library_exports_every_declared_symbol():
+    import drtk_b200
+    from drtk_b200 import _lib
+    path = drtk_b200.native_library_path()
+    assert os.path.exists(path), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(path)
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/drtk_b200.h but not exported"
+        assert name in _lib.PROTOTYPES, f"{name} has no ctypes prototype in drtk_b200/_lib.py"
+    assert set(_lib.PROTOTYPES) == set(declared_functions())
+
+
+def test_abi_version_and_error_strings():
+    from drtk_b200 import _lib
+    lib = _lib.load()
+    assert lib.drtk_b200_abi_version() == 1
+    assert b"workspace" in lib.drtk_b200_error_string(-2)
+    assert lib.drtk_b200_error_string(0) == b"success"
+    assert lib.drtk_b200_rasterize_workspace_bytes(8, 100352, 2048, 2048, 0) > 4 * 8 * 100352 * 4
+    assert lib.drtk_b200_rasterize_workspace_bytes(1, 10, 64, 64, 1) >= 64 * 64 * 8
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    from drtk_b200 import _lib
+    lib = _lib.load()
+    s3 = (ctypes.c_int64 * 3)(0, 3, 1)
+    # wireframe is declared unsupported; negative sizes are invalid; both return before any CUDA call
+    assert lib.drtk_b200_rasterize(None, s3, None, s3, 1, 1, 1, 8, 8, 1, 0, None, None, None, 0, None) == -3
+    assert lib.drtk_b200_rasterize(None, s3, None, s3, 1, 1, 1, -8, 8, 0, 0, None, None, None, 0, None) == -1
+    # empty problems are a successful no-op
+    assert lib.drtk_b200_render_forward(None, s3, None, s3, None, s3, 0, 0, 0, 0, 0, None, None, None) == 0

@@ -1,0 +1,42 @@
+"""CPU suite: the N>1 path (batch sharding + shared-gradient all-reduce) with world_size 2 on gloo."""
+import os
+import socket
+
+import torch as th
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_global, V, C, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from drtk_b200 import dist as ddist
+    gen = th.Generator().manual_seed(1234)
+    gv_all = th.randn(n_global, V, 3, generator=gen)      # per-item gradients of the whole job
+    ga_all = th.randn(n_global, V, C, generator=gen)
+    b, e = ddist.shard_batch(n_global, rank, world)
+    (gv, ga), work = ddist.allreduce_shared_grads([gv_all[b:e], ga_all[b:e]], async_op=True)
+    work.wait()
+    th.save((gv, ga), os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_shared_gradient_allreduce(tmp_path):
+    world, n_global, V, C = 2, 5, 17, 4
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_global, V, C, str(tmp_path)), nprocs=world, join=True)
+    gen = th.Generator().manual_seed(1234)
+    gv_all = th.randn(n_global, V, 3, generator=gen)
+    ga_all = th.randn(n_global, V, C, generator=gen)
+    for r in range(world):
+        gv, ga = th.load(os.path.join(str(tmp_path), f"r{r}.pt"))
+        assert th.allclose(gv, gv_all.sum(0), atol=1e-5)
+        assert th.allclose(ga, ga_all.sum(0), atol=1e-5)
