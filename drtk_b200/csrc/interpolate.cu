@@ -16,6 +16,7 @@
 //                (red.global.add.v4.f32) -- no shared memory, no block barriers (the reference
 //                needs one barrier and up to three scalar atomics per channel per run).
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace drtk {
 namespace {
@@ -238,6 +239,234 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(InterpBwdArgs b, float*
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// backward, tiled (the fast path): bulk-async staged tiles + register run-reduction
+// ------------------------------------------------------------------------------------------
+// A CTA owns a 128 x 8 pixel tile.  One warp issues cp.async.bulk row copies (TMA engine, SASS
+// UBLKCP) that land the tile's grad_out planes (up to LPW channels per pass), bary planes and
+// index row segments in shared memory and complete on an mbarrier; nobody spends LSU
+// instructions or registers on the 16+4C B/px stream.  Then
+//   phase A (vertex grads): "walkers" of LPW lanes -- lane = channel -- walk a row segment in
+//     4-pixel steps (one conflict-free LDS.128 of their own channel plane, broadcast LDS.128 of
+//     index/bary), accumulate g*bary_k for the current triangle run in three registers and, when
+//     the triangle id changes, flush the run with three reductions whose LPW lanes hit LPW
+//     consecutive floats of one vertex row (a single coalesced 64-B RED per vertex at C=16).
+//     No shuffles, no shared-memory atomics, one reduction per (run, vertex) instead of per pixel.
+//   phase B (bary grads): lane = pixel quad; dot products of the staged gradients with the three
+//     attribute rows, accumulated across channel passes in registers, 128-bit streaming stores.
+constexpr int kTW = 128, kTH = 8, kTP = kTW * kTH;
+constexpr int kBwdThreads = 256;
+
+template <int LPW>
+struct BwdTileSmem {
+  static constexpr int PITCH = kTP + 4;  // plane pitch == 4 (mod 32) words: LDS.128 by LPW lanes of
+                                         // consecutive planes is bank-conflict free
+  float g[LPW * PITCH];
+  float bary[3 * kTP];
+  int idx[kTP];
+  unsigned long long bar;
+};
+
+template <int LPW, bool NEED_VERT, bool NEED_BARY, bool AVEC>
+__global__ void __launch_bounds__(kBwdThreads, 2)
+interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __restrict__ bary_grad,
+                       int tilesX, int tilesY, int64_t num_tiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BwdTileSmem<LPW>& S = *reinterpret_cast<BwdTileSmem<LPW>*>(smem_raw);
+  constexpr int PITCH = BwdTileSmem<LPW>::PITCH;
+  const InterpArgs& a = b.f;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t HW = (int64_t)a.H * a.W;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(&S.bar);
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  uint32_t phase = 0;
+  const int nchunks = (a.C + LPW - 1) / LPW;
+
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int tpi = tilesX * tilesY;
+    const int n = (int)(tile / tpi);
+    const int tl = (int)(tile - (int64_t)n * tpi);
+    const int ty = tl / tilesX, tx = tl - ty * tilesX;
+    const int x0 = tx * kTW, y0 = ty * kTH;
+    const int tw = min(kTW, a.W - x0), th = min(kTH, a.H - y0);
+    const uint32_t row_bytes = (uint32_t)tw * 4u;
+
+    // phase-B ownership: thread -> pixel quad (row qr, columns qx..qx+3)
+    const int qr = tid >> 5, qx = (tid & 31) << 2;
+    const bool q_in = NEED_BARY && qr < th && qx < tw;
+    float gb[4][3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gb[j][0] = gb[j][1] = gb[j][2] = 0.f;
+    int qid[4] = {-1, -1, -1, -1};
+    int qv[4][3];
+
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+      const int c0 = chunk * LPW;
+      const int nc = min(LPW, a.C - c0);
+      // ---- stage the tile: warp 0 issues the bulk copies ----
+      if (tid < 32) {
+        const int extra_planes = (chunk == 0) ? ((NEED_VERT ? 3 : 0) + 1) : 0;
+        const int items = (nc + extra_planes) * th;
+        if (lane == 0) {
+          fence_proxy_async_smem();
+          mbar_arrive_expect_tx(bar, (uint32_t)items * row_bytes);
+        }
+        __syncwarp();
+        for (int i = lane; i < items; i += 32) {
+          const int pl = i / th, r = i - pl * th;
+          const void* src;
+          void* dst;
+          if (pl < nc) {
+            src = b.grad_out + (int64_t)n * b.gs.s0 + (int64_t)(c0 + pl) * b.gs.s1 + (int64_t)(y0 + r) * b.gs.s2 + x0;
+            dst = S.g + pl * PITCH + r * kTW;
+          } else if (NEED_VERT && pl < nc + 3) {
+            const int k = pl - nc;
+            src = a.bary + (int64_t)n * a.bs.s0 + (int64_t)k * a.bs.s1 + (int64_t)(y0 + r) * a.bs.s2 + x0;
+            dst = S.bary + k * kTP + r * kTW;
+          } else {
+            src = a.index_img + (int64_t)n * a.is.s0 + (int64_t)(y0 + r) * a.is.s1 + x0;
+            dst = S.idx + r * kTW;
+          }
+          bulk_g2s(dst, src, row_bytes, bar);
+        }
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+
+      // ---- phase A: vertex-attribute gradients ----
+      if (NEED_VERT) {
+        constexpr int WALKERS = kBwdThreads / LPW;
+        constexpr int SEGS = WALKERS / kTH;  // walkers per tile row
+        constexpr int SEG = kTW / SEGS;      // pixels per walker
+        const int walker = tid / LPW, c = tid - walker * LPW;
+        const int row = walker / SEGS, seg = walker - row * SEGS;
+        if (row < th) {
+          const bool c_on = c < nc;
+          const float* gp = S.g + (c_on ? c : 0) * PITCH + row * kTW;
+          const int* ip = S.idx + row * kTW;
+          const float* b0p = S.bary + row * kTW;
+          const float* b1p = b0p + kTP;
+          const float* b2p = b1p + kTP;
+          float* vg = vert_grad + (int64_t)n * a.V * a.C + c0 + c;
+          const int32_t* vib = a.vi + (int64_t)n * a.vis.s0;
+          const int xe = min(seg * SEG + SEG, tw);
+          int cur = -1, v0 = 0, v1 = 0, v2 = 0;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+          for (int x = seg * SEG; x < xe; x += 4) {
+            const float4 gq = *reinterpret_cast<const float4*>(gp + x);
+            const int4 iq = *reinterpret_cast<const int4*>(ip + x);
+            const float4 p0 = *reinterpret_cast<const float4*>(b0p + x);
+            const float4 p1 = *reinterpret_cast<const float4*>(b1p + x);
+            const float4 p2 = *reinterpret_cast<const float4*>(b2p + x);
+            const int ids[4] = {iq.x, iq.y, iq.z, iq.w};
+            const float gs[4] = {gq.x, gq.y, gq.z, gq.w};
+            const float q0[4] = {p0.x, p0.y, p0.z, p0.w};
+            const float q1[4] = {p1.x, p1.y, p1.z, p1.w};
+            const float q2[4] = {p2.x, p2.y, p2.z, p2.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int id = ids[j];
+              if (id != cur) {  // uniform across the walker's lanes
+                if (cur >= 0 && c_on) {
+                  red_add(vg + (int64_t)v0 * a.C, a0);
+                  red_add(vg + (int64_t)v1 * a.C, a1);
+                  red_add(vg + (int64_t)v2 * a.C, a2);
+                }
+                a0 = a1 = a2 = 0.f;
+                cur = id;
+                if (id >= 0) {
+                  const int32_t* vip = vib + (int64_t)id * a.vis.s1;
+                  v0 = vip[0]; v1 = vip[a.vis.s2]; v2 = vip[2 * a.vis.s2];
+                }
+              }
+              if (id >= 0) {
+                a0 = fmaf(gs[j], q0[j], a0);
+                a1 = fmaf(gs[j], q1[j], a1);
+                a2 = fmaf(gs[j], q2[j], a2);
+              }
+            }
+          }
+          if (cur >= 0 && c_on) {
+            red_add(vg + (int64_t)v0 * a.C, a0);
+            red_add(vg + (int64_t)v1 * a.C, a1);
+            red_add(vg + (int64_t)v2 * a.C, a2);
+          }
+        }
+      }
+
+      // ---- phase B: barycentric gradients (partial over this channel pass) ----
+      if (q_in) {
+        if (chunk == 0) {
+          const int4 iq = *reinterpret_cast<const int4*>(S.idx + qr * kTW + qx);
+          qid[0] = iq.x; qid[1] = iq.y; qid[2] = iq.z; qid[3] = iq.w;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            qv[j][0] = qv[j][1] = qv[j][2] = 0;
+            if (qid[j] >= 0) {
+              if (j > 0 && qid[j] == qid[j - 1]) {
+                qv[j][0] = qv[j - 1][0]; qv[j][1] = qv[j - 1][1]; qv[j][2] = qv[j - 1][2];
+              } else {
+                load_vi(a, n, qid[j], qv[j][0], qv[j][1], qv[j][2]);
+              }
+            }
+          }
+        }
+        const float* an = a.attr + (int64_t)n * a.as.s0;
+        const float* gq_base = S.g + qr * kTW + qx;
+        if (AVEC) {
+          for (int cc = 0; cc < nc; cc += 4) {
+            float4 gq[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gq[k] = *reinterpret_cast<const float4*>(gq_base + (cc + k) * PITCH);
+            float4 A0, A1, A2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (qid[j] < 0) continue;
+              if (!(j > 0 && qid[j] == qid[j - 1])) {
+                A0 = *reinterpret_cast<const float4*>(an + (int64_t)qv[j][0] * a.as.s1 + c0 + cc);
+                A1 = *reinterpret_cast<const float4*>(an + (int64_t)qv[j][1] * a.as.s1 + c0 + cc);
+                A2 = *reinterpret_cast<const float4*>(an + (int64_t)qv[j][2] * a.as.s1 + c0 + cc);
+              }
+              const float g0 = j == 0 ? gq[0].x : j == 1 ? gq[0].y : j == 2 ? gq[0].z : gq[0].w;
+              const float g1 = j == 0 ? gq[1].x : j == 1 ? gq[1].y : j == 2 ? gq[1].z : gq[1].w;
+              const float g2 = j == 0 ? gq[2].x : j == 1 ? gq[2].y : j == 2 ? gq[2].z : gq[2].w;
+              const float g3 = j == 0 ? gq[3].x : j == 1 ? gq[3].y : j == 2 ? gq[3].z : gq[3].w;
+              gb[j][0] += g0 * A0.x + g1 * A0.y + g2 * A0.z + g3 * A0.w;
+              gb[j][1] += g0 * A1.x + g1 * A1.y + g2 * A1.z + g3 * A1.w;
+              gb[j][2] += g0 * A2.x + g1 * A2.y + g2 * A2.z + g3 * A2.w;
+            }
+          }
+        } else {
+          for (int cc = 0; cc < nc; ++cc) {
+            const float4 gq = *reinterpret_cast<const float4*>(gq_base + cc * PITCH);
+            const float gs[4] = {gq.x, gq.y, gq.z, gq.w};
+            float A0 = 0.f, A1 = 0.f, A2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (qid[j] < 0) continue;
+              if (!(j > 0 && qid[j] == qid[j - 1])) {
+                A0 = an[(int64_t)qv[j][0] * a.as.s1 + (int64_t)(c0 + cc) * a.as.s2];
+                A1 = an[(int64_t)qv[j][1] * a.as.s1 + (int64_t)(c0 + cc) * a.as.s2];
+                A2 = an[(int64_t)qv[j][2] * a.as.s1 + (int64_t)(c0 + cc) * a.as.s2];
+              }
+              gb[j][0] += gs[j] * A0; gb[j][1] += gs[j] * A1; gb[j][2] += gs[j] * A2;
+            }
+          }
+        }
+      }
+      __syncthreads();  // all reads of this pass done before the next bulk copies overwrite the tile
+    }
+    if (q_in) {
+      float* gp = bary_grad + (int64_t)n * 3 * HW + (int64_t)(y0 + qr) * a.W + x0 + qx;
+      stg_stream_f4(gp, make_float4(gb[0][0], gb[1][0], gb[2][0], gb[3][0]));
+      stg_stream_f4(gp + HW, make_float4(gb[0][1], gb[1][1], gb[2][1], gb[3][1]));
+      stg_stream_f4(gp + 2 * HW, make_float4(gb[0][2], gb[1][2], gb[2][2], gb[3][2]));
+    }
+  }
+}
+
 inline unsigned grid_for(int64_t work_items, int threads, int ctas_per_sm) {
   const int64_t need = (work_items + threads - 1) / threads;
   const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
@@ -317,9 +546,51 @@ extern "C" int drtk_b200_interpolate_backward(
                            bary_img, bary_strides, N, V, F, C, H, W);
   if (rc) return rc;
   b.grad_out = grad_out; b.gs = make4(grad_out_strides);
+  const bool nv = vert_attributes_grad != nullptr, nb = bary_img_grad != nullptr;
+
+  // fast path: tiles staged through shared memory by bulk-async copies; needs dense, 16-B aligned rows
+  const bool rows_ok =
+      (W % 4 == 0) && VecOk::image(grad_out, W, b.gs.s3, b.gs.s2, b.gs.s1, b.gs.s0) &&
+      VecOk::image(index_img, W, b.f.is.s2, b.f.is.s1, b.f.is.s0) &&
+      (!nv || VecOk::image(bary_img, W, b.f.bs.s3, b.f.bs.s2, b.f.bs.s1, b.f.bs.s0)) &&
+      (!nb || reinterpret_cast<uintptr_t>(bary_img_grad) % 16 == 0);
+  if (rows_ok) {
+    const bool avec = nb && (C % 4 == 0) && b.f.as.s2 == 1 && (b.f.as.s1 % 4 == 0) && (b.f.as.s0 % 4 == 0) &&
+                      (reinterpret_cast<uintptr_t>(vert_attributes) % 16 == 0);
+    const int tilesX = (int)((W + kTW - 1) / kTW), tilesY = (int)((H + kTH - 1) / kTH);
+    const int64_t num_tiles = N * tilesX * tilesY;
+    int rc2 = 0;
+    auto launch = [&](auto kern, size_t smem) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { rc2 = (int)e; return; }
+      int occ = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBwdThreads, smem);
+      if (e != cudaSuccess || occ < 1) { rc2 = e != cudaSuccess ? (int)e : DRTK_B200_EUNSUPPORTED; return; }
+      const int64_t cap = (int64_t)kNumSMs * occ;
+      const unsigned grid = (unsigned)(num_tiles < cap ? num_tiles : cap);
+      kern<<<grid, kBwdThreads, smem, stream>>>(b, vert_attributes_grad, bary_img_grad, tilesX, tilesY, num_tiles);
+    };
+#define DRTK_BWD_TILE(LPW)                                                                                  \
+    do {                                                                                                    \
+      const size_t smem = sizeof(BwdTileSmem<LPW>) + 128;                                                   \
+      if (nv && nb) { if (avec) launch(interp_bwd_tile_kernel<LPW, true, true, true>, smem);                \
+                      else launch(interp_bwd_tile_kernel<LPW, true, true, false>, smem); }                  \
+      else if (nv) launch(interp_bwd_tile_kernel<LPW, true, false, false>, smem);                           \
+      else { if (avec) launch(interp_bwd_tile_kernel<LPW, false, true, true>, smem);                        \
+             else launch(interp_bwd_tile_kernel<LPW, false, true, false>, smem); }                          \
+    } while (0)
+    if (C <= 4) DRTK_BWD_TILE(4);
+    else if (C <= 8) DRTK_BWD_TILE(8);
+    else DRTK_BWD_TILE(16);
+#undef DRTK_BWD_TILE
+    if (rc2) return rc2;
+    DRTK_CHECK_LAUNCH();
+    return 0;
+  }
+
+  // generic path (arbitrary strides / odd widths): one thread per pixel, segmented shuffle reduction
   const unsigned blocks = (unsigned)((npix + 255) / 256);
   const bool rv4 = (C % 4 == 0) && (reinterpret_cast<uintptr_t>(vert_attributes_grad) % 16 == 0);
-  const bool nv = vert_attributes_grad != nullptr, nb = bary_img_grad != nullptr;
   if (nv && nb) {
     if (rv4) interp_bwd_kernel<true, true, true><<<blocks, 256, 0, stream>>>(b, vert_attributes_grad, bary_img_grad);
     else interp_bwd_kernel<true, true, false><<<blocks, 256, 0, stream>>>(b, vert_attributes_grad, bary_img_grad);

@@ -171,39 +171,57 @@ __global__ void __launch_bounds__(256) bin_kernel(RasterArgs a, int64_t total, u
 }
 
 // exclusive scan of `count[0..M)` into `offset[0..M)`, zeroing `count` so that bin_kernel<true>
-// can reuse it as the per-tile cursor.  One CTA; M is #tiles * N (1e5 .. 1e6 at most).
+// can reuse it as the per-tile cursor.  One CTA of 1024 threads sweeps the array in coalesced
+// slabs of 4096 entries (uint4 per thread) carrying the running total; M is #tiles * N (3e4 at
+// config 4, 1.3e5 at config 5), so a multi-CTA scan would not pay for its extra launch.
 __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* count, uint32_t* offset, int64_t M) {
   __shared__ uint32_t warp_sums[32];
-  const int tid = threadIdx.x;
-  const int64_t chunk = (M + 1023) / 1024;
-  const int64_t b = tid * chunk, e = min(M, b + chunk);
-  uint32_t sum = 0;
-  for (int64_t i = b; i < e; ++i) sum += count[i];
-  // block exclusive scan of `sum`
-  uint32_t inc = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-    if ((tid & 31) >= o) inc += t;
-  }
-  if ((tid & 31) == 31) warp_sums[tid >> 5] = inc;
+  __shared__ uint32_t carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0u;
   __syncthreads();
-  if (tid < 32) {
-    uint32_t w = warp_sums[tid];
+  for (int64_t base = 0; base < M; base += 4096) {
+    const int64_t i = base + (int64_t)tid * 4;
+    uint32_t c[4] = {0u, 0u, 0u, 0u};
+    if (i + 3 < M) {
+      const uint4 q = *reinterpret_cast<const uint4*>(count + i);
+      c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
+    } else {
+      for (int k = 0; k < 4; ++k) if (i + k < M) c[k] = count[i + k];
+    }
+    const uint32_t sum = c[0] + c[1] + c[2] + c[3];
+    uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
-      if (tid >= o) w += t;
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
     }
-    warp_sums[tid] = w;
-  }
-  __syncthreads();
-  uint32_t run = inc - sum + ((tid >> 5) ? warp_sums[(tid >> 5) - 1] : 0u);
-  for (int64_t i = b; i < e; ++i) {
-    const uint32_t c = count[i];
-    offset[i] = run;
-    count[i] = 0u;
-    run += c;
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    uint32_t run = carry + inc - sum + (wid ? warp_sums[wid - 1] : 0u);
+    uint32_t o4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { o4[k] = run; run += c[k]; }
+    if (i + 3 < M) {
+      *reinterpret_cast<uint4*>(offset + i) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      *reinterpret_cast<uint4*>(count + i) = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      for (int k = 0; k < 4; ++k) if (i + k < M) { offset[i + k] = o4[k]; count[i + k] = 0u; }
+    }
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_sums[31];
+    __syncthreads();
   }
 }
 

@@ -241,10 +241,10 @@ def test_interpolate_golden(name):
     assert_close(npy(bary.grad), g["grad_bary"], what="bary_img_grad")
 
 
-@pytest.mark.parametrize("C", [1, 2, 3, 5, 8, 16])
-def test_interpolate_vs_oracle_channels(C):
-    v, vi = scenes.grid_mesh(17, 13, 96, 128, 2, seed=31, overdraw=True)
-    H, W = 96, 128
+@pytest.mark.parametrize("C", [1, 2, 3, 5, 8, 16, 19])
+@pytest.mark.parametrize("H,W", [(96, 128), (70, 260), (61, 97)])  # tiled path (two sizes) / generic path
+def test_interpolate_vs_oracle_channels(C, H, W):
+    v, vi = scenes.grid_mesh(17, 13, H, W, 2, seed=31, overdraw=True)
     _, index = O.rasterize(v.numpy(), vi.numpy(), H, W, mode=1)
     _, bary = O.render_fwd(v.numpy(), vi.numpy(), index)
     attr = scenes.vertex_attributes(2, v.shape[1], C, seed=C)
