@@ -6,11 +6,13 @@
 //
 // The reference is a SCATTER: every pixel (x < W-1, y < H-1) acts as "centre", classifies the
 // (centre,right) and (centre,down) pairs and atomically adds 9 values into a zero-initialised
-// output (12 B/px memset + 9 REDG per pixel, interior pixels included).  Here the same sums are
-// formed as a GATHER: the thread that owns output pixel p evaluates the (at most) four pairs p
-// takes part in -- (p,right), (p,down) as centre and (left,p), (up,p) as neighbour -- and writes
-// its three output values exactly once.  No memset, no atomics, deterministic; pairs whose two
-// pixels show the same triangle (the vast majority) cost two integer compares.
+// output (12 B/px memset + 9 REDG per pixel, interior pixels included), and reads img/grad for
+// every pair that shows two different triangles.  Here a CTA owns a 64x8 output tile: pairs
+// showing different triangles are compacted into a job list, each job is evaluated once by one
+// thread, its contributions go to per-role shared-memory slots (single writer each) and every
+// pixel sums its slots and writes its three outputs exactly once.  No memset, no atomics,
+// deterministic; img/grad_output are read only for pairs that actually contribute (adjacent
+// triangles of a watertight mesh -- the bulk of all pairs -- do not).
 //
 // The discrete inside/outside tests use the reference's compiled arithmetic
 // (x*y - z*w  ==  FFMA(x, y, -FMUL(z, w)), FTZ) so that classification agrees sample for sample.
@@ -124,12 +126,11 @@ __device__ __forceinline__ float grad_dot(const EdgeArgs& a, int n, int xc, int 
   return acc;
 }
 
-// Contribution of the pair (centre=(xc,yc) showing triangle ci, neighbour=(xn,yn) showing ni) to
-// ONE of its two pixels.  axis: 0 = horizontal pair (x gradient), 1 = vertical pair (y gradient).
-// want_centre selects which side's (axis, z) contribution is returned.
-__device__ __forceinline__ float2 pair_term(const EdgeArgs& a, int n, int ci, int ni, int xc, int yc,
-                                            int xn, int yn, int axis, bool want_centre) {
-  if (ci == ni) return make_float2(0.f, 0.f);  // lr_diff / ud_diff false (:304-306)
+// Both sides of the pair (centre=(xc,yc) showing triangle ci, neighbour=(xn,yn) showing ni != ci).
+// axis: 0 = horizontal pair (x gradient), 1 = vertical pair (y gradient).
+// Returns (centre.axis, centre.z, neighbour.axis, neighbour.z) before the final negation.
+__device__ __forceinline__ float4 pair_eval(const EdgeArgs& a, int n, int ci, int ni, int xc, int yc,
+                                            int xn, int yn, int axis) {
   const bool cv = ci >= 0, nv = ni >= 0;      // (:290-292)
   bool c_in_n = false, n_in_c = false;
   Tri2 tc, tn;
@@ -139,58 +140,121 @@ __device__ __forceinline__ float2 pair_term(const EdgeArgs& a, int n, int ci, in
     c_in_n = pix_in_tri(tn, xc, yc);
     n_in_c = pix_in_tri(tc, xn, yn);
   }
-  const bool inter = c_in_n && n_in_c;                    // (:334-335)
-  if (!inter) {
+  if (!(c_in_n && n_in_c)) {                               // no intersection (:391-393, :408-410)
     const bool adj = cv && nv && !c_in_n && !n_in_c;      // (:338-341)
     const bool c_over = c_in_n && !n_in_c;                // l_over_r / u_over_d (:328-331)
     const bool n_over = n_in_c && !c_in_n;                // r_over_l / d_over_u
-    const bool zero = want_centre ? (!cv || n_over || adj) : (!nv || c_over || adj);  // (:392-393, :409-410)
-    if (zero) return make_float2(0.f, 0.f);
-    return make_float2(grad_dot(a, n, xc, yc, xn, yn), 0.f);
+    const bool c_zero = !cv || n_over || adj, n_zero = !nv || c_over || adj;
+    if (c_zero && n_zero) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const float g = grad_dot(a, n, xc, yc, xn, yn);
+    return make_float4(c_zero ? 0.f : g, 0.f, n_zero ? 0.f : g, 0.f);
   }
   // intersection: both triangles valid (:394-406, :411-423)
   const float g = grad_dot(a, n, xc, yc, xn, yn);
   const float3 nc = tri_normal(a, n, tc), nn = tri_normal(a, n, tn);
   const float nca = axis == 0 ? nc.x : nc.y, nna = axis == 0 ? nn.x : nn.y;
-  const float2 d = want_centre ? dp_dr(nca, nc.z, nna, nn.z, a.max_dp_dr)
-                               : dp_dr(nna, nn.z, nca, nc.z, a.max_dp_dr);
-  return make_float2(g * d.x, g * d.y);
+  const float2 dc = dp_dr(nca, nc.z, nna, nn.z, a.max_dp_dr);
+  const float2 dn = dp_dr(nna, nn.z, nca, nc.z, a.max_dp_dr);
+  return make_float4(g * dc.x, g * dc.y, g * dn.x, g * dn.y);
 }
 
-__global__ void __launch_bounds__(256) edge_grad_bwd_kernel(EdgeArgs a, float* __restrict__ out) {
+// One CTA per 64 x 8 output tile.
+//   phase 0: triangle ids of the tile plus a one-pixel ring -> shared memory
+//   phase 1: every (centre, right) / (centre, down) pair that touches the tile and shows two
+//            different triangles becomes a JOB (warp-ballot compaction; ~20 % of the pair slots on
+//            the 100k-triangle config, far fewer on large triangles)
+//   phase 2: one thread per job evaluates the pair ONCE (the scatter form's work, all lanes busy)
+//            and drops the centre / neighbour contributions into per-role slots of the two pixels
+//            (each slot has exactly one writer, so no atomics)
+//   phase 3: every pixel adds its <= 8 slots and writes its three outputs once, coalesced.
+constexpr int kETW = 64, kETH = 8, kEThreads = 256;
+constexpr int kEIW = kETW + 2, kEIH = kETH + 2;                 // id tile with ring
+constexpr int kEHSlots = (kETW + 1) * kETH;                     // horizontal pairs: centres x0-1 .. x0+TW-1
+constexpr int kEVSlots = kETW * (kETH + 1);                     // vertical pairs:   centres y0-1 .. y0+TH-1
+constexpr int kESlots = kEHSlots + kEVSlots;
+
+__global__ void __launch_bounds__(kEThreads, 3) edge_grad_tile_kernel(EdgeArgs a, float* __restrict__ out) {
+  __shared__ int ids[kEIH * kEIW];
+  __shared__ int jobs[kESlots];
+  __shared__ int njobs;
+  __shared__ float slot[8][kETW * kETH];  // 0 cx, 1 czx, 2 cy, 3 czy (centre roles); 4 rx, 5 rz, 6 dy, 7 dz
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n = blockIdx.z;
+  const int x0 = blockIdx.x * kETW, y0 = blockIdx.y * kETH;
+  const int32_t* ip = a.index_img + (int64_t)n * a.is.s0;
+
+  for (int i = tid; i < kEIH * kEIW; i += kEThreads) {
+    const int ly = i / kEIW, lx = i - ly * kEIW;
+    const int x = x0 - 1 + lx, y = y0 - 1 + ly;
+    ids[i] = (x >= 0 && x < a.W && y >= 0 && y < a.H) ? ip[(int64_t)y * a.is.s1 + (int64_t)x * a.is.s2] : -2;
+  }
+  for (int i = tid; i < 8 * kETW * kETH; i += kEThreads) (&slot[0][0])[i] = 0.f;
+  if (tid == 0) njobs = 0;
+  __syncthreads();
+
+  // ---- phase 1: job list ----
+  for (int base = 0; base < kESlots; base += kEThreads) {
+    const int sidx = base + tid;
+    bool has = false;
+    int job = 0;
+    if (sidx < kESlots) {
+      int lx, ly, axis;  // centre in id-tile coordinates
+      if (sidx < kEHSlots) { axis = 0; ly = 1 + sidx / (kETW + 1); lx = sidx % (kETW + 1); }
+      else { const int t = sidx - kEHSlots; axis = 1; ly = t / kETW; lx = 1 + t % kETW; }
+      const int cx = x0 - 1 + lx, cy = y0 - 1 + ly;
+      // only pixels with 0 <= x < W-1 and 0 <= y < H-1 act as centre (:270)
+      if (cx >= 0 && cy >= 0 && cx < a.W - 1 && cy < a.H - 1) {
+        const int ci = ids[ly * kEIW + lx];
+        const int ni = axis == 0 ? ids[ly * kEIW + lx + 1] : ids[(ly + 1) * kEIW + lx];
+        has = ci != ni;
+        job = (axis << 16) | (ly << 8) | lx;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    int wbase = 0;
+    if (lane == 0 && m) wbase = atomicAdd(&njobs, __popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (has) jobs[wbase + __popc(m & ((1u << lane) - 1u))] = job;
+  }
+  __syncthreads();
+
+  // ---- phase 2: evaluate each pair once ----
+  const int nj = njobs;
+  for (int j = tid; j < nj; j += kEThreads) {
+    const int job = jobs[j];
+    const int axis = job >> 16, ly = (job >> 8) & 0xff, lx = job & 0xff;
+    const int cx = x0 - 1 + lx, cy = y0 - 1 + ly;
+    const int nx = cx + (axis == 0), ny = cy + (axis == 1);
+    const int ci = ids[ly * kEIW + lx];
+    const int ni = axis == 0 ? ids[ly * kEIW + lx + 1] : ids[(ly + 1) * kEIW + lx];
+    const float4 r = pair_eval(a, n, ci, ni, cx, cy, nx, ny, axis);
+    // centre pixel inside the tile?
+    if (lx >= 1 && ly >= 1) {
+      const int o = (ly - 1) * kETW + (lx - 1);
+      slot[axis == 0 ? 0 : 2][o] = r.x;
+      slot[axis == 0 ? 1 : 3][o] = r.y;
+    }
+    const int nlx = lx + (axis == 0), nly = ly + (axis == 1);
+    if (nlx <= kETW && nly <= kETH) {  // neighbour pixel inside the tile (it is >= 1 by construction)
+      const int o = (nly - 1) * kETW + (nlx - 1);
+      slot[axis == 0 ? 4 : 6][o] = r.z;
+      slot[axis == 0 ? 5 : 7][o] = r.w;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: combine and store (negated sums, :431-445) ----
   const int64_t HW = (int64_t)a.H * a.W;
-  const int64_t npix = (int64_t)a.N * HW;
-  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
-       pix += (int64_t)gridDim.x * blockDim.x) {
-    const int n = (int)(pix / HW);
-    const int64_t rem = pix - (int64_t)n * HW;
-    const int y = (int)(rem / a.W), x = (int)(rem - (int64_t)y * a.W);
-    const int32_t* ip = a.index_img + (int64_t)n * a.is.s0;
-    const int id = ip[(int64_t)y * a.is.s1 + (int64_t)x * a.is.s2];
-    const bool has_r = x < a.W - 1, has_d = y < a.H - 1, has_l = x > 0, has_u = y > 0;
-    float gx = 0.f, gy = 0.f, gz_c = 0.f, gz_r = 0.f, gz_d = 0.f;
-    // p as centre: only pixels with x < W-1 && y < H-1 act as centre (:270)
-    if (has_r && has_d) {
-      const int ir = ip[(int64_t)y * a.is.s1 + (int64_t)(x + 1) * a.is.s2];
-      const int idn = ip[(int64_t)(y + 1) * a.is.s1 + (int64_t)x * a.is.s2];
-      const float2 tx = pair_term(a, n, id, ir, x, y, x + 1, y, 0, true);
-      const float2 ty = pair_term(a, n, id, idn, x, y, x, y + 1, 1, true);
-      gx += tx.x; gy += ty.x; gz_c = tx.y + ty.y;
-    }
-    // p as right neighbour of (x-1, y): that centre must satisfy y < H-1
-    if (has_l && has_d) {
-      const int il = ip[(int64_t)y * a.is.s1 + (int64_t)(x - 1) * a.is.s2];
-      const float2 t = pair_term(a, n, il, id, x - 1, y, x, y, 0, false);
-      gx += t.x; gz_r = t.y;
-    }
-    // p as down neighbour of (x, y-1): that centre must satisfy x < W-1
-    if (has_u && has_r) {
-      const int iu = ip[(int64_t)(y - 1) * a.is.s1 + (int64_t)x * a.is.s2];
-      const float2 t = pair_term(a, n, iu, id, x, y - 1, x, y, 1, false);
-      gy += t.x; gz_d = t.y;
-    }
-    float* o = out + (int64_t)n * 3 * HW + rem;
-    o[0] = -gx; o[HW] = -gy; o[2 * HW] = -(gz_c + gz_r + gz_d);  // negated sums (:431-445)
+  float* ob = out + (int64_t)n * 3 * HW;
+  for (int i = tid; i < kETW * kETH; i += kEThreads) {
+    const int ly = i / kETW, lx = i - ly * kETW;
+    const int x = x0 + lx, y = y0 + ly;
+    if (x >= a.W || y >= a.H) continue;
+    const float gx = slot[0][i] + slot[4][i];
+    const float gy = slot[2][i] + slot[6][i];
+    const float gz = (slot[1][i] + slot[3][i]) + slot[5][i] + slot[7][i];
+    float* o = ob + (int64_t)y * a.W + x;
+    o[0] = -gx; o[HW] = -gy; o[2 * HW] = -gz;
   }
 }
 
@@ -218,9 +282,10 @@ extern "C" int drtk_b200_edge_grad_backward(const float* v_pix, const int64_t* v
   a.go = grad_output; a.gs = make4(grad_output_strides);
   a.N = (int)N; a.V = (int)V; a.F = (int)F; a.C = (int)C; a.H = (int)H; a.W = (int)W;
   a.max_dp_dr = max_dp_dr;
-  const int64_t need = (npix + 255) / 256;
-  const int64_t cap = (int64_t)kNumSMs * 8 * 8;
-  edge_grad_bwd_kernel<<<(unsigned)(need < cap ? need : cap), 256, 0, stream>>>(a, grad_v_pix_img);
+  if (N > 65535) return DRTK_B200_EUNSUPPORTED;
+  const dim3 grid((unsigned)((W + kETW - 1) / kETW), (unsigned)((H + kETH - 1) / kETH), (unsigned)N);
+  if (grid.y > 65535) return DRTK_B200_EUNSUPPORTED;
+  edge_grad_tile_kernel<<<grid, kEThreads, 0, stream>>>(a, grad_v_pix_img);
   DRTK_CHECK_LAUNCH();
   return 0;
 }

@@ -47,15 +47,12 @@ __device__ __forceinline__ float sweep_x(int w, int W) { return ((float)w * 2.0f
 // AVEC: attribute rows 16-B aligned and C % 4 == 0 (float4 gathers).
 template <bool VEC, bool AVEC>
 __global__ void __launch_bounds__(256) interp_fwd_kernel(InterpArgs a, float* __restrict__ out) {
-  const int64_t HW = (int64_t)a.H * a.W;
+  const int HW = a.H * a.W;  // blockIdx.y = image, 32-bit pixel arithmetic inside it
   constexpr int PX = VEC ? 4 : 1;
-  const int64_t ngroups = (int64_t)a.N * HW / PX;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < ngroups;
-       q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t pix = q * PX;
-    const int n = (int)(pix / HW);
-    const int64_t rem = pix - (int64_t)n * HW;
-    const int h = (int)(rem / a.W), w = (int)(rem - (int64_t)h * a.W);
+  const int n = blockIdx.y;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < HW / PX; q += gridDim.x * blockDim.x) {
+    const int rem = q * PX;
+    const int h = rem / a.W, w = rem - h * a.W;
     int ids[PX];
     float b0[PX], b1[PX], b2[PX];
     const int32_t* ip = a.index_img + (int64_t)n * a.is.s0 + (int64_t)h * a.is.s1 + (int64_t)w * a.is.s2;
@@ -82,7 +79,7 @@ __global__ void __launch_bounds__(256) interp_fwd_kernel(InterpArgs a, float* __
     }
     const float sy = sweep_x(h, a.H);
     const float* an = a.attr + (int64_t)n * a.as.s0;
-    float* op = out + (int64_t)n * a.C * HW + rem;
+    float* op = out + (int64_t)n * a.C * HW + rem;  // 64-bit: n*C*HW may exceed 2^31
 
     if (AVEC) {
       for (int c = 0; c < a.C; c += 4) {
@@ -150,17 +147,14 @@ template <bool NEED_VERT, bool NEED_BARY, bool RV4>
 __global__ void __launch_bounds__(256) interp_bwd_kernel(InterpBwdArgs b, float* __restrict__ vert_grad,
                                                          float* __restrict__ bary_grad) {
   const InterpArgs& a = b.f;
-  const int64_t HW = (int64_t)a.H * a.W;
-  const int64_t npix = (int64_t)a.N * HW;
+  const int64_t HW = (int64_t)a.H * a.W;  // blockIdx.y = image
   const int lane = threadIdx.x & 31;
-  const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = pix < npix;
-  int n = 0, h = 0, w = 0, id = -1;
-  int64_t rem = 0;
+  const int rem = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = rem < (int)HW;
+  const int n = blockIdx.y;
+  int h = 0, w = 0, id = -1;
   if (in_range) {
-    n = (int)(pix / HW);
-    rem = pix - (int64_t)n * HW;
-    h = (int)(rem / a.W); w = (int)(rem - (int64_t)h * a.W);
+    h = rem / a.W; w = rem - h * a.W;
     id = a.index_img[(int64_t)n * a.is.s0 + (int64_t)h * a.is.s1 + (int64_t)w * a.is.s2];
   }
   const bool used = id != -1;
@@ -182,9 +176,9 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(InterpBwdArgs b, float*
     }
   }
   // runs of equal (image, triangle) along the warp
-  const int64_t key = used ? (((int64_t)n << 32) | (uint32_t)id) : ((int64_t)-1 - lane);
-  const int64_t key_up = __shfl_up_sync(0xffffffffu, key, 1);
-  const int64_t key_dn = __shfl_down_sync(0xffffffffu, key, 1);
+  const int key = used ? id : (-2 - lane);  // a block never spans two images
+  const int key_up = __shfl_up_sync(0xffffffffu, key, 1);
+  const int key_dn = __shfl_down_sync(0xffffffffu, key, 1);
   const bool head = (lane == 0) || (key_up != key);
   const bool tail = (lane == 31) || (key_dn != key);
   const unsigned tail_mask = __ballot_sync(0xffffffffu, tail);
@@ -243,227 +237,259 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(InterpBwdArgs b, float*
 // ------------------------------------------------------------------------------------------
 // backward, tiled (the fast path): bulk-async staged tiles + register run-reduction
 // ------------------------------------------------------------------------------------------
-// A CTA owns a 128 x 8 pixel tile.  One warp issues cp.async.bulk row copies (TMA engine, SASS
-// UBLKCP) that land the tile's grad_out planes (up to LPW channels per pass), bary planes and
-// index row segments in shared memory and complete on an mbarrier; nobody spends LSU
-// instructions or registers on the 16+4C B/px stream.  Then
-//   phase A (vertex grads): "walkers" of LPW lanes -- lane = channel -- walk a row segment in
+// One persistent CTA of 512 threads per SM walks "tiles" of TP consecutive pixels of the flattened
+// H*W plane of one image (planes are dense, so a tile is ONE contiguous 4*TP-byte span per plane).
+// A two-stage shared-memory ring is fed by cp.async.bulk copies (the TMA engine, SASS UBLKCP:
+// one copy per plane, completing on an mbarrier); the copies of tile i+1 are in flight while tile i
+// is reduced, and no LSU instruction or register is spent on the 16+4C B/px input stream.
+//   phase A (vertex grads): "walkers" of LPW lanes -- lane = channel -- walk a pixel segment in
 //     4-pixel steps (one conflict-free LDS.128 of their own channel plane, broadcast LDS.128 of
-//     index/bary), accumulate g*bary_k for the current triangle run in three registers and, when
-//     the triangle id changes, flush the run with three reductions whose LPW lanes hit LPW
-//     consecutive floats of one vertex row (a single coalesced 64-B RED per vertex at C=16).
+//     index/bary), accumulate g*bary_k of the current triangle run in three registers and, when the
+//     triangle id changes, flush the run with three reductions whose LPW lanes hit LPW consecutive
+//     floats of one vertex row (one coalesced 64-B RED per vertex at C=16; measured 69 G rows/s).
 //     No shuffles, no shared-memory atomics, one reduction per (run, vertex) instead of per pixel.
-//   phase B (bary grads): lane = pixel quad; dot products of the staged gradients with the three
-//     attribute rows, accumulated across channel passes in registers, 128-bit streaming stores.
-constexpr int kTW = 128, kTH = 8, kTP = kTW * kTH;
-constexpr int kBwdThreads = 256;
+//     A run is "consecutive pixels showing the same triangle", so crossing an image-row boundary
+//     inside a tile is harmless: sums are per triangle.
+//   phase B (bary grads): thread = 2 (or 4) consecutive pixels; dot products of the staged gradients
+//     with the three attribute rows (LDG.128 row gathers, shared by neighbouring pixels of a triangle).
+constexpr int kBwdThreads = 512;
+constexpr int kBwdStages = 2;
+
+template <int LPW> struct BwdTileCfg { static constexpr int TP = (LPW == 16) ? 1024 : 2048; };
+
+template <int LPW>
+struct BwdStage {
+  static constexpr int TP = BwdTileCfg<LPW>::TP;
+  static constexpr int PITCH = TP + 4;  // plane pitch == 4 (mod 32) words: LDS.128 of LPW consecutive
+                                        // planes by LPW lanes is bank-conflict free
+  float g[LPW * PITCH];
+  float bary[3 * TP];
+  int idx[TP];
+};
 
 template <int LPW>
 struct BwdTileSmem {
-  static constexpr int PITCH = kTP + 4;  // plane pitch == 4 (mod 32) words: LDS.128 by LPW lanes of
-                                         // consecutive planes is bank-conflict free
-  float g[LPW * PITCH];
-  float bary[3 * kTP];
-  int idx[kTP];
-  unsigned long long bar;
+  BwdStage<LPW> st[kBwdStages];
+  unsigned long long full[kBwdStages];
 };
 
+// Phase A of the tiled backward for one walker lane (see the kernel comment).  Kept out of line so
+// that its loop gets its own register allocation: the run-boundary block must stay short (it
+// executes once per ~5 pixels), which needs the table pointers and strides resident in registers.
+//   gp: this lane's channel plane; ip/bp: index and bary planes of the stage (bary plane pitch TP)
+//   vg: vertex-gradient table of this image, already offset by this lane's channel
+//   vib: vi rows of this image; vs1/vs2 element strides of vi (row, corner)
+template <int TP>
+__device__ __noinline__ void walk_runs(const float* __restrict__ gp, const int* __restrict__ ip,
+                                       const float* __restrict__ bp, int xs, int xe, float* vg,
+                                       const int32_t* __restrict__ vib, int vs1, int vs2, unsigned Cs,
+                                       bool c_on) {
+  int cur = -1;
+  unsigned v0 = 0, v1 = 0, v2 = 0;  // vertex ids of the current run
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 1
+  for (int x = xs; x < xe; x += 4) {
+    const float4 gq = *reinterpret_cast<const float4*>(gp + x);
+    const int4 iq = *reinterpret_cast<const int4*>(ip + x);
+    const float4 p0q = *reinterpret_cast<const float4*>(bp + x);
+    const float4 p1q = *reinterpret_cast<const float4*>(bp + TP + x);
+    const float4 p2q = *reinterpret_cast<const float4*>(bp + 2 * TP + x);
+    const int ids[4] = {iq.x, iq.y, iq.z, iq.w};
+    const float gs[4] = {gq.x, gq.y, gq.z, gq.w};
+    const float q0[4] = {p0q.x, p0q.y, p0q.z, p0q.w};
+    const float q1[4] = {p1q.x, p1q.y, p1q.z, p1q.w};
+    const float q2[4] = {p2q.x, p2q.y, p2q.z, p2q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int id = ids[j];
+      if (id != cur) {  // run boundary (uniform across the walker's lanes)
+        if (cur >= 0 && c_on) {
+          red_add(vg + (size_t)(v0 * Cs), a0);
+          red_add(vg + (size_t)(v1 * Cs), a1);
+          red_add(vg + (size_t)(v2 * Cs), a2);
+        }
+        // vertex ids of the new run: fetched now, consumed at its flush.  Empty pixels (id < 0)
+        // read triangle 0 harmlessly; their run is never flushed.
+        const int32_t* vip = vib + (size_t)((unsigned)max(id, 0) * (unsigned)vs1);
+        v0 = (unsigned)vip[0];
+        v1 = (unsigned)vip[vs2];
+        v2 = (unsigned)vip[2 * vs2];
+        a0 = a1 = a2 = 0.f;
+        cur = id;
+      }
+      // unconditional: while cur < 0 the sums are garbage that is reset before use
+      a0 = fmaf(gs[j], q0[j], a0);
+      a1 = fmaf(gs[j], q1[j], a1);
+      a2 = fmaf(gs[j], q2[j], a2);
+    }
+  }
+  if (cur >= 0 && c_on) {
+    red_add(vg + (size_t)(v0 * Cs), a0);
+    red_add(vg + (size_t)(v1 * Cs), a1);
+    red_add(vg + (size_t)(v2 * Cs), a2);
+  }
+}
+
 template <int LPW, bool NEED_VERT, bool NEED_BARY, bool AVEC>
-__global__ void __launch_bounds__(kBwdThreads, 2)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __restrict__ bary_grad,
-                       int tilesX, int tilesY, int64_t num_tiles) {
+                       int tiles_per_img, int64_t num_tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BwdTileSmem<LPW>& S = *reinterpret_cast<BwdTileSmem<LPW>*>(smem_raw);
-  constexpr int PITCH = BwdTileSmem<LPW>::PITCH;
+  constexpr int TP = BwdTileCfg<LPW>::TP;
+  constexpr int PITCH = BwdStage<LPW>::PITCH;
   const InterpArgs& a = b.f;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int64_t HW = (int64_t)a.H * a.W;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(&S.bar);
-  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  const int HW = a.H * a.W;  // < 2^31 guaranteed by the host
+  if (tid == 0) {
+    for (int s = 0; s < kBwdStages; ++s) mbar_init(reinterpret_cast<uint64_t*>(&S.full[s]), 1);
+    mbar_fence_init();
+  }
   __syncthreads();
-  uint32_t phase = 0;
   const int nchunks = (a.C + LPW - 1) / LPW;
+  // pipeline items: (tile, channel pass); this CTA owns tiles blockIdx.x, +gridDim.x, ...
+  const int64_t my_tiles = (num_tiles > blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t n_items = my_tiles * nchunks;
 
-  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int tpi = tilesX * tilesY;
-    const int n = (int)(tile / tpi);
-    const int tl = (int)(tile - (int64_t)n * tpi);
-    const int ty = tl / tilesX, tx = tl - ty * tilesX;
-    const int x0 = tx * kTW, y0 = ty * kTH;
-    const int tw = min(kTW, a.W - x0), th = min(kTH, a.H - y0);
-    const uint32_t row_bytes = (uint32_t)tw * 4u;
-
-    // phase-B ownership: thread -> pixel quad (row qr, columns qx..qx+3)
-    const int qr = tid >> 5, qx = (tid & 31) << 2;
-    const bool q_in = NEED_BARY && qr < th && qx < tw;
-    float gb[4][3];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) gb[j][0] = gb[j][1] = gb[j][2] = 0.f;
-    int qid[4] = {-1, -1, -1, -1};
-    int qv[4][3];
-
-    for (int chunk = 0; chunk < nchunks; ++chunk) {
-      const int c0 = chunk * LPW;
-      const int nc = min(LPW, a.C - c0);
-      // ---- stage the tile: warp 0 issues the bulk copies ----
-      if (tid < 32) {
-        const int extra_planes = (chunk == 0) ? ((NEED_VERT ? 3 : 0) + 1) : 0;
-        const int items = (nc + extra_planes) * th;
-        if (lane == 0) {
-          fence_proxy_async_smem();
-          mbar_arrive_expect_tx(bar, (uint32_t)items * row_bytes);
-        }
-        __syncwarp();
-        for (int i = lane; i < items; i += 32) {
-          const int pl = i / th, r = i - pl * th;
-          const void* src;
-          void* dst;
-          if (pl < nc) {
-            src = b.grad_out + (int64_t)n * b.gs.s0 + (int64_t)(c0 + pl) * b.gs.s1 + (int64_t)(y0 + r) * b.gs.s2 + x0;
-            dst = S.g + pl * PITCH + r * kTW;
-          } else if (NEED_VERT && pl < nc + 3) {
-            const int k = pl - nc;
-            src = a.bary + (int64_t)n * a.bs.s0 + (int64_t)k * a.bs.s1 + (int64_t)(y0 + r) * a.bs.s2 + x0;
-            dst = S.bary + k * kTP + r * kTW;
-          } else {
-            src = a.index_img + (int64_t)n * a.is.s0 + (int64_t)(y0 + r) * a.is.s1 + x0;
-            dst = S.idx + r * kTW;
-          }
-          bulk_g2s(dst, src, row_bytes, bar);
-        }
+  auto issue = [&](int64_t item) {  // executed by warp 0 only
+    const int s = (int)(item & 1);
+    const int64_t tile = blockIdx.x + (item / nchunks) * gridDim.x;
+    const int chunk = (int)(item % nchunks);
+    const int n = (int)(tile / tiles_per_img);
+    const int p0 = (int)(tile - (int64_t)n * tiles_per_img) * TP;
+    const int npx = min(TP, HW - p0);
+    const int c0 = chunk * LPW, nc = min(LPW, a.C - c0);
+    const int ncopies = nc + (NEED_VERT ? 3 : 0) + 1;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(&S.full[s]);
+    BwdStage<LPW>& st = S.st[s];
+    if (lane == 0) {
+      fence_proxy_async_smem();
+      mbar_arrive_expect_tx(bar, (uint32_t)ncopies * (uint32_t)npx * 4u);
+    }
+    __syncwarp();
+    if (lane < ncopies) {
+      const void* src;
+      void* dst;
+      if (lane < nc) {
+        src = b.grad_out + (int64_t)n * b.gs.s0 + (int64_t)(c0 + lane) * b.gs.s1 + p0;
+        dst = st.g + lane * PITCH;
+      } else if (NEED_VERT && lane < nc + 3) {
+        src = a.bary + (int64_t)n * a.bs.s0 + (int64_t)(lane - nc) * a.bs.s1 + p0;
+        dst = st.bary + (lane - nc) * TP;
+      } else {
+        src = a.index_img + (int64_t)n * a.is.s0 + p0;
+        dst = st.idx;
       }
-      mbar_wait(bar, phase);
-      phase ^= 1u;
+      bulk_g2s(dst, src, (uint32_t)npx * 4u, bar);
+    }
+  };
 
-      // ---- phase A: vertex-attribute gradients ----
-      if (NEED_VERT) {
-        constexpr int WALKERS = kBwdThreads / LPW;
-        constexpr int SEGS = WALKERS / kTH;  // walkers per tile row
-        constexpr int SEG = kTW / SEGS;      // pixels per walker
-        const int walker = tid / LPW, c = tid - walker * LPW;
-        const int row = walker / SEGS, seg = walker - row * SEGS;
-        if (row < th) {
-          const bool c_on = c < nc;
-          const float* gp = S.g + (c_on ? c : 0) * PITCH + row * kTW;
-          const int* ip = S.idx + row * kTW;
-          const float* b0p = S.bary + row * kTW;
-          const float* b1p = b0p + kTP;
-          const float* b2p = b1p + kTP;
-          float* vg = vert_grad + (int64_t)n * a.V * a.C + c0 + c;
-          const int32_t* vib = a.vi + (int64_t)n * a.vis.s0;
-          const int xe = min(seg * SEG + SEG, tw);
-          int cur = -1, v0 = 0, v1 = 0, v2 = 0;
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-          for (int x = seg * SEG; x < xe; x += 4) {
-            const float4 gq = *reinterpret_cast<const float4*>(gp + x);
-            const int4 iq = *reinterpret_cast<const int4*>(ip + x);
-            const float4 p0 = *reinterpret_cast<const float4*>(b0p + x);
-            const float4 p1 = *reinterpret_cast<const float4*>(b1p + x);
-            const float4 p2 = *reinterpret_cast<const float4*>(b2p + x);
-            const int ids[4] = {iq.x, iq.y, iq.z, iq.w};
-            const float gs[4] = {gq.x, gq.y, gq.z, gq.w};
-            const float q0[4] = {p0.x, p0.y, p0.z, p0.w};
-            const float q1[4] = {p1.x, p1.y, p1.z, p1.w};
-            const float q2[4] = {p2.x, p2.y, p2.z, p2.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int id = ids[j];
-              if (id != cur) {  // uniform across the walker's lanes
-                if (cur >= 0 && c_on) {
-                  red_add(vg + (int64_t)v0 * a.C, a0);
-                  red_add(vg + (int64_t)v1 * a.C, a1);
-                  red_add(vg + (int64_t)v2 * a.C, a2);
-                }
-                a0 = a1 = a2 = 0.f;
-                cur = id;
-                if (id >= 0) {
-                  const int32_t* vip = vib + (int64_t)id * a.vis.s1;
-                  v0 = vip[0]; v1 = vip[a.vis.s2]; v2 = vip[2 * a.vis.s2];
-                }
-              }
-              if (id >= 0) {
-                a0 = fmaf(gs[j], q0[j], a0);
-                a1 = fmaf(gs[j], q1[j], a1);
-                a2 = fmaf(gs[j], q2[j], a2);
-              }
-            }
-          }
-          if (cur >= 0 && c_on) {
-            red_add(vg + (int64_t)v0 * a.C, a0);
-            red_add(vg + (int64_t)v1 * a.C, a1);
-            red_add(vg + (int64_t)v2 * a.C, a2);
-          }
-        }
+  if (tid < 32 && n_items > 0) issue(0);
+  uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
+
+  // phase-B state of the current tile (a thread owns the same PPT pixels across channel passes)
+  constexpr int PPT = TP / kBwdThreads;  // 2 (TP 1024) or 4 (TP 2048) consecutive pixels per thread
+  float gb[PPT][3];
+
+  for (int64_t item = 0; item < n_items; ++item) {
+    const int s = (int)(item & 1);
+    if (tid < 32 && item + 1 < n_items) issue(item + 1);  // stage s^1 was released by the barrier below
+    const int64_t tile = blockIdx.x + (item / nchunks) * gridDim.x;
+    const int chunk = (int)(item % nchunks);
+    const int n = (int)(tile / tiles_per_img);
+    const int p0 = (int)(tile - (int64_t)n * tiles_per_img) * TP;
+    const int npx = min(TP, HW - p0);
+    const int c0 = chunk * LPW, nc = min(LPW, a.C - c0);
+    BwdStage<LPW>& st = S.st[s];
+    mbar_wait(reinterpret_cast<uint64_t*>(&S.full[s]), (phase_bits >> s) & 1u);
+    phase_bits ^= (1u << s);
+
+    // ---- phase A: vertex-attribute gradients ----
+    if (NEED_VERT) {
+      constexpr int WALKERS = kBwdThreads / LPW;
+      constexpr int SEG = TP / WALKERS;  // pixels per walker (32 / 32 / 16 for LPW 16 / 8 / 4)
+      const int walker = tid / LPW, c = tid - walker * LPW;
+      const int xs = walker * SEG, xe = min(xs + SEG, npx);
+      if (xs < xe) {
+        const bool c_on = c < nc;
+        walk_runs<TP>(st.g + (c_on ? c : 0) * PITCH, st.idx, st.bary, xs, xe,
+                      vert_grad + (int64_t)n * a.V * a.C + c0 + (c_on ? c : 0),
+                      a.vi + (int64_t)n * a.vis.s0, (int)a.vis.s1, (int)a.vis.s2, (unsigned)a.C, c_on);
       }
+    }
 
-      // ---- phase B: barycentric gradients (partial over this channel pass) ----
-      if (q_in) {
-        if (chunk == 0) {
-          const int4 iq = *reinterpret_cast<const int4*>(S.idx + qr * kTW + qx);
-          qid[0] = iq.x; qid[1] = iq.y; qid[2] = iq.z; qid[3] = iq.w;
+    // ---- phase B: barycentric gradients: thread = PPT consecutive pixels, all channels ----
+    if (NEED_BARY) {
+      const int x = tid * PPT;
+      if (chunk == 0) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            qv[j][0] = qv[j][1] = qv[j][2] = 0;
-            if (qid[j] >= 0) {
-              if (j > 0 && qid[j] == qid[j - 1]) {
-                qv[j][0] = qv[j - 1][0]; qv[j][1] = qv[j - 1][1]; qv[j][2] = qv[j - 1][2];
-              } else {
-                load_vi(a, n, qid[j], qv[j][0], qv[j][1], qv[j][2]);
-              }
+        for (int j = 0; j < PPT; ++j) gb[j][0] = gb[j][1] = gb[j][2] = 0.f;
+      }
+      if (x < npx) {
+        int qid[PPT], qv[PPT][3];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          qid[j] = st.idx[x + j];
+          qv[j][0] = qv[j][1] = qv[j][2] = 0;
+          if (qid[j] >= 0) {
+            if (j > 0 && qid[j] == qid[j - 1]) {
+              qv[j][0] = qv[j - 1][0]; qv[j][1] = qv[j - 1][1]; qv[j][2] = qv[j - 1][2];
+            } else {
+              load_vi(a, n, qid[j], qv[j][0], qv[j][1], qv[j][2]);
             }
           }
         }
-        const float* an = a.attr + (int64_t)n * a.as.s0;
-        const float* gq_base = S.g + qr * kTW + qx;
+        const float* an = a.attr + (int64_t)n * a.as.s0 + (int64_t)c0 * a.as.s2;
+        const float* gq_base = st.g + x;
         if (AVEC) {
           for (int cc = 0; cc < nc; cc += 4) {
-            float4 gq[4];
+            float gq[4][PPT];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) gq[k] = *reinterpret_cast<const float4*>(gq_base + (cc + k) * PITCH);
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+              for (int j = 0; j < PPT; ++j) gq[k][j] = gq_base[(cc + k) * PITCH + j];
+            }
             float4 A0, A1, A2;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < PPT; ++j) {
               if (qid[j] < 0) continue;
               if (!(j > 0 && qid[j] == qid[j - 1])) {
-                A0 = *reinterpret_cast<const float4*>(an + (int64_t)qv[j][0] * a.as.s1 + c0 + cc);
-                A1 = *reinterpret_cast<const float4*>(an + (int64_t)qv[j][1] * a.as.s1 + c0 + cc);
-                A2 = *reinterpret_cast<const float4*>(an + (int64_t)qv[j][2] * a.as.s1 + c0 + cc);
+                A0 = *reinterpret_cast<const float4*>(an + (int64_t)qv[j][0] * a.as.s1 + cc);
+                A1 = *reinterpret_cast<const float4*>(an + (int64_t)qv[j][1] * a.as.s1 + cc);
+                A2 = *reinterpret_cast<const float4*>(an + (int64_t)qv[j][2] * a.as.s1 + cc);
               }
-              const float g0 = j == 0 ? gq[0].x : j == 1 ? gq[0].y : j == 2 ? gq[0].z : gq[0].w;
-              const float g1 = j == 0 ? gq[1].x : j == 1 ? gq[1].y : j == 2 ? gq[1].z : gq[1].w;
-              const float g2 = j == 0 ? gq[2].x : j == 1 ? gq[2].y : j == 2 ? gq[2].z : gq[2].w;
-              const float g3 = j == 0 ? gq[3].x : j == 1 ? gq[3].y : j == 2 ? gq[3].z : gq[3].w;
-              gb[j][0] += g0 * A0.x + g1 * A0.y + g2 * A0.z + g3 * A0.w;
-              gb[j][1] += g0 * A1.x + g1 * A1.y + g2 * A1.z + g3 * A1.w;
-              gb[j][2] += g0 * A2.x + g1 * A2.y + g2 * A2.z + g3 * A2.w;
+              gb[j][0] += gq[0][j] * A0.x + gq[1][j] * A0.y + gq[2][j] * A0.z + gq[3][j] * A0.w;
+              gb[j][1] += gq[0][j] * A1.x + gq[1][j] * A1.y + gq[2][j] * A1.z + gq[3][j] * A1.w;
+              gb[j][2] += gq[0][j] * A2.x + gq[1][j] * A2.y + gq[2][j] * A2.z + gq[3][j] * A2.w;
             }
           }
         } else {
           for (int cc = 0; cc < nc; ++cc) {
-            const float4 gq = *reinterpret_cast<const float4*>(gq_base + cc * PITCH);
-            const float gs[4] = {gq.x, gq.y, gq.z, gq.w};
             float A0 = 0.f, A1 = 0.f, A2 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < PPT; ++j) {
               if (qid[j] < 0) continue;
               if (!(j > 0 && qid[j] == qid[j - 1])) {
-                A0 = an[(int64_t)qv[j][0] * a.as.s1 + (int64_t)(c0 + cc) * a.as.s2];
-                A1 = an[(int64_t)qv[j][1] * a.as.s1 + (int64_t)(c0 + cc) * a.as.s2];
-                A2 = an[(int64_t)qv[j][2] * a.as.s1 + (int64_t)(c0 + cc) * a.as.s2];
+                A0 = an[(int64_t)qv[j][0] * a.as.s1 + (int64_t)cc * a.as.s2];
+                A1 = an[(int64_t)qv[j][1] * a.as.s1 + (int64_t)cc * a.as.s2];
+                A2 = an[(int64_t)qv[j][2] * a.as.s1 + (int64_t)cc * a.as.s2];
               }
-              gb[j][0] += gs[j] * A0; gb[j][1] += gs[j] * A1; gb[j][2] += gs[j] * A2;
+              const float g = gq_base[cc * PITCH + j];
+              gb[j][0] += g * A0; gb[j][1] += g * A1; gb[j][2] += g * A2;
             }
           }
         }
+        if (chunk == nchunks - 1) {
+          float* gp = bary_grad + (int64_t)n * 3 * HW + p0 + x;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            if (PPT == 2) *reinterpret_cast<float2*>(gp + (int64_t)k * HW) = make_float2(gb[0][k], gb[PPT - 1][k]);
+            else *reinterpret_cast<float4*>(gp + (int64_t)k * HW) = make_float4(gb[0][k], gb[1 % PPT][k], gb[2 % PPT][k], gb[3 % PPT][k]);
+          }
+        }
       }
-      __syncthreads();  // all reads of this pass done before the next bulk copies overwrite the tile
     }
-    if (q_in) {
-      float* gp = bary_grad + (int64_t)n * 3 * HW + (int64_t)(y0 + qr) * a.W + x0 + qx;
-      stg_stream_f4(gp, make_float4(gb[0][0], gb[1][0], gb[2][0], gb[3][0]));
-      stg_stream_f4(gp + HW, make_float4(gb[0][1], gb[1][1], gb[2][1], gb[3][1]));
-      stg_stream_f4(gp + 2 * HW, make_float4(gb[0][2], gb[1][2], gb[2][2], gb[3][2]));
-    }
+    __syncthreads();  // every reader of stage s is done: the next issue may overwrite it
   }
 }
 
@@ -510,15 +536,14 @@ extern "C" int drtk_b200_interpolate_forward(const float* vert_attributes, const
                    VecOk::image(bary_img, W, a.bs.s3, a.bs.s2, a.bs.s1, a.bs.s0);
   const bool avec = (C % 4 == 0) && a.as.s2 == 1 && (a.as.s1 % 4 == 0) && (a.as.s0 % 4 == 0) &&
                     (reinterpret_cast<uintptr_t>(vert_attributes) % 16 == 0);
-  const int64_t npix = N * H * W;
-  if (vec && avec)
-    interp_fwd_kernel<true, true><<<grid_for(npix / 4, 256, 8), 256, 0, stream>>>(a, out);
-  else if (vec)
-    interp_fwd_kernel<true, false><<<grid_for(npix / 4, 256, 8), 256, 0, stream>>>(a, out);
-  else if (avec)
-    interp_fwd_kernel<false, true><<<grid_for(npix, 256, 8), 256, 0, stream>>>(a, out);
-  else
-    interp_fwd_kernel<false, false><<<grid_for(npix, 256, 8), 256, 0, stream>>>(a, out);
+  if (H * W >= (int64_t)0x7FFFFFF0 || N > 65535) return DRTK_B200_EUNSUPPORTED;
+  const int per_img = (int)((8 + N - 1) / N);
+  const unsigned gx = grid_for(vec ? H * W / 4 : H * W, 256, per_img > 0 ? per_img : 1);
+  const dim3 grid(gx, (unsigned)N);
+  if (vec && avec) interp_fwd_kernel<true, true><<<grid, 256, 0, stream>>>(a, out);
+  else if (vec) interp_fwd_kernel<true, false><<<grid, 256, 0, stream>>>(a, out);
+  else if (avec) interp_fwd_kernel<false, true><<<grid, 256, 0, stream>>>(a, out);
+  else interp_fwd_kernel<false, false><<<grid, 256, 0, stream>>>(a, out);
   DRTK_CHECK_LAUNCH();
   return 0;
 }
@@ -549,35 +574,35 @@ extern "C" int drtk_b200_interpolate_backward(
   const bool nv = vert_attributes_grad != nullptr, nb = bary_img_grad != nullptr;
 
   // fast path: tiles staged through shared memory by bulk-async copies; needs dense, 16-B aligned rows
+  // (dense H*W planes, 16-B aligned plane starts)
   const bool rows_ok =
-      (W % 4 == 0) && VecOk::image(grad_out, W, b.gs.s3, b.gs.s2, b.gs.s1, b.gs.s0) &&
-      VecOk::image(index_img, W, b.f.is.s2, b.f.is.s1, b.f.is.s0) &&
-      (!nv || VecOk::image(bary_img, W, b.f.bs.s3, b.f.bs.s2, b.f.bs.s1, b.f.bs.s0)) &&
+      ((H * W) % 4 == 0) && (H * W < (int64_t)0x7FFFFFF0) && (V * C < (int64_t)0x7FFFFFF0) &&
+      (F == 0 || (F * (b.f.vis.s1 > 0 ? b.f.vis.s1 : 1) < (int64_t)0x7FFFFFF0 && b.f.vis.s2 >= 0 && b.f.vis.s2 < (1 << 28) && b.f.vis.s1 >= 0)) &&
+      VecOk::image(grad_out, 4, b.gs.s3, 4, b.gs.s1, b.gs.s0) && b.gs.s2 == W &&
+      VecOk::image(index_img, 4, b.f.is.s2, 4, b.f.is.s0) && b.f.is.s1 == W &&
+      (!nv || (VecOk::image(bary_img, 4, b.f.bs.s3, 4, b.f.bs.s1, b.f.bs.s0) && b.f.bs.s2 == W)) &&
       (!nb || reinterpret_cast<uintptr_t>(bary_img_grad) % 16 == 0);
   if (rows_ok) {
     const bool avec = nb && (C % 4 == 0) && b.f.as.s2 == 1 && (b.f.as.s1 % 4 == 0) && (b.f.as.s0 % 4 == 0) &&
                       (reinterpret_cast<uintptr_t>(vert_attributes) % 16 == 0);
-    const int tilesX = (int)((W + kTW - 1) / kTW), tilesY = (int)((H + kTH - 1) / kTH);
-    const int64_t num_tiles = N * tilesX * tilesY;
     int rc2 = 0;
-    auto launch = [&](auto kern, size_t smem) {
+    auto launch = [&](auto kern, size_t smem, int TP) {
+      const int tiles_per_img = (int)((H * W + TP - 1) / TP);
+      const int64_t num_tiles = N * (int64_t)tiles_per_img;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { rc2 = (int)e; return; }
-      int occ = 0;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBwdThreads, smem);
-      if (e != cudaSuccess || occ < 1) { rc2 = e != cudaSuccess ? (int)e : DRTK_B200_EUNSUPPORTED; return; }
-      const int64_t cap = (int64_t)kNumSMs * occ;
-      const unsigned grid = (unsigned)(num_tiles < cap ? num_tiles : cap);
-      kern<<<grid, kBwdThreads, smem, stream>>>(b, vert_attributes_grad, bary_img_grad, tilesX, tilesY, num_tiles);
+      const unsigned grid = (unsigned)(num_tiles < kNumSMs ? num_tiles : kNumSMs);  // one persistent CTA per SM
+      kern<<<grid, kBwdThreads, smem, stream>>>(b, vert_attributes_grad, bary_img_grad, tiles_per_img, num_tiles);
     };
 #define DRTK_BWD_TILE(LPW)                                                                                  \
     do {                                                                                                    \
       const size_t smem = sizeof(BwdTileSmem<LPW>) + 128;                                                   \
-      if (nv && nb) { if (avec) launch(interp_bwd_tile_kernel<LPW, true, true, true>, smem);                \
-                      else launch(interp_bwd_tile_kernel<LPW, true, true, false>, smem); }                  \
-      else if (nv) launch(interp_bwd_tile_kernel<LPW, true, false, false>, smem);                           \
-      else { if (avec) launch(interp_bwd_tile_kernel<LPW, false, true, true>, smem);                        \
-             else launch(interp_bwd_tile_kernel<LPW, false, true, false>, smem); }                          \
+      const int TP = BwdTileCfg<LPW>::TP;                                                                   \
+      if (nv && nb) { if (avec) launch(interp_bwd_tile_kernel<LPW, true, true, true>, smem, TP);            \
+                      else launch(interp_bwd_tile_kernel<LPW, true, true, false>, smem, TP); }              \
+      else if (nv) launch(interp_bwd_tile_kernel<LPW, true, false, false>, smem, TP);                       \
+      else { if (avec) launch(interp_bwd_tile_kernel<LPW, false, true, true>, smem, TP);                    \
+             else launch(interp_bwd_tile_kernel<LPW, false, true, false>, smem, TP); }                      \
     } while (0)
     if (C <= 4) DRTK_BWD_TILE(4);
     else if (C <= 8) DRTK_BWD_TILE(8);
@@ -589,7 +614,8 @@ extern "C" int drtk_b200_interpolate_backward(
   }
 
   // generic path (arbitrary strides / odd widths): one thread per pixel, segmented shuffle reduction
-  const unsigned blocks = (unsigned)((npix + 255) / 256);
+  if (H * W >= (int64_t)0x7FFFFFF0 || N > 65535) return DRTK_B200_EUNSUPPORTED;
+  const dim3 blocks((unsigned)((H * W + 255) / 256), (unsigned)N);
   const bool rv4 = (C % 4 == 0) && (reinterpret_cast<uintptr_t>(vert_attributes_grad) % 16 == 0);
   if (nv && nb) {
     if (rv4) interp_bwd_kernel<true, true, true><<<blocks, 256, 0, stream>>>(b, vert_attributes_grad, bary_img_grad);

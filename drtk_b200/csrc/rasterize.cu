@@ -40,22 +40,27 @@ struct RasterArgs {
 
 // Everything a sample test needs, derived once per triangle.
 struct TriSetup {
-  // canonical edges k = 0,1,2  <->  (v1,v2), (v2,v0), (v0,v1); origin = endpoint with the lower
-  // vertex index (src/rasterize/rasterize_kernel.cu:29-40)
-  float ox[3], oy[3], abx[3], aby[3], sg[3];
+  // canonical edges k = 0,1,2  <->  (v1,v2), (v2,v0), (v0,v1); origin o = endpoint with the lower
+  // vertex index (src/rasterize/rasterize_kernel.cu:29-40).  (ax, ay) is the edge direction times
+  // s = sign(den) * (swapped ? -1 : 1): b_k = s * fma(-ab.y, p.x-o.x, rn((p.y-o.y)*ab.x)) equals
+  // fma(-ay, p.x-o.x, rn((p.y-o.y)*ax)) bit for bit (round-to-nearest is sign symmetric), which
+  // saves the three multiplications by +-1 per sample.
+  float ox[3], oy[3], ax[3], ay[3];
   float d0, d1, d2;  // MUFU.RCP(epsclamp(z_k))
   float rden;        // MUFU.RCP(|den|)
   bool tl[3];
   int bx0, by0, bx1, by1;  // clamped pixel bounding box (inclusive); may be empty
 };
 
-__device__ __forceinline__ void canon_edge_setup(int ia, int ib, float ax, float ay, float bx,
-                                                 float by, float sgn, float& ox, float& oy,
-                                                 float& abx, float& aby, float& sg) {
+__device__ __forceinline__ void canon_edge_setup(int ia, int ib, float pax, float pay, float pbx,
+                                                 float pby, float sgn, float& ox, float& oy,
+                                                 float& ax, float& ay) {
   if (ia <= ib) {
-    ox = ax; oy = ay; abx = sub_rn(bx, ax); aby = sub_rn(by, ay); sg = sgn;
+    ox = pax; oy = pay;
+    ax = mul_rn(sub_rn(pbx, pax), sgn); ay = mul_rn(sub_rn(pby, pay), sgn);
   } else {
-    ox = bx; oy = by; abx = sub_rn(ax, bx); aby = sub_rn(ay, by); sg = -sgn;
+    ox = pbx; oy = pby;
+    ax = mul_rn(sub_rn(pax, pbx), -sgn); ay = mul_rn(sub_rn(pay, pby), -sgn);
   }
 }
 
@@ -95,9 +100,9 @@ __device__ __forceinline__ bool tri_setup(const RasterArgs& a, int n, int f, Tri
   s.by1 = min(a.H - 1, (int)((unsigned)__float2int_rz(mxy) + 1u));
 
   const float sgn = den > 0.f ? 1.f : -1.f;  // sign(den), den != 0 (:125)
-  canon_edge_setup(i1, i2, p1x, p1y, p2x, p2y, sgn, s.ox[0], s.oy[0], s.abx[0], s.aby[0], s.sg[0]);
-  canon_edge_setup(i2, i0, p2x, p2y, p0x, p0y, sgn, s.ox[1], s.oy[1], s.abx[1], s.aby[1], s.sg[1]);
-  canon_edge_setup(i0, i1, p0x, p0y, p1x, p1y, sgn, s.ox[2], s.oy[2], s.abx[2], s.aby[2], s.sg[2]);
+  canon_edge_setup(i1, i2, p1x, p1y, p2x, p2y, sgn, s.ox[0], s.oy[0], s.ax[0], s.ay[0]);
+  canon_edge_setup(i2, i0, p2x, p2y, p0x, p0y, sgn, s.ox[1], s.oy[1], s.ax[1], s.ay[1]);
+  canon_edge_setup(i0, i1, p0x, p0y, p1x, p1y, sgn, s.ox[2], s.oy[2], s.ax[2], s.ay[2]);
 
   if (den > 0.f) {  // top-left classification (:133-141)
     s.tl[0] = (v12y < 0.f) || (v12y == 0.f && v12x > 0.f);
@@ -116,28 +121,50 @@ __device__ __forceinline__ bool tri_setup(const RasterArgs& a, int n, int f, Tri
 }
 
 // One (triangle, pixel) sample.  Returns true and the depth bits when the pixel centre (x, y)
-// is covered under the top-left rule (:118-153).
-__device__ __forceinline__ bool sample(const TriSetup& s, float px, const float (&row)[3],
-                                       const float (&apy)[3], uint32_t& depth_bits) {
-  (void)apy;
-  // e_k = fma(-ab.y, p.x - o.x, rn((p.y - o.y) * ab.x)); the product is per-row (hoisted by the
-  // reference compiler as well; same value either way)
-  const float b0 = mul_rn(fma_rn(-s.aby[0], sub_rn(px, s.ox[0]), row[0]), s.sg[0]);
-  const float b1 = mul_rn(fma_rn(-s.aby[1], sub_rn(px, s.ox[1]), row[1]), s.sg[1]);
-  const float b2 = mul_rn(fma_rn(-s.aby[2], sub_rn(px, s.ox[2]), row[2]), s.sg[2]);
+// is covered under the top-left rule (:118-153).  row[k] = rn((p.y - o_k.y) * ax_k) is per row (the
+// reference compiler hoists the same product; same value either way).
+__device__ __forceinline__ bool sample(const float (&ox)[3], const float (&ay)[3], const bool (&tl)[3],
+                                       float rden, float d0, float d1, float d2, float px,
+                                       const float (&row)[3], uint32_t& depth_bits) {
+  const float b0 = fma_rn(-ay[0], sub_rn(px, ox[0]), row[0]);
+  const float b1 = fma_rn(-ay[1], sub_rn(px, ox[1]), row[1]);
+  const float b2 = fma_rn(-ay[2], sub_rn(px, ox[2]), row[2]);
   if (!(b0 >= 0.f && b1 >= 0.f && b2 >= 0.f)) return false;
-  if ((b0 == 0.f && !s.tl[0]) || (b1 == 0.f && !s.tl[1]) || (b2 == 0.f && !s.tl[2])) return false;
-  const float c0 = mul_rn(b0, s.rden), c1 = mul_rn(b1, s.rden), c2 = mul_rn(b2, s.rden);
+  if ((b0 == 0.f && !tl[0]) || (b1 == 0.f && !tl[1]) || (b2 == 0.f && !tl[2])) return false;
+  const float c0 = mul_rn(b0, rden), c1 = mul_rn(b1, rden), c2 = mul_rn(b2, rden);
   // dot(d_inv, bary) as compiled: FMUL(b1,d1) -> FFMA(b0,d0,.) -> FFMA(b2,d2,.)
-  const float inv = fma_rn(c2, s.d2, fma_rn(c0, s.d0, mul_rn(c1, s.d1)));
+  const float inv = fma_rn(c2, d2, fma_rn(c0, d0, mul_rn(c1, d1)));
   depth_bits = __float_as_uint(rcp_approx(epsclamp(inv)));
   return true;
 }
+__device__ __forceinline__ bool sample(const TriSetup& s, float px, const float (&row)[3],
+                                       uint32_t& depth_bits) {
+  return sample(s.ox, s.ay, s.tl, s.rden, s.d0, s.d1, s.d2, px, row, depth_bits);
+}
 
 __device__ __forceinline__ void row_terms(const TriSetup& s, float py, float (&row)[3]) {
-  row[0] = mul_rn(sub_rn(py, s.oy[0]), s.abx[0]);
-  row[1] = mul_rn(sub_rn(py, s.oy[1]), s.abx[1]);
-  row[2] = mul_rn(sub_rn(py, s.oy[2]), s.abx[2]);
+  row[0] = mul_rn(sub_rn(py, s.oy[0]), s.ax[0]);
+  row[1] = mul_rn(sub_rn(py, s.oy[1]), s.ax[1]);
+  row[2] = mul_rn(sub_rn(py, s.oy[2]), s.ax[2]);
+}
+
+// Conservative x-range of one image row: pixels outside [xs, xe] cannot pass the edge tests.
+// Edge k crosses zero at x* = o.x + row/ay; samples within one pixel of x* are always kept, which
+// covers the rounding of the exact test (<= 2^-23 (|dy| |ax/ay| + |dx|) px) as long as the edge is
+// not nearly horizontal and the coordinates are moderate; otherwise the edge does not prune.
+__device__ __forceinline__ void row_span(const float (&ox)[3], const float (&ax)[3], const float (&ay)[3],
+                                         const float (&row)[3], float dy_max, int& xs, int& xe) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float aay = fabsf(ay[k]);
+    if (aay * 1048576.f >= fabsf(ax[k]) * dy_max && fabsf(ox[k]) < 1048576.f) {  // (false for ay == 0, NaN)
+      const float xstar = fma_rn(row[k], rcp_approx(ay[k]), ox[k]);
+      if (fabsf(xstar) < 1.0e9f) {
+        if (ay[k] < 0.f) xs = max(xs, __float2int_rd(xstar) - 1);  // b grows with x: x >= x*
+        else xe = min(xe, __float2int_ru(xstar) + 1);              // b falls with x: x <= x*
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -228,45 +255,112 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* count, uint32_t* o
 // ------------------------------------------------------------------------------------------
 // per-tile resolve
 // ------------------------------------------------------------------------------------------
+// Shared-memory records of the triangles of one pass (structure of arrays, one slot per thread).
+struct TileRecs {
+  float ox[3][kRasterThreads], oy[3][kRasterThreads], ax[3][kRasterThreads], ay[3][kRasterThreads];
+  float d[3][kRasterThreads], rden[kRasterThreads];
+  int meta[kRasterThreads];  // tl bits 0-2 | bx0 << 3 | bx1 << 8 | by0 << 13   (tile-local 0..31)
+  int tri[kRasterThreads];
+  int prefix[kRasterThreads + 1];  // exclusive scan of the per-triangle row counts
+};
+
 __global__ void __launch_bounds__(kRasterThreads) raster_tiles_kernel(
     RasterArgs a, const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_offset,
     const uint32_t* __restrict__ tile_list, const uint32_t* __restrict__ large_count,
     const uint32_t* __restrict__ large_list, float* __restrict__ depth_img,
     int32_t* __restrict__ index_img) {
   __shared__ unsigned long long zbuf[kTilePix];
-  const int tid = threadIdx.x;
-  const int64_t t = blockIdx.x;
-  const int tiles_per_img = a.tilesX * a.tilesY;
-  const int n = (int)(t / tiles_per_img);
-  const int tl = (int)(t - (int64_t)n * tiles_per_img);
-  const int tile_y = tl / a.tilesX, tile_x = tl - tile_y * a.tilesX;
+  __shared__ TileRecs R;
+  __shared__ int warp_tot[kRasterThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = blockIdx.z;
+  const int64_t t = ((int64_t)n * a.tilesY + tile_y) * a.tilesX + tile_x;
   const int x_lo = tile_x << kTileLog, y_lo = tile_y << kTileLog;
   const int x_hi = min(x_lo + kTile - 1, a.W - 1), y_hi = min(y_lo + kTile - 1, a.H - 1);
 
   for (int i = tid; i < kTilePix; i += kRasterThreads) zbuf[i] = ~0ull;  // (:484-488)
-  __syncthreads();
 
-  // (1) small triangles: one thread per list entry, serial walk of the clipped bounding box
+  // (1) small triangles.  Work item = one image row of one triangle's clipped bounding box, so the
+  // threads of a warp do equally sized pieces of work whatever the triangle sizes are.
   const uint32_t cnt = tile_count[t];
   const uint32_t* list = tile_list + tile_offset[t];
-  for (uint32_t i = tid; i < cnt; i += kRasterThreads) {
-    const int f = (int)list[i];
-    TriSetup s;
-    if (!tri_setup(a, n, f, s)) continue;
-    const int bx0 = max(s.bx0, x_lo), bx1 = min(s.bx1, x_hi);
-    const int by0 = max(s.by0, y_lo), by1 = min(s.by1, y_hi);
-    for (int y = by0; y <= by1; ++y) {
-      float row[3];
-      row_terms(s, (float)y, row);
-      for (int x = bx0; x <= bx1; ++x) {
-        uint32_t db;
-        if (sample(s, (float)x, row, row, db)) {
-          const unsigned long long packed = ((unsigned long long)db << 32) | (uint32_t)f;  // (:155-157)
-          atomicMin(&zbuf[((y - y_lo) << kTileLog) + (x - x_lo)], packed);
+  for (uint32_t base = 0; base < cnt; base += kRasterThreads) {
+    __syncthreads();  // zbuf initialised / previous pass done with the records
+    int rows = 0;
+    if (base + tid < cnt) {
+      const int f = (int)list[base + tid];
+      TriSetup s;
+      if (tri_setup(a, n, f, s)) {
+        const int bx0 = max(s.bx0, x_lo), bx1 = min(s.bx1, x_hi);
+        const int by0 = max(s.by0, y_lo), by1 = min(s.by1, y_hi);
+        if (bx0 <= bx1 && by0 <= by1) {
+          rows = by1 - by0 + 1;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            R.ox[k][tid] = s.ox[k]; R.oy[k][tid] = s.oy[k]; R.ax[k][tid] = s.ax[k]; R.ay[k][tid] = s.ay[k];
+          }
+          R.d[0][tid] = s.d0; R.d[1][tid] = s.d1; R.d[2][tid] = s.d2; R.rden[tid] = s.rden;
+          R.meta[tid] = (s.tl[0] ? 1 : 0) | (s.tl[1] ? 2 : 0) | (s.tl[2] ? 4 : 0) | ((bx0 - x_lo) << 3) |
+                        ((bx1 - x_lo) << 8) | ((by0 - y_lo) << 13);
+          R.tri[tid] = f;
         }
       }
     }
+    // block-wide exclusive scan of `rows`
+    int inc = rows;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    int woff = 0;
+#pragma unroll
+    for (int w = 0; w < kRasterThreads / 32; ++w) woff += (w < wid) ? warp_tot[w] : 0;
+    R.prefix[tid] = woff + inc - rows;
+    if (tid == kRasterThreads - 1) R.prefix[kRasterThreads] = woff + inc;
+    __syncthreads();
+    const int total = R.prefix[kRasterThreads];
+
+    for (int item = tid; item < total; item += kRasterThreads) {
+      // owner = largest slot with prefix[slot] <= item (slots with zero rows are skipped naturally)
+      int lo = 0, hi = kRasterThreads;
+#pragma unroll
+      for (int it = 0; it < 7; ++it) {  // log2(128)
+        const int mid = (lo + hi) >> 1;
+        if (R.prefix[mid] <= item) lo = mid; else hi = mid;
+      }
+      const int sl = lo;
+      const int meta = R.meta[sl];
+      const int ly = ((meta >> 13) & 31) + (item - R.prefix[sl]);
+      int xs = (meta >> 3) & 31, xe = (meta >> 8) & 31;
+      const float ox[3] = {R.ox[0][sl], R.ox[1][sl], R.ox[2][sl]};
+      const float ax[3] = {R.ax[0][sl], R.ax[1][sl], R.ax[2][sl]};
+      const float ay[3] = {R.ay[0][sl], R.ay[1][sl], R.ay[2][sl]};
+      const bool tl[3] = {(meta & 1) != 0, (meta & 2) != 0, (meta & 4) != 0};
+      const float py = (float)(y_lo + ly);
+      float row[3], dy_max = 1.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float dy = sub_rn(py, R.oy[k][sl]);
+        row[k] = mul_rn(dy, ax[k]);
+        dy_max = fmaxf(dy_max, fabsf(dy));
+      }
+      int gxs = x_lo + xs, gxe = x_lo + xe;
+      row_span(ox, ax, ay, row, dy_max, gxs, gxe);
+      if (gxs > gxe) continue;
+      const float rden = R.rden[sl], d0 = R.d[0][sl], d1 = R.d[1][sl], d2 = R.d[2][sl];
+      const unsigned long long f = (unsigned long long)(uint32_t)R.tri[sl];
+      unsigned long long* zrow = zbuf + (ly << kTileLog) - x_lo;
+      for (int x = gxs; x <= gxe; ++x) {
+        uint32_t db;
+        if (sample(ox, ay, tl, rden, d0, d1, d2, (float)x, row, db))
+          atomicMin(zrow + x, ((unsigned long long)db << 32) | f);  // (:155-161)
+      }
+    }
   }
+  __syncthreads();
 
   // (2) large triangles of this image: whole CTA cooperates on each one
   const uint32_t nlarge = large_count[n];
@@ -285,7 +379,7 @@ __global__ void __launch_bounds__(kRasterThreads) raster_tiles_kernel(
       float row[3];
       row_terms(s, (float)y, row);
       uint32_t db;
-      if (sample(s, (float)x, row, row, db)) {
+      if (sample(s, (float)x, row, db)) {
         const unsigned long long packed = ((unsigned long long)db << 32) | (uint32_t)f;
         atomicMin(&zbuf[((y - y_lo) << kTileLog) + (x - x_lo)], packed);
       }
@@ -348,7 +442,7 @@ __global__ void __launch_bounds__(256) raster_atomic_kernel(RasterArgs a, int64_
     row_terms(s, (float)y, row);
     for (int x = s.bx0; x <= s.bx1; ++x) {
       uint32_t db;
-      if (sample(s, (float)x, row, row, db))
+      if (sample(s, (float)x, row, db))
         atomicMin(img + (int64_t)y * a.W + x, ((unsigned long long)db << 32) | (uint32_t)f);
     }
   }
@@ -456,7 +550,8 @@ extern "C" int drtk_b200_rasterize(const float* v, const int64_t* v_strides, con
                                                  large_count, large_list);
     DRTK_CHECK_LAUNCH();
   }
-  raster_tiles_kernel<<<(unsigned)w.M, kRasterThreads, 0, stream>>>(
+  if (N > 65535 || a.tilesY > 65535) return DRTK_B200_EUNSUPPORTED;
+  raster_tiles_kernel<<<dim3((unsigned)a.tilesX, (unsigned)a.tilesY, (unsigned)N), kRasterThreads, 0, stream>>>(
       a, tile_count, tile_offset, tile_list, large_count, large_list, depth_img, index_img);
   DRTK_CHECK_LAUNCH();
   return 0;

@@ -71,16 +71,17 @@ __device__ __forceinline__ PixOut shade(const TriVerts& t, float px, float py) {
 template <bool VEC>
 __global__ void __launch_bounds__(256) render_fwd_kernel(RenderArgs a, float* __restrict__ depth_img,
                                                          float* __restrict__ bary_img) {
-  const int64_t HW = (int64_t)a.H * a.W;
+  // blockIdx.y = image; 32-bit pixel arithmetic inside an image (host guarantees H*W < 2^31)
+  const int HW = a.H * a.W;
+  const int n = blockIdx.y;
+  const int32_t* ibase = a.index_img + (int64_t)n * a.is.s0;
+  float* bbase = bary_img + (int64_t)n * 3 * HW;
+  float* dbase = depth_img + (int64_t)n * HW;
   if (VEC) {
-    const int64_t nquads = (int64_t)a.N * HW / 4;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads;
-         q += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t pix = q * 4;
-      const int n = (int)(pix / HW);
-      const int64_t rem = pix - (int64_t)n * HW;
-      const int h = (int)(rem / a.W), w = (int)(rem - (int64_t)h * a.W);
-      const int4 id = ldg_stream_i4(a.index_img + (int64_t)n * a.is.s0 + (int64_t)h * a.is.s1 + w);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < HW / 4; q += gridDim.x * blockDim.x) {
+      const int rem = q * 4;
+      const int h = rem / a.W, w = rem - h * a.W;
+      const int4 id = ldg_stream_i4(ibase + (int64_t)h * a.is.s1 + w);
       const int ids[4] = {id.x, id.y, id.z, id.w};
       float o0[4], o1[4], o2[4], od[4];
       TriVerts tv;
@@ -95,28 +96,24 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderArgs a, float* __
           o0[j] = 0.f; o1[j] = 0.f; o2[j] = 0.f; od[j] = 0.f;  // (:110-115)
         }
       }
-      float* bp = bary_img + (int64_t)n * 3 * HW + rem;
+      float* bp = bbase + rem;
       stg_stream_f4(bp, make_float4(o0[0], o0[1], o0[2], o0[3]));
       stg_stream_f4(bp + HW, make_float4(o1[0], o1[1], o1[2], o1[3]));
-      stg_stream_f4(bp + 2 * HW, make_float4(o2[0], o2[1], o2[2], o2[3]));
-      stg_stream_f4(depth_img + pix, make_float4(od[0], od[1], od[2], od[3]));
+      stg_stream_f4(bp + 2 * (int64_t)HW, make_float4(o2[0], o2[1], o2[2], o2[3]));
+      stg_stream_f4(dbase + rem, make_float4(od[0], od[1], od[2], od[3]));
     }
   } else {
-    const int64_t npix = (int64_t)a.N * HW;
-    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
-         pix += (int64_t)gridDim.x * blockDim.x) {
-      const int n = (int)(pix / HW);
-      const int64_t rem = pix - (int64_t)n * HW;
-      const int h = (int)(rem / a.W), w = (int)(rem - (int64_t)h * a.W);
-      const int id = a.index_img[(int64_t)n * a.is.s0 + (int64_t)h * a.is.s1 + (int64_t)w * a.is.s2];
-      float* bp = bary_img + (int64_t)n * 3 * HW + rem;
+    for (int rem = blockIdx.x * blockDim.x + threadIdx.x; rem < HW; rem += gridDim.x * blockDim.x) {
+      const int h = rem / a.W, w = rem - h * a.W;
+      const int id = ibase[(int64_t)h * a.is.s1 + (int64_t)w * a.is.s2];
+      float* bp = bbase + rem;
       if (id != -1) {
         TriVerts tv;
         load_tri(a, n, id, tv);
         const PixOut p = shade(tv, (float)w, (float)h);
-        bp[0] = p.b0; bp[HW] = p.b1; bp[2 * HW] = p.b2; depth_img[pix] = p.depth;
+        bp[0] = p.b0; bp[HW] = p.b1; bp[2 * (int64_t)HW] = p.b2; dbase[rem] = p.depth;
       } else {
-        bp[0] = 0.f; bp[HW] = 0.f; bp[2 * HW] = 0.f; depth_img[pix] = 0.f;
+        bp[0] = 0.f; bp[HW] = 0.f; bp[2 * (int64_t)HW] = 0.f; dbase[rem] = 0.f;
       }
     }
   }
@@ -133,20 +130,18 @@ struct RenderBwdArgs {
 // One thread per pixel; a warp covers 32 consecutive pixels of one image row segment.
 __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs b, float* __restrict__ grad_v) {
   const RenderArgs& a = b.r;
-  const int64_t HW = (int64_t)a.H * a.W;
-  const int64_t npix = (int64_t)a.N * HW;
+  const int HW = a.H * a.W;  // blockIdx.y = image, 32-bit pixel arithmetic inside it
   const int lane = threadIdx.x & 31;
-  const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = pix < npix;
-  int n = 0, h = 0, w = 0, id = -1;
+  const int rem = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = rem < HW;
+  const int n = blockIdx.y;
+  int h = 0, w = 0, id = -1;
   if (in_range) {
-    n = (int)(pix / HW);
-    const int64_t rem = pix - (int64_t)n * HW;
-    h = (int)(rem / a.W); w = (int)(rem - (int64_t)h * a.W);
+    h = rem / a.W; w = rem - h * a.W;
     id = a.index_img[(int64_t)n * a.is.s0 + (int64_t)h * a.is.s1 + (int64_t)w * a.is.s2];
   }
-  // key of the run: (image, triangle); -1 lanes never match their neighbours' valid keys
-  const int64_t key = (id == -1) ? (int64_t)-1 - lane : ((int64_t)n << 32) | (uint32_t)id;
+  // key of a run: the triangle id (a block never spans two images); -1 lanes get unique keys
+  const int key = (id == -1) ? (-2 - lane) : id;
   if (__all_sync(0xffffffffu, id == -1)) return;
 
   float g[9];  // dL/d(p0.x, p0.y, z0, p1.x, p1.y, z1, p2.x, p2.y, z2)
@@ -203,8 +198,8 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs b, float*
   }
 
   // segmented reduction over runs of equal (image, triangle)
-  const int64_t key_up = __shfl_up_sync(0xffffffffu, key, 1);
-  const int64_t key_dn = __shfl_down_sync(0xffffffffu, key, 1);
+  const int key_up = __shfl_up_sync(0xffffffffu, key, 1);
+  const int key_dn = __shfl_down_sync(0xffffffffu, key, 1);
   const bool head = (lane == 0) || (key_up != key);
   const bool tail = (lane == 31) || (key_dn != key);
   const unsigned tail_mask = __ballot_sync(0xffffffffu, tail);
@@ -246,12 +241,12 @@ extern "C" int drtk_b200_render_forward(const float* v, const int64_t* v_strides
   a.index_img = index_img; a.is = make3(index_strides);
   a.N = (int)N; a.V = (int)V; a.F = (int)F; a.H = (int)H; a.W = (int)W;
   const bool vec = VecOk::image(index_img, W, a.is.s2, a.is.s1, a.is.s0);
-  if (vec) {
-    // persistent-style grid: a multiple of the SM count, 8 CTAs of 256 threads per SM
-    render_fwd_kernel<true><<<grid_for(N * H * W / 4, 256, 8), 256, 0, stream>>>(a, depth_img, bary_img);
-  } else {
-    render_fwd_kernel<false><<<grid_for(N * H * W, 256, 8), 256, 0, stream>>>(a, depth_img, bary_img);
-  }
+  if (H * W >= (int64_t)0x7FFFFFF0 || N > 65535) return DRTK_B200_EUNSUPPORTED;
+  // grid.y = image; grid.x sized so that the whole grid is ~8 CTAs of 256 threads per SM
+  const int64_t items = vec ? H * W / 4 : H * W;
+  const unsigned gx = grid_for(items, 256, (int)((8 + N - 1) / N > 0 ? (8 + N - 1) / N : 1));
+  if (vec) render_fwd_kernel<true><<<dim3(gx, (unsigned)N), 256, 0, stream>>>(a, depth_img, bary_img);
+  else render_fwd_kernel<false><<<dim3(gx, (unsigned)N), 256, 0, stream>>>(a, depth_img, bary_img);
   DRTK_CHECK_LAUNCH();
   return 0;
 }
@@ -279,7 +274,8 @@ extern "C" int drtk_b200_render_backward(const float* v, const int64_t* v_stride
   b.r.N = (int)N; b.r.V = (int)V; b.r.F = (int)F; b.r.H = (int)H; b.r.W = (int)W;
   b.grad_depth = grad_depth; b.gds = grad_depth ? make3(grad_depth_strides) : Strides3{0, 0, 0};
   b.grad_bary = grad_bary; b.gbs = grad_bary ? make4(grad_bary_strides) : Strides4{0, 0, 0, 0};
-  render_bwd_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(b, grad_v);
+  if (H * W >= (int64_t)0x7FFFFFF0 || N > 65535) return DRTK_B200_EUNSUPPORTED;
+  render_bwd_kernel<<<dim3((unsigned)((H * W + 255) / 256), (unsigned)N), 256, 0, stream>>>(b, grad_v);
   DRTK_CHECK_LAUNCH();
   return 0;
 }
