@@ -173,7 +173,7 @@ constexpr int kEHSlots = (kETW + 1) * kETH;                     // horizontal pa
 constexpr int kEVSlots = kETW * (kETH + 1);                     // vertical pairs:   centres y0-1 .. y0+TH-1
 constexpr int kESlots = kEHSlots + kEVSlots;
 
-__global__ void __launch_bounds__(kEThreads, 3) edge_grad_tile_kernel(EdgeArgs a, float* __restrict__ out) {
+__global__ void __launch_bounds__(kEThreads, 4) edge_grad_tile_kernel(EdgeArgs a, float* __restrict__ out) {
   __shared__ int ids[kEIH * kEIW];
   __shared__ int jobs[kESlots];
   __shared__ int njobs;

@@ -252,7 +252,8 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(InterpBwdArgs b, float*
 //     inside a tile is harmless: sums are per triangle.
 //   phase B (bary grads): thread = 2 (or 4) consecutive pixels; dot products of the staged gradients
 //     with the three attribute rows (LDG.128 row gathers, shared by neighbouring pixels of a triangle).
-constexpr int kBwdThreads = 512;
+constexpr int kBwdThreads = 512;               // consumer threads (16 warps)
+constexpr int kBwdBlock = kBwdThreads + 32;     // + one producer warp that only issues bulk copies
 constexpr int kBwdStages = 2;
 
 template <int LPW> struct BwdTileCfg { static constexpr int TP = (LPW == 16) ? 1024 : 2048; };
@@ -270,7 +271,8 @@ struct BwdStage {
 template <int LPW>
 struct BwdTileSmem {
   BwdStage<LPW> st[kBwdStages];
-  unsigned long long full[kBwdStages];
+  unsigned long long full[kBwdStages];   // producer -> consumers: tile landed (transaction barrier)
+  unsigned long long empty[kBwdStages];  // consumers -> producer: every warp is done reading the stage
 };
 
 // Phase A of the tiled backward for one walker lane (see the kernel comment).  Kept out of line so
@@ -279,16 +281,20 @@ struct BwdTileSmem {
 //   gp: this lane's channel plane; ip/bp: index and bary planes of the stage (bary plane pitch TP)
 //   vg: vertex-gradient table of this image, already offset by this lane's channel
 //   vib: vi rows of this image; vs1/vs2 element strides of vi (row, corner)
-template <int TP>
+// NOTE: it must be entered from CONVERGENT control flow with a warp-uniform trip count: uniform-datapath
+// instructions cannot be issued from divergent code, and a divergent entry makes the compiler keep the
+// global-memory descriptor in vector registers and R2UR it before every LDG/REDG (measured: 14 % of all
+// executed instructions).  Tail tiles are therefore padded with index -1 instead of shortening the loop.
+template <int TP, int SEG>
 __device__ __noinline__ void walk_runs(const float* __restrict__ gp, const int* __restrict__ ip,
-                                       const float* __restrict__ bp, int xs, int xe, float* vg,
+                                       const float* __restrict__ bp, int xs, float* vg,
                                        const int32_t* __restrict__ vib, int vs1, int vs2, unsigned Cs,
                                        bool c_on) {
   int cur = -1;
   unsigned v0 = 0, v1 = 0, v2 = 0;  // vertex ids of the current run
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll 1
-  for (int x = xs; x < xe; x += 4) {
+  for (int x = xs; x < xs + SEG; x += 4) {
     const float4 gq = *reinterpret_cast<const float4*>(gp + x);
     const int4 iq = *reinterpret_cast<const int4*>(ip + x);
     const float4 p0q = *reinterpret_cast<const float4*>(bp + x);
@@ -331,7 +337,7 @@ __device__ __noinline__ void walk_runs(const float* __restrict__ gp, const int* 
 }
 
 template <int LPW, bool NEED_VERT, bool NEED_BARY, bool AVEC>
-__global__ void __launch_bounds__(kBwdThreads, 1)
+__global__ void __launch_bounds__(kBwdBlock, 1)
 interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __restrict__ bary_grad,
                        int tiles_per_img, int64_t num_tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -342,7 +348,10 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
   const int tid = threadIdx.x, lane = tid & 31;
   const int HW = a.H * a.W;  // < 2^31 guaranteed by the host
   if (tid == 0) {
-    for (int s = 0; s < kBwdStages; ++s) mbar_init(reinterpret_cast<uint64_t*>(&S.full[s]), 1);
+    for (int s = 0; s < kBwdStages; ++s) {
+      mbar_init(reinterpret_cast<uint64_t*>(&S.full[s]), 1);
+      mbar_init(reinterpret_cast<uint64_t*>(&S.empty[s]), kBwdThreads / 32);  // one arrival per consumer warp
+    }
     mbar_fence_init();
   }
   __syncthreads();
@@ -351,7 +360,13 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
   const int64_t my_tiles = (num_tiles > blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int64_t n_items = my_tiles * nchunks;
 
-  auto issue = [&](int64_t item) {  // executed by warp 0 only
+  // Executed by one lane of a dedicated producer warp: bulk copies take warp-uniform operands (UBLKCP).
+  // The warp role is made warp-uniform with a shuffle broadcast (the CUTLASS canonical_warp_idx idiom)
+  // so that the role branch is uniform and the consumers' code stays in CONVERGENT control flow: behind
+  // a thread-dependent branch, or with UBLKCP code inside the consumers' loop, the compiler keeps the
+  // global-memory descriptor in vector registers and R2URs it before every LDG/REDG (measured: 14 %
+  // of all executed instructions).
+  auto issue = [&](int64_t item) {
     const int s = (int)(item & 1);
     const int64_t tile = blockIdx.x + (item / nchunks) * gridDim.x;
     const int chunk = (int)(item % nchunks);
@@ -362,30 +377,30 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
     const int ncopies = nc + (NEED_VERT ? 3 : 0) + 1;
     uint64_t* bar = reinterpret_cast<uint64_t*>(&S.full[s]);
     BwdStage<LPW>& st = S.st[s];
-    if (lane == 0) {
-      fence_proxy_async_smem();
-      mbar_arrive_expect_tx(bar, (uint32_t)ncopies * (uint32_t)npx * 4u);
+    const uint32_t bytes = (uint32_t)npx * 4u;
+    fence_proxy_async_smem();
+    mbar_arrive_expect_tx(bar, (uint32_t)ncopies * bytes);
+    const float* gsrc = b.grad_out + (int64_t)n * b.gs.s0 + (int64_t)c0 * b.gs.s1 + p0;
+    for (int i = 0; i < nc; ++i) bulk_g2s(st.g + i * PITCH, gsrc + (int64_t)i * b.gs.s1, bytes, bar);
+    if (NEED_VERT) {
+      const float* bsrc = a.bary + (int64_t)n * a.bs.s0 + p0;
+      for (int k = 0; k < 3; ++k) bulk_g2s(st.bary + k * TP, bsrc + (int64_t)k * a.bs.s1, bytes, bar);
     }
-    __syncwarp();
-    if (lane < ncopies) {
-      const void* src;
-      void* dst;
-      if (lane < nc) {
-        src = b.grad_out + (int64_t)n * b.gs.s0 + (int64_t)(c0 + lane) * b.gs.s1 + p0;
-        dst = st.g + lane * PITCH;
-      } else if (NEED_VERT && lane < nc + 3) {
-        src = a.bary + (int64_t)n * a.bs.s0 + (int64_t)(lane - nc) * a.bs.s1 + p0;
-        dst = st.bary + (lane - nc) * TP;
-      } else {
-        src = a.index_img + (int64_t)n * a.is.s0 + p0;
-        dst = st.idx;
-      }
-      bulk_g2s(dst, src, (uint32_t)npx * 4u, bar);
-    }
+    bulk_g2s(st.idx, a.index_img + (int64_t)n * a.is.s0 + p0, bytes, bar);
   };
 
-  if (tid < 32 && n_items > 0) issue(0);
-  uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
+  const int warp_role = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
+  if (warp_role == kBwdThreads / 32) {  // ---- producer warp ----
+    if (lane == 0) {
+      for (int64_t item = 0; item < n_items; ++item) {
+        if (item >= kBwdStages)  // wait until the consumers released this stage (its previous use)
+          mbar_wait(reinterpret_cast<uint64_t*>(&S.empty[item & 1]), (uint32_t)((item / kBwdStages - 1) & 1));
+        issue(item);
+      }
+    }
+    return;
+  }
+  uint32_t phase_bits = 0;  // bit s = parity to wait for on full[s]
 
   // phase-B state of the current tile (a thread owns the same PPT pixels across channel passes)
   constexpr int PPT = TP / kBwdThreads;  // 2 (TP 1024) or 4 (TP 2048) consecutive pixels per thread
@@ -393,7 +408,6 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
 
   for (int64_t item = 0; item < n_items; ++item) {
     const int s = (int)(item & 1);
-    if (tid < 32 && item + 1 < n_items) issue(item + 1);  // stage s^1 was released by the barrier below
     const int64_t tile = blockIdx.x + (item / nchunks) * gridDim.x;
     const int chunk = (int)(item % nchunks);
     const int n = (int)(tile / tiles_per_img);
@@ -403,19 +417,20 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
     BwdStage<LPW>& st = S.st[s];
     mbar_wait(reinterpret_cast<uint64_t*>(&S.full[s]), (phase_bits >> s) & 1u);
     phase_bits ^= (1u << s);
+    if (npx < TP) {  // last tile of an image (warp-uniform): pad with "no triangle" so loops keep full length
+      for (int i = npx + tid; i < TP; i += kBwdThreads) st.idx[i] = -1;
+      asm volatile("bar.sync 1, %0;" :: "n"(kBwdThreads) : "memory");  // consumers only (producer warp excluded)
+    }
 
     // ---- phase A: vertex-attribute gradients ----
     if (NEED_VERT) {
       constexpr int WALKERS = kBwdThreads / LPW;
       constexpr int SEG = TP / WALKERS;  // pixels per walker (32 / 32 / 16 for LPW 16 / 8 / 4)
       const int walker = tid / LPW, c = tid - walker * LPW;
-      const int xs = walker * SEG, xe = min(xs + SEG, npx);
-      if (xs < xe) {
-        const bool c_on = c < nc;
-        walk_runs<TP>(st.g + (c_on ? c : 0) * PITCH, st.idx, st.bary, xs, xe,
-                      vert_grad + (int64_t)n * a.V * a.C + c0 + (c_on ? c : 0),
-                      a.vi + (int64_t)n * a.vis.s0, (int)a.vis.s1, (int)a.vis.s2, (unsigned)a.C, c_on);
-      }
+      const bool c_on = c < nc;
+      walk_runs<TP, SEG>(st.g + (c_on ? c : 0) * PITCH, st.idx, st.bary, walker * SEG,
+                         vert_grad + (int64_t)n * a.V * a.C + c0 + (c_on ? c : 0),
+                         a.vi + (int64_t)n * a.vis.s0, (int)a.vis.s1, (int)a.vis.s2, (unsigned)a.C, c_on);
     }
 
     // ---- phase B: barycentric gradients: thread = PPT consecutive pixels, all channels ----
@@ -425,7 +440,7 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
 #pragma unroll
         for (int j = 0; j < PPT; ++j) gb[j][0] = gb[j][1] = gb[j][2] = 0.f;
       }
-      if (x < npx) {
+      {
         int qid[PPT], qv[PPT][3];
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
@@ -440,8 +455,16 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
           }
         }
         const float* an = a.attr + (int64_t)n * a.as.s0 + (int64_t)c0 * a.as.s2;
+        const float* r0[PPT], *r1[PPT], *r2[PPT];  // attribute rows of each pixel's three vertices
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          r0[j] = an + (int64_t)qv[j][0] * a.as.s1;
+          r1[j] = an + (int64_t)qv[j][1] * a.as.s1;
+          r2[j] = an + (int64_t)qv[j][2] * a.as.s1;
+        }
         const float* gq_base = st.g + x;
         if (AVEC) {
+#pragma unroll 1
           for (int cc = 0; cc < nc; cc += 4) {
             float gq[4][PPT];
 #pragma unroll
@@ -449,38 +472,41 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
 #pragma unroll
               for (int j = 0; j < PPT; ++j) gq[k][j] = gq_base[(cc + k) * PITCH + j];
             }
-            float4 A0, A1, A2;
+            float4 A0 = make_float4(0.f, 0.f, 0.f, 0.f), A1 = A0, A2 = A0;
 #pragma unroll
             for (int j = 0; j < PPT; ++j) {
-              if (qid[j] < 0) continue;
-              if (!(j > 0 && qid[j] == qid[j - 1])) {
-                A0 = *reinterpret_cast<const float4*>(an + (int64_t)qv[j][0] * a.as.s1 + cc);
-                A1 = *reinterpret_cast<const float4*>(an + (int64_t)qv[j][1] * a.as.s1 + cc);
-                A2 = *reinterpret_cast<const float4*>(an + (int64_t)qv[j][2] * a.as.s1 + cc);
+              if (qid[j] >= 0 && !(j > 0 && qid[j] == qid[j - 1])) {
+                A0 = *reinterpret_cast<const float4*>(r0[j] + cc);
+                A1 = *reinterpret_cast<const float4*>(r1[j] + cc);
+                A2 = *reinterpret_cast<const float4*>(r2[j] + cc);
               }
+              // empty pixels (qid < 0) keep accumulating into a slot that is zeroed at the store
               gb[j][0] += gq[0][j] * A0.x + gq[1][j] * A0.y + gq[2][j] * A0.z + gq[3][j] * A0.w;
               gb[j][1] += gq[0][j] * A1.x + gq[1][j] * A1.y + gq[2][j] * A1.z + gq[3][j] * A1.w;
               gb[j][2] += gq[0][j] * A2.x + gq[1][j] * A2.y + gq[2][j] * A2.z + gq[3][j] * A2.w;
             }
           }
         } else {
+#pragma unroll 1
           for (int cc = 0; cc < nc; ++cc) {
             float A0 = 0.f, A1 = 0.f, A2 = 0.f;
 #pragma unroll
             for (int j = 0; j < PPT; ++j) {
-              if (qid[j] < 0) continue;
-              if (!(j > 0 && qid[j] == qid[j - 1])) {
-                A0 = an[(int64_t)qv[j][0] * a.as.s1 + (int64_t)cc * a.as.s2];
-                A1 = an[(int64_t)qv[j][1] * a.as.s1 + (int64_t)cc * a.as.s2];
-                A2 = an[(int64_t)qv[j][2] * a.as.s1 + (int64_t)cc * a.as.s2];
+              if (qid[j] >= 0 && !(j > 0 && qid[j] == qid[j - 1])) {
+                A0 = r0[j][(int64_t)cc * a.as.s2];
+                A1 = r1[j][(int64_t)cc * a.as.s2];
+                A2 = r2[j][(int64_t)cc * a.as.s2];
               }
               const float g = gq_base[cc * PITCH + j];
               gb[j][0] += g * A0; gb[j][1] += g * A1; gb[j][2] += g * A2;
             }
           }
         }
-        if (chunk == nchunks - 1) {
+        if (chunk == nchunks - 1 && x < npx) {
           float* gp = bary_grad + (int64_t)n * 3 * HW + p0 + x;
+#pragma unroll
+          for (int j = 0; j < PPT; ++j)
+            if (qid[j] < 0) gb[j][0] = gb[j][1] = gb[j][2] = 0.f;  // (:282-297) zeros where empty
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             if (PPT == 2) *reinterpret_cast<float2*>(gp + (int64_t)k * HW) = make_float2(gb[0][k], gb[PPT - 1][k]);
@@ -489,7 +515,8 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
         }
       }
     }
-    __syncthreads();  // every reader of stage s is done: the next issue may overwrite it
+    __syncwarp();  // this warp is done reading stage s: let the producer refill it
+    if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&S.empty[s]));
   }
 }
 
@@ -592,7 +619,7 @@ extern "C" int drtk_b200_interpolate_backward(
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { rc2 = (int)e; return; }
       const unsigned grid = (unsigned)(num_tiles < kNumSMs ? num_tiles : kNumSMs);  // one persistent CTA per SM
-      kern<<<grid, kBwdThreads, smem, stream>>>(b, vert_attributes_grad, bary_img_grad, tiles_per_img, num_tiles);
+      kern<<<grid, kBwdBlock, smem, stream>>>(b, vert_attributes_grad, bary_img_grad, tiles_per_img, num_tiles);
     };
 #define DRTK_BWD_TILE(LPW)                                                                                  \
     do {                                                                                                    \
