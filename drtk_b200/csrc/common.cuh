@@ -89,6 +89,10 @@ __device__ __forceinline__ void stg_stream_i4(int32_t* p, int4 v) {
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+}
+
 // fire-and-forget float reduction (REDG.ADD.F32)
 __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");

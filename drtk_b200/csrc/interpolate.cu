@@ -253,7 +253,10 @@ __global__ void __launch_bounds__(256) interp_bwd_kernel(InterpBwdArgs b, float*
 //   phase B (bary grads): thread = 2 (or 4) consecutive pixels; dot products of the staged gradients
 //     with the three attribute rows (LDG.128 row gathers, shared by neighbouring pixels of a triangle).
 constexpr int kBwdThreads = 512;               // consumer threads (16 warps)
-constexpr int kBwdBlock = kBwdThreads + 32;     // + one producer warp that only issues bulk copies
+constexpr int kBwdProducers = 4;                // producer warps: a bulk copy costs its issuing thread ~0.145 us
+                                                // whatever its size (profiles/r01_microbench_bulk_copy.txt), so the
+                                                // ~20 copies of a tile are spread over 4 issuing warps
+constexpr int kBwdBlock = kBwdThreads + 32 * kBwdProducers;
 constexpr int kBwdStages = 2;
 
 template <int LPW> struct BwdTileCfg { static constexpr int TP = (LPW == 16) ? 1024 : 2048; };
@@ -349,7 +352,7 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
   const int HW = a.H * a.W;  // < 2^31 guaranteed by the host
   if (tid == 0) {
     for (int s = 0; s < kBwdStages; ++s) {
-      mbar_init(reinterpret_cast<uint64_t*>(&S.full[s]), 1);
+      mbar_init(reinterpret_cast<uint64_t*>(&S.full[s]), kBwdProducers);
       mbar_init(reinterpret_cast<uint64_t*>(&S.empty[s]), kBwdThreads / 32);  // one arrival per consumer warp
     }
     mbar_fence_init();
@@ -366,7 +369,7 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
   // a thread-dependent branch, or with UBLKCP code inside the consumers' loop, the compiler keeps the
   // global-memory descriptor in vector registers and R2URs it before every LDG/REDG (measured: 14 %
   // of all executed instructions).
-  auto issue = [&](int64_t item) {
+  auto issue = [&](int64_t item, int pw) {  // producer warp pw issues copies pw, pw + kBwdProducers, ...
     const int s = (int)(item & 1);
     const int64_t tile = blockIdx.x + (item / nchunks) * gridDim.x;
     const int chunk = (int)(item % nchunks);
@@ -378,24 +381,34 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
     uint64_t* bar = reinterpret_cast<uint64_t*>(&S.full[s]);
     BwdStage<LPW>& st = S.st[s];
     const uint32_t bytes = (uint32_t)npx * 4u;
+    const int mine = (ncopies - pw + kBwdProducers - 1) / kBwdProducers;
     fence_proxy_async_smem();
-    mbar_arrive_expect_tx(bar, (uint32_t)ncopies * bytes);
-    const float* gsrc = b.grad_out + (int64_t)n * b.gs.s0 + (int64_t)c0 * b.gs.s1 + p0;
-    for (int i = 0; i < nc; ++i) bulk_g2s(st.g + i * PITCH, gsrc + (int64_t)i * b.gs.s1, bytes, bar);
-    if (NEED_VERT) {
-      const float* bsrc = a.bary + (int64_t)n * a.bs.s0 + p0;
-      for (int k = 0; k < 3; ++k) bulk_g2s(st.bary + k * TP, bsrc + (int64_t)k * a.bs.s1, bytes, bar);
+    mbar_arrive_expect_tx(bar, (uint32_t)mine * bytes);  // one arrival per producer warp, also when mine == 0
+    for (int k = pw; k < ncopies; k += kBwdProducers) {
+      const void* src;
+      void* dst;
+      if (k < nc) {
+        src = b.grad_out + (int64_t)n * b.gs.s0 + (int64_t)(c0 + k) * b.gs.s1 + p0;
+        dst = st.g + k * PITCH;
+      } else if (NEED_VERT && k < nc + 3) {
+        src = a.bary + (int64_t)n * a.bs.s0 + (int64_t)(k - nc) * a.bs.s1 + p0;
+        dst = st.bary + (k - nc) * TP;
+      } else {
+        src = a.index_img + (int64_t)n * a.is.s0 + p0;
+        dst = st.idx;
+      }
+      bulk_g2s(dst, src, bytes, bar);
     }
-    bulk_g2s(st.idx, a.index_img + (int64_t)n * a.is.s0 + p0, bytes, bar);
   };
 
   const int warp_role = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
-  if (warp_role == kBwdThreads / 32) {  // ---- producer warp ----
+  if (warp_role >= kBwdThreads / 32) {  // ---- producer warps ----
     if (lane == 0) {
+      const int pw = warp_role - kBwdThreads / 32;
       for (int64_t item = 0; item < n_items; ++item) {
         if (item >= kBwdStages)  // wait until the consumers released this stage (its previous use)
           mbar_wait(reinterpret_cast<uint64_t*>(&S.empty[item & 1]), (uint32_t)((item / kBwdStages - 1) & 1));
-        issue(item);
+        issue(item, pw);
       }
     }
     return;

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kRasterThreads) raster_tiles_kernel(
     int32_t* __restrict__ index_img) {
   __shared__ unsigned long long zbuf[kTilePix];
   __shared__ TileRecs R;
-  __shared__ int warp_tot[kRasterThreads / 32];
+  __shared__ __align__(16) int warp_tot[kRasterThreads / 32];  // aligned: its vector load must not straddle R.prefix
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = blockIdx.z;
   const int64_t t = ((int64_t)n * a.tilesY + tile_y) * a.tilesX + tile_x;
