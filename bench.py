@@ -50,7 +50,9 @@ ALGO_BYTES_PER_PX = {
     "rasterize": lambda C: 8,                       # index + depth written
     "render_fwd": lambda C: 20,                     # index read; depth + 3 bary written
     "interpolate_fwd": lambda C: 16 + 4 * C,        # index + bary read; C planes written
-    "edge_grad_bwd": lambda C: 4 + 8 * C + 12,      # index, img, grad_out read; 3 planes written
+    "edge_grad_bwd": lambda C: 4 + 12,              # index read; 3 planes written.  img / grad_out (8C B/px in the
+                                                    # reference, which reads them at every triangle change) are only
+                                                    # read for pairs that contribute -- data dependent, not compulsory
     "interpolate_bwd_vpix": lambda C: 16 + 12,      # C=3 conduit: index + bary + 3 grad planes read
     "interpolate_bwd": lambda C: 16 + 4 * C + 12,   # index + bary + C grad planes read; bary grad written
     "render_bwd": lambda C: 4 + 12,                 # index + grad_bary read (grad_depth undefined here)
@@ -79,7 +81,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -181,6 +183,16 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE line (the JSON): everything else that libraries print there (e.g. NCCL's
+    # version banner) is routed to stderr at the file-descriptor level
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -200,7 +212,7 @@ def main():
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     assert th.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
@@ -327,7 +339,7 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get(dom)
+                traffic = json.load(f).get(dom)  # ncu dram bytes per launch of the dominant kernel
         roofline = {"bound": "hbm", "kernel": dom, "achieved": breakdown[dom]["GBps"], "peak": peak, "unit": "GB/s",
                     "frac": breakdown[dom]["frac_of_peak"], "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX[dom](C_ATTR) * npx_rank}
@@ -370,7 +382,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         r = run_reference_cpu(cfg, steps=3, warmup=1)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
