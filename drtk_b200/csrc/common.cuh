@@ -111,12 +111,25 @@ __device__ __forceinline__ void seg_reduce_to_head(float (&val)[NV], unsigned ta
   // distance from this lane to the end of its run
   const unsigned above = tail_mask >> lane;          // bit0 = own tail flag
   const int dist_to_tail = __ffs(above) - 1;         // >= 0 because lane 31 is always a tail
+  // runs are short on fine meshes (~5 px): when no run of this warp is longer than 8 lanes, three
+  // shuffle steps suffice (warp-uniform choice)
+  const bool short_runs = __all_sync(0xffffffffu, dist_to_tail < 8);
 #pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
+  for (int off = 1; off < 8; off <<= 1) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const float o = __shfl_down_sync(0xffffffffu, val[i], off);
       if (off <= dist_to_tail) val[i] += o;
+    }
+  }
+  if (!short_runs) {
+#pragma unroll
+    for (int off = 8; off < 32; off <<= 1) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float o = __shfl_down_sync(0xffffffffu, val[i], off);
+        if (off <= dist_to_tail) val[i] += o;
+      }
     }
   }
 }

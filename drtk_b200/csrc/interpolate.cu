@@ -46,7 +46,7 @@ __device__ __forceinline__ float sweep_x(int w, int W) { return ((float)w * 2.0f
 // VEC: index/bary images dense & 16-B aligned along W (4 px per thread).
 // AVEC: attribute rows 16-B aligned and C % 4 == 0 (float4 gathers).
 template <bool VEC, bool AVEC>
-__global__ void __launch_bounds__(256, 3) interp_fwd_kernel(InterpArgs a, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) interp_fwd_kernel(InterpArgs a, float* __restrict__ out) {
   const int HW = a.H * a.W;  // blockIdx.y = image, 32-bit pixel arithmetic inside it
   constexpr int PX = VEC ? 4 : 1;
   const int n = blockIdx.y;
@@ -407,7 +407,7 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
       const int pw = warp_role - kBwdThreads / 32;
       for (int64_t item = 0; item < n_items; ++item) {
         if (item >= kBwdStages)  // wait until the consumers released this stage (its previous use)
-          mbar_wait(reinterpret_cast<uint64_t*>(&S.empty[item & 1]), (uint32_t)((item / kBwdStages - 1) & 1));
+          mbar_wait_backoff(reinterpret_cast<uint64_t*>(&S.empty[item & 1]), (uint32_t)((item / kBwdStages - 1) & 1), 400);
         issue(item, pw);
       }
     }
@@ -428,7 +428,7 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
     const int npx = min(TP, HW - p0);
     const int c0 = chunk * LPW, nc = min(LPW, a.C - c0);
     BwdStage<LPW>& st = S.st[s];
-    mbar_wait(reinterpret_cast<uint64_t*>(&S.full[s]), (phase_bits >> s) & 1u);
+    mbar_wait_backoff(reinterpret_cast<uint64_t*>(&S.full[s]), (phase_bits >> s) & 1u, 40);
     phase_bits ^= (1u << s);
     if (npx < TP) {  // last tile of an image (warp-uniform): pad with "no triangle" so loops keep full length
       for (int i = npx + tid; i < TP; i += kBwdThreads) st.idx[i] = -1;
@@ -577,13 +577,9 @@ extern "C" int drtk_b200_interpolate_forward(const float* vert_attributes, const
   const bool avec = (C % 4 == 0) && a.as.s2 == 1 && (a.as.s1 % 4 == 0) && (a.as.s0 % 4 == 0) &&
                     (reinterpret_cast<uintptr_t>(vert_attributes) % 16 == 0);
   if (H * W >= (int64_t)0x7FFFFFF0 || N > 65535) return DRTK_B200_EUNSUPPORTED;
-  // grid-stride kernel at 3 resident CTAs / SM (80 registers): one wave of 148 * 3 CTAs over all images
-  const int64_t items = vec ? H * W / 4 : H * W;
-  int64_t gx64 = ((int64_t)kNumSMs * 3 + N - 1) / N;
-  const int64_t need = (items + 255) / 256;
-  if (gx64 > need) gx64 = need;
-  if (gx64 < 1) gx64 = 1;
-  const dim3 grid((unsigned)gx64, (unsigned)N);
+  const int per_img = (int)((8 + N - 1) / N);
+  const unsigned gx = grid_for(vec ? H * W / 4 : H * W, 256, per_img > 0 ? per_img : 1);
+  const dim3 grid(gx, (unsigned)N);
   if (vec && avec) interp_fwd_kernel<true, true><<<grid, 256, 0, stream>>>(a, out);
   else if (vec) interp_fwd_kernel<true, false><<<grid, 256, 0, stream>>>(a, out);
   else if (avec) interp_fwd_kernel<false, true><<<grid, 256, 0, stream>>>(a, out);

@@ -39,6 +39,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// Waiting with back-off: a polling warp competes for issue slots with the warps doing the work
+// (measured: 4 producer warps spinning on their "stage free" barrier executed as many instructions as
+// the 16 consumer warps), so sleep between polls.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-B aligned; completes `bytes`
 // transaction bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
