@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kEThreads, 4) edge_grad_tile_kernel(EdgeArgs a
   __shared__ int ids[kEIH * kEIW];
   __shared__ int jobs[kESlots];
   __shared__ int njobs;
-  __shared__ float slot[8][kETW * kETH];  // 0 cx, 1 czx, 2 cy, 3 czy (centre roles); 4 rx, 5 rz, 6 dy, 7 dz
+  __shared__ __align__(16) float slot[8][kETW * kETH];  // 0 cx, 1 czx, 2 cy, 3 czy (centre roles); 4 rx, 5 rz, 6 dy, 7 dz
   const int tid = threadIdx.x, lane = tid & 31;
   const int n = blockIdx.z;
   const int x0 = blockIdx.x * kETW, y0 = blockIdx.y * kETH;
@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(kEThreads, 4) edge_grad_tile_kernel(EdgeArgs a
     const int x = x0 - 1 + lx, y = y0 - 1 + ly;
     ids[i] = (x >= 0 && x < a.W && y >= 0 && y < a.H) ? ip[(int64_t)y * a.is.s1 + (int64_t)x * a.is.s2] : -2;
   }
-  for (int i = tid; i < 8 * kETW * kETH; i += kEThreads) (&slot[0][0])[i] = 0.f;
+  for (int i = tid; i < 8 * kETW * kETH / 4; i += kEThreads)  // 16 KB of slots, 128-bit stores
+    reinterpret_cast<float4*>(&slot[0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) njobs = 0;
   __syncthreads();
 

@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(256) interp_fwd_kernel(InterpArgs a, float* __
     float* op = out + (int64_t)n * a.C * HW + rem;  // 64-bit: n*C*HW may exceed 2^31
 
     if (AVEC) {
+      // row offsets in 32 bits (host guarantees V * row_stride < 2^31 on this path)
+      const unsigned rs = (unsigned)a.as.s1;
+#pragma unroll
+      for (int j = 0; j < PX; ++j) { i0[j] *= rs; i1[j] *= rs; i2[j] *= rs; }
       for (int c = 0; c < a.C; c += 4) {
         float r[4][PX];  // [channel][pixel]
         float4 A0, A1, A2;
@@ -89,9 +93,9 @@ __global__ void __launch_bounds__(256) interp_fwd_kernel(InterpArgs a, float* __
         for (int j = 0; j < PX; ++j) {
           if (ids[j] != -1) {
             if (!(j > 0 && ids[j] == ids[j - 1])) {
-              A0 = *reinterpret_cast<const float4*>(an + (int64_t)i0[j] * a.as.s1 + c);
-              A1 = *reinterpret_cast<const float4*>(an + (int64_t)i1[j] * a.as.s1 + c);
-              A2 = *reinterpret_cast<const float4*>(an + (int64_t)i2[j] * a.as.s1 + c);
+              A0 = *reinterpret_cast<const float4*>(an + (unsigned)(i0[j] + c));
+              A1 = *reinterpret_cast<const float4*>(an + (unsigned)(i1[j] + c));
+              A2 = *reinterpret_cast<const float4*>(an + (unsigned)(i2[j] + c));
             }
             r[0][j] = A0.x * b0[j] + A1.x * b1[j] + A2.x * b2[j];  // (:102)
             r[1][j] = A0.y * b0[j] + A1.y * b1[j] + A2.y * b2[j];
@@ -574,8 +578,8 @@ extern "C" int drtk_b200_interpolate_forward(const float* vert_attributes, const
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool vec = VecOk::image(index_img, W, a.is.s2, a.is.s1, a.is.s0) &&
                    VecOk::image(bary_img, W, a.bs.s3, a.bs.s2, a.bs.s1, a.bs.s0);
-  const bool avec = (C % 4 == 0) && a.as.s2 == 1 && (a.as.s1 % 4 == 0) && (a.as.s0 % 4 == 0) &&
-                    (reinterpret_cast<uintptr_t>(vert_attributes) % 16 == 0);
+  const bool avec = (C % 4 == 0) && a.as.s2 == 1 && (a.as.s1 % 4 == 0) && (a.as.s0 % 4 == 0) && a.as.s1 > 0 &&
+                    (V * a.as.s1 + C < (int64_t)0x7FFFFFF0) && (reinterpret_cast<uintptr_t>(vert_attributes) % 16 == 0);
   if (H * W >= (int64_t)0x7FFFFFF0 || N > 65535) return DRTK_B200_EUNSUPPORTED;
   const int per_img = (int)((8 + N - 1) / N);
   const unsigned gx = grid_for(vec ? H * W / 4 : H * W, 256, per_img > 0 ? per_img : 1);

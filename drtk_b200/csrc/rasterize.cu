@@ -130,7 +130,11 @@ __device__ __forceinline__ bool sample(const float (&ox)[3], const float (&ay)[3
   const float b1 = fma_rn(-ay[1], sub_rn(px, ox[1]), row[1]);
   const float b2 = fma_rn(-ay[2], sub_rn(px, ox[2]), row[2]);
   if (!(b0 >= 0.f && b1 >= 0.f && b2 >= 0.f)) return false;
-  if ((b0 == 0.f && !tl[0]) || (b1 == 0.f && !tl[1]) || (b2 == 0.f && !tl[2])) return false;
+  // top-left rule: only reached by samples exactly on an edge (one min3 + compare guards the three
+  // equality tests; all b are >= 0 and not NaN here, so min == 0 <=> some b == 0)
+  if (fminf(fminf(b0, b1), b2) == 0.f) {
+    if ((b0 == 0.f && !tl[0]) || (b1 == 0.f && !tl[1]) || (b2 == 0.f && !tl[2])) return false;
+  }
   const float c0 = mul_rn(b0, rden), c1 = mul_rn(b1, rden), c2 = mul_rn(b2, rden);
   // dot(d_inv, bary) as compiled: FMUL(b1,d1) -> FFMA(b0,d0,.) -> FFMA(b2,d2,.)
   const float inv = fma_rn(c2, d2, fma_rn(c0, d0, mul_rn(c1, d1)));
