@@ -50,16 +50,17 @@ ALGO_BYTES_PER_PX = {
     "rasterize": lambda C: 8,                       # index + depth written
     "render_fwd": lambda C: 20,                     # index read; depth + 3 bary written
     "interpolate_fwd": lambda C: 16 + 4 * C,        # index + bary read; C planes written
-    "edge_grad_bwd": lambda C: 4 + 12,              # index read; 3 planes written.  img / grad_out (8C B/px in the
-                                                    # reference, which reads them at every triangle change) are only
-                                                    # read for pairs that contribute -- data dependent, not compulsory
-    "interpolate_bwd_vpix": lambda C: 16 + 12,      # C=3 conduit: index + bary + 3 grad planes read
+    # edge_grad: img / grad_out (8C B/px in the reference, which reads them at every triangle change) are
+    # only read for pairs that contribute -- data dependent, not compulsory.  The bench pipeline registers
+    # no hook, so the fused kernel runs; the two-kernel plan (hook) costs 16 + 28 B/px instead.
+    "edge_grad_bwd_fused": lambda C: 4,             # index read; the sparse non-zero gradients go straight to
+                                                    # grad_v_pix (REDs into an L2-resident [N,V,3] table)
     "interpolate_bwd": lambda C: 16 + 4 * C + 12,   # index + bary + C grad planes read; bary grad written
     "render_bwd": lambda C: 4 + 12,                 # index + grad_bary read (grad_depth undefined here)
 }
 # CUDA kernels launched by libdrtk_b200.so per op call (memsets are driver operations, not counted)
-KERNELS = {"rasterize": 4, "render_fwd": 1, "interpolate_fwd": 1, "edge_grad_bwd": 1,
-           "interpolate_bwd_vpix": 1, "interpolate_bwd": 1, "render_bwd": 1}
+KERNELS = {"rasterize": 4, "render_fwd": 1, "interpolate_fwd": 1, "edge_grad_bwd_fused": 1,
+           "interpolate_bwd": 1, "render_bwd": 1}
 
 
 def load_peaks():
@@ -259,8 +260,8 @@ def main():
     wrap("render_forward", lambda *a, **k: "render_fwd")
     wrap("render_backward", lambda *a, **k: "render_bwd")
     wrap("interpolate_forward", lambda *a, **k: "interpolate_fwd")
-    wrap("interpolate_backward", lambda g, attr, *a, **k: "interpolate_bwd_vpix" if attr.shape[2] == 3 else "interpolate_bwd")
-    wrap("edge_grad_backward", lambda *a, **k: "edge_grad_bwd")
+    wrap("interpolate_backward", lambda *a, **k: "interpolate_bwd")
+    wrap("edge_grad_backward_fused", lambda *a, **k: "edge_grad_bwd_fused")
 
     def step_device():
         v_d.grad = None

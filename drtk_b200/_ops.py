@@ -103,6 +103,7 @@ def render_forward(v, vi, index_img):
 
 def render_backward(v, vi, index_img, grad_depth, grad_bary):
     """-> grad_v [N,V,3] (src/render/render_kernel.cu:382-436). grad_* may be None (= zeros)."""
+    _chk(vi.dim() == 3 and vi.size(2) == 3, "drtk_b200: internal launchers expect vi as [N,F,3]")
     lib = _lib.load()
     N, V, F = v.size(0), v.size(1), vi.size(1)
     H, W = index_img.size(1), index_img.size(2)
@@ -170,6 +171,7 @@ def interpolate_forward(attr, vi, index_img, bary_img):
 def interpolate_backward(grad_out, attr, vi, index_img, bary_img, need_attr_grad, need_bary_grad):
     """-> (vert_attributes_grad [N,V,C] | None, bary_img_grad [N,3,H,W] | None)
     (src/interpolate/interpolate_kernel.cu:642-697)."""
+    _chk(vi.dim() == 3 and vi.size(2) == 3, "drtk_b200: internal launchers expect vi as [N,F,3]")
     lib = _lib.load()
     N, V, C = attr.shape
     F = vi.size(1)
@@ -210,6 +212,7 @@ def check_edge_grad(v_pix, v_pix_img, vi, img, index_img):
 
 def edge_grad_backward(v_pix, img, index_img, vi, grad_output, max_dp_dr):
     """-> grad_v_pix_img [N,3,H,W] (src/edge_grad/edge_grad_kernel.cu:475-506)."""
+    _chk(vi.dim() == 3 and vi.size(2) == 3, "drtk_b200: internal launchers expect vi as [N,F,3]")
     lib = _lib.load()
     v_pix = _f32(v_pix, "edge_grad_estimator", "v_pix")
     img = _f32(img, "edge_grad_estimator", "img")
@@ -224,5 +227,28 @@ def edge_grad_backward(v_pix, img, index_img, vi, grad_output, max_dp_dr):
             _lib.strides(index_img), _lib.ptr(vi), _lib.strides(vi), _lib.ptr(grad_output),
             _lib.strides(grad_output), N, V, F, C, H, W, float(max_dp_dr), _lib.ptr(out),
             _stream(v_pix.device))
+    _lib.check(rc, "edge_grad_estimator() backward")
+    return out
+
+
+def edge_grad_backward_fused(v_pix, img, index_img, vi, grad_output, bary_img, max_dp_dr):
+    """-> grad_v_pix [N,V,3]: edge_grad backward followed by the C = 3 interpolate backward of the conduit,
+    in one kernel (no [N,3,H,W] gradient image)."""
+    _chk(vi.dim() == 3 and vi.size(2) == 3, "drtk_b200: internal launchers expect vi as [N,F,3]")
+    lib = _lib.load()
+    v_pix = _f32(v_pix, "edge_grad_estimator", "v_pix")
+    img = _f32(img, "edge_grad_estimator", "img")
+    grad_output = _f32(grad_output, "edge_grad_estimator", "grad_output")
+    bary_img = _f32(bary_img, "edge_grad_estimator", "bary_img")
+    N, V = v_pix.size(0), v_pix.size(1)
+    F = vi.size(1)
+    C, H, W = img.size(1), img.size(2), img.size(3)
+    with torch.cuda.device(v_pix.device):
+        out = torch.empty((N, V, 3), dtype=torch.float32, device=v_pix.device)
+        rc = lib.drtk_b200_edge_grad_backward_fused(
+            _lib.ptr(v_pix), _lib.strides(v_pix), _lib.ptr(img), _lib.strides(img), _lib.ptr(index_img),
+            _lib.strides(index_img), _lib.ptr(vi), _lib.strides(vi), _lib.ptr(grad_output),
+            _lib.strides(grad_output), _lib.ptr(bary_img), _lib.strides(bary_img), N, V, F, C, H, W,
+            float(max_dp_dr), _lib.ptr(out), _stream(v_pix.device))
     _lib.check(rc, "edge_grad_estimator() backward")
     return out

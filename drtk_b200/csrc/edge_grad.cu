@@ -173,7 +173,18 @@ constexpr int kEHSlots = (kETW + 1) * kETH;                     // horizontal pa
 constexpr int kEVSlots = kETW * (kETH + 1);                     // vertical pairs:   centres y0-1 .. y0+TH-1
 constexpr int kESlots = kEHSlots + kEVSlots;
 
-__global__ void __launch_bounds__(kEThreads, 4) edge_grad_tile_kernel(EdgeArgs a, float* __restrict__ out) {
+// FUSED: instead of writing dL/d(v_pix_img), push it straight through the backward of
+// interpolate(v_pix, vi, index_img, bary) (drtk/edge_grad_estimator.py:172): grad_v_pix[vi_k] += g * bary_k.
+// The estimator's gradient image is sparse (non-zero only at silhouettes / overlaps / intersections), so
+// a handful of direct REDs replaces a 12 B/px write, a 28 B/px re-read and a whole reduction kernel.
+struct FusedArgs {
+  const float* bary;
+  Strides4 bs;
+  float* grad_v;  // [N,V,3], zero-filled by the launcher
+};
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kEThreads, 4) edge_grad_tile_kernel(EdgeArgs a, float* __restrict__ out, FusedArgs fz) {
   __shared__ int ids[kEIH * kEIW];
   __shared__ int jobs[kESlots];
   __shared__ int njobs;
@@ -246,16 +257,31 @@ __global__ void __launch_bounds__(kEThreads, 4) edge_grad_tile_kernel(EdgeArgs a
 
   // ---- phase 3: combine and store (negated sums, :431-445) ----
   const int64_t HW = (int64_t)a.H * a.W;
-  float* ob = out + (int64_t)n * 3 * HW;
+  float* ob = FUSED ? nullptr : out + (int64_t)n * 3 * HW;
   for (int i = tid; i < kETW * kETH; i += kEThreads) {
     const int ly = i / kETW, lx = i - ly * kETW;
     const int x = x0 + lx, y = y0 + ly;
     if (x >= a.W || y >= a.H) continue;
-    const float gx = slot[0][i] + slot[4][i];
-    const float gy = slot[2][i] + slot[6][i];
-    const float gz = (slot[1][i] + slot[3][i]) + slot[5][i] + slot[7][i];
-    float* o = ob + (int64_t)y * a.W + x;
-    o[0] = -gx; o[HW] = -gy; o[2 * HW] = -gz;
+    const float gx = -(slot[0][i] + slot[4][i]);
+    const float gy = -(slot[2][i] + slot[6][i]);
+    const float gz = -((slot[1][i] + slot[3][i]) + slot[5][i] + slot[7][i]);
+    if (!FUSED) {
+      float* o = ob + (int64_t)y * a.W + x;
+      o[0] = gx; o[HW] = gy; o[2 * HW] = gz;
+    } else if (gx != 0.f || gy != 0.f || gz != 0.f) {
+      const int id = ids[(ly + 1) * kEIW + lx + 1];
+      if (id != -1) {  // interpolate's backward only touches covered pixels
+        const int32_t* vip = a.vi + (int64_t)n * a.vis.s0 + (int64_t)id * a.vis.s1;
+        const float* bp = fz.bary + (int64_t)n * fz.bs.s0 + (int64_t)y * fz.bs.s2 + (int64_t)x * fz.bs.s3;
+        float* gv = fz.grad_v + (int64_t)n * a.V * 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float bk = bp[(int64_t)k * fz.bs.s1];
+          float* q = gv + (int64_t)vip[(int64_t)k * a.vis.s2] * 3;
+          red_add(q + 0, gx * bk); red_add(q + 1, gy * bk); red_add(q + 2, gz * bk);
+        }
+      }
+    }
   }
 }
 
@@ -264,6 +290,37 @@ __global__ void __launch_bounds__(kEThreads, 4) edge_grad_tile_kernel(EdgeArgs a
 
 using namespace drtk;
 
+static int edge_launch(const float* v_pix, const int64_t* v_strides, const float* img, const int64_t* img_strides,
+                       const int32_t* index_img, const int64_t* index_strides, const int32_t* vi,
+                       const int64_t* vi_strides, const float* grad_output, const int64_t* grad_output_strides,
+                       int64_t N, int64_t V, int64_t F, int64_t C, int64_t H, int64_t W, float max_dp_dr,
+                       float* grad_v_pix_img, const float* bary_img, const int64_t* bary_strides, float* grad_v_pix,
+                       void* stream_) {
+  if (N < 0 || C < 0 || H < 0 || W < 0) return DRTK_B200_EINVAL;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool fused = grad_v_pix != nullptr;
+  if (fused && N * V > 0) DRTK_CUDA(cudaMemsetAsync(grad_v_pix, 0, sizeof(float) * (size_t)(N * V * 3), stream));
+  const int64_t npix = N * H * W;
+  if (npix == 0) return 0;
+  if (!v_pix || !img || !index_img || !vi || !grad_output || (!fused && !grad_v_pix_img) || (fused && !bary_img))
+    return DRTK_B200_EINVAL;
+  if (H > (1 << 30) || W > (1 << 30) || N > 65535) return DRTK_B200_EUNSUPPORTED;
+  EdgeArgs a;
+  a.v = v_pix; a.vs = make3(v_strides); a.img = img; a.ims = make4(img_strides);
+  a.index_img = index_img; a.is = make3(index_strides); a.vi = vi; a.vis = make3(vi_strides);
+  a.go = grad_output; a.gs = make4(grad_output_strides);
+  a.N = (int)N; a.V = (int)V; a.F = (int)F; a.C = (int)C; a.H = (int)H; a.W = (int)W;
+  a.max_dp_dr = max_dp_dr;
+  const dim3 grid((unsigned)((W + kETW - 1) / kETW), (unsigned)((H + kETH - 1) / kETH), (unsigned)N);
+  if (grid.y > 65535) return DRTK_B200_EUNSUPPORTED;
+  FusedArgs fz;
+  fz.bary = bary_img; fz.bs = fused ? make4(bary_strides) : Strides4{0, 0, 0, 0}; fz.grad_v = grad_v_pix;
+  if (fused) edge_grad_tile_kernel<true><<<grid, kEThreads, 0, stream>>>(a, nullptr, fz);
+  else edge_grad_tile_kernel<false><<<grid, kEThreads, 0, stream>>>(a, grad_v_pix_img, fz);
+  DRTK_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int drtk_b200_edge_grad_backward(const float* v_pix, const int64_t* v_strides, const float* img,
                                             const int64_t* img_strides, const int32_t* index_img,
                                             const int64_t* index_strides, const int32_t* vi,
@@ -271,22 +328,20 @@ extern "C" int drtk_b200_edge_grad_backward(const float* v_pix, const int64_t* v
                                             const int64_t* grad_output_strides, int64_t N, int64_t V,
                                             int64_t F, int64_t C, int64_t H, int64_t W, float max_dp_dr,
                                             float* grad_v_pix_img, void* stream_) {
-  if (N < 0 || C < 0 || H < 0 || W < 0) return DRTK_B200_EINVAL;
-  const int64_t npix = N * H * W;
-  if (npix == 0) return 0;
-  if (!v_pix || !img || !index_img || !vi || !grad_output || !grad_v_pix_img) return DRTK_B200_EINVAL;
-  if (H > (1 << 30) || W > (1 << 30) || N > (1 << 30)) return DRTK_B200_EUNSUPPORTED;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  EdgeArgs a;
-  a.v = v_pix; a.vs = make3(v_strides); a.img = img; a.ims = make4(img_strides);
-  a.index_img = index_img; a.is = make3(index_strides); a.vi = vi; a.vis = make3(vi_strides);
-  a.go = grad_output; a.gs = make4(grad_output_strides);
-  a.N = (int)N; a.V = (int)V; a.F = (int)F; a.C = (int)C; a.H = (int)H; a.W = (int)W;
-  a.max_dp_dr = max_dp_dr;
-  if (N > 65535) return DRTK_B200_EUNSUPPORTED;
-  const dim3 grid((unsigned)((W + kETW - 1) / kETW), (unsigned)((H + kETH - 1) / kETH), (unsigned)N);
-  if (grid.y > 65535) return DRTK_B200_EUNSUPPORTED;
-  edge_grad_tile_kernel<<<grid, kEThreads, 0, stream>>>(a, grad_v_pix_img);
-  DRTK_CHECK_LAUNCH();
-  return 0;
+  return edge_launch(v_pix, v_strides, img, img_strides, index_img, index_strides, vi, vi_strides, grad_output,
+                     grad_output_strides, N, V, F, C, H, W, max_dp_dr, grad_v_pix_img, nullptr, nullptr, nullptr,
+                     stream_);
+}
+
+extern "C" int drtk_b200_edge_grad_backward_fused(
+    const float* v_pix, const int64_t* v_strides, const float* img, const int64_t* img_strides,
+    const int32_t* index_img, const int64_t* index_strides, const int32_t* vi, const int64_t* vi_strides,
+    const float* grad_output, const int64_t* grad_output_strides, const float* bary_img,
+    const int64_t* bary_strides, int64_t N, int64_t V, int64_t F, int64_t C, int64_t H, int64_t W,
+    float max_dp_dr, float* grad_v_pix, void* stream_) {
+  if (!grad_v_pix && N * V > 0) return DRTK_B200_EINVAL;
+  if (N * V == 0) return 0;
+  return edge_launch(v_pix, v_strides, img, img_strides, index_img, index_strides, vi, vi_strides, grad_output,
+                     grad_output_strides, N, V, F, C, H, W, max_dp_dr, nullptr, bary_img, bary_strides, grad_v_pix,
+                     stream_);
 }

@@ -481,7 +481,7 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
         }
         const float* gq_base = st.g + x;
         if (AVEC) {
-#pragma unroll 1
+#pragma unroll(PPT == 2 ? 2 : 1)  // two channel groups in flight: their LDG.128 (L2 hits) overlap
           for (int cc = 0; cc < nc; cc += 4) {
             float gq[4][PPT];
 #pragma unroll
@@ -489,15 +489,16 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
 #pragma unroll
               for (int j = 0; j < PPT; ++j) gq[k][j] = gq_base[(cc + k) * PITCH + j];
             }
-            float4 A0 = make_float4(0.f, 0.f, 0.f, 0.f), A1 = A0, A2 = A0;
+            float4 A0, A1, A2;
 #pragma unroll
             for (int j = 0; j < PPT; ++j) {
-              if (qid[j] >= 0 && !(j > 0 && qid[j] == qid[j - 1])) {
+              // rows are (re)loaded only when the triangle changes; empty pixels (qid < 0) use the rows of
+              // vertex 0 and accumulate into a slot that is zeroed at the store
+              if (j == 0 || qid[j] != qid[j - 1]) {
                 A0 = *reinterpret_cast<const float4*>(r0[j] + cc);
                 A1 = *reinterpret_cast<const float4*>(r1[j] + cc);
                 A2 = *reinterpret_cast<const float4*>(r2[j] + cc);
               }
-              // empty pixels (qid < 0) keep accumulating into a slot that is zeroed at the store
               gb[j][0] += gq[0][j] * A0.x + gq[1][j] * A0.y + gq[2][j] * A0.z + gq[3][j] * A0.w;
               gb[j][1] += gq[0][j] * A1.x + gq[1][j] * A1.y + gq[2][j] * A1.z + gq[3][j] * A1.w;
               gb[j][2] += gq[0][j] * A2.x + gq[1][j] * A2.y + gq[2][j] * A2.z + gq[3][j] * A2.w;
@@ -506,10 +507,10 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
         } else {
 #pragma unroll 1
           for (int cc = 0; cc < nc; ++cc) {
-            float A0 = 0.f, A1 = 0.f, A2 = 0.f;
+            float A0, A1, A2;
 #pragma unroll
             for (int j = 0; j < PPT; ++j) {
-              if (qid[j] >= 0 && !(j > 0 && qid[j] == qid[j - 1])) {
+              if (j == 0 || qid[j] != qid[j - 1]) {
                 A0 = r0[j][(int64_t)cc * a.as.s2];
                 A1 = r1[j][(int64_t)cc * a.as.s2];
                 A2 = r2[j][(int64_t)cc * a.as.s2];
@@ -610,6 +611,10 @@ extern "C" int drtk_b200_interpolate_backward(
     return 0;
   }
   if (!grad_out || !grad_out_strides) return DRTK_B200_EINVAL;
+  if (V == 0 || F == 0) {  // nothing can be covered: all gradients are zero (index_img must be all -1)
+    if (bary_img_grad) DRTK_CUDA(cudaMemsetAsync(bary_img_grad, 0, sizeof(float) * (size_t)(npix * 3), stream));
+    return 0;
+  }
   InterpBwdArgs b;
   const int rc = fill_args(b.f, vert_attributes, attr_strides, vi, vi_strides, index_img, index_strides,
                            bary_img, bary_strides, N, V, F, C, H, W);

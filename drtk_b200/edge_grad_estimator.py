@@ -14,6 +14,12 @@ of `EdgeGradEstimatorFunction` (`src/edge_grad/edge_grad_module.cpp:116-170`):
 * `v_pix_img_hook` is registered on `v_pix_img` and therefore observes (or replaces) the
   [N,3,H,W] gradient image, exactly like the reference.
 
+Two launch plans produce that gradient:
+* with a `v_pix_img_hook` (the image must exist): edge_grad kernel -> [N,3,H,W] -> C = 3
+  interpolate-backward kernel, as in the reference;
+* without a hook: ONE fused kernel (`drtk_b200_edge_grad_backward_fused`) that multiplies each non-zero
+  pixel gradient by the pixel's barycentrics and REDs it into grad_v_pix directly.  Same sums, no image.
+
 Difference to the reference (forward only, values identical): the reference materialises
 `v_pix_img = interpolate(v_pix, ...)` although its values are never read
 (`drtk/edge_grad_estimator.py:168-172`, 28 B/px of traffic).  Here the conduit's forward returns a
@@ -69,6 +75,30 @@ class _EdgeGradFn(th.autograd.Function):
         return None, grad_v_pix_img, None, grad_output, None, None
 
 
+class _EdgeGradFusedFn(th.autograd.Function):
+    """edge_grad_estimator op + conduit in one node (no hook => nobody can observe v_pix_img)."""
+
+    @staticmethod
+    def forward(ctx, v_pix, vi, bary_img, img, index_img, max_dp_dr):
+        _ops.check_edge_grad(v_pix, bary_img, vi, img, index_img)
+        _ops._check_interp(v_pix, vi, index_img, bary_img)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(v_pix, img, index_img, vi, bary_img)
+        ctx.max_dp_dr = float(max_dp_dr)
+        return img.view_as(img)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if grad_output is None:
+            return None, None, None, None, None, None
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, grad_output, None, None
+        v_pix, img, index_img, vi, bary_img = ctx.saved_tensors
+        gv = _ops.edge_grad_backward_fused(v_pix.detach(), img.detach(), index_img, vi, grad_output,
+                                           bary_img, ctx.max_dp_dr)
+        return gv.to(v_pix.dtype), None, None, grad_output, None, None
+
+
 @th.compiler.disable
 def edge_grad_estimator(
     v_pix: th.Tensor,
@@ -88,6 +118,8 @@ def edge_grad_estimator(
     """
     if vi.ndim == 2:
         vi = vi[None, ...].expand(v_pix.shape[0], -1, -1)
+    if v_pix_img_hook is None:
+        return _EdgeGradFusedFn.apply(v_pix, vi, bary_img.detach(), img, index_img, max_dp_dr)
     v_pix_img = _VPixImgConduit.apply(v_pix, vi, index_img, bary_img.detach())
     out = _EdgeGradFn.apply(v_pix, v_pix_img, vi, img, index_img, max_dp_dr)
     if v_pix_img_hook is not None and v_pix_img.requires_grad:

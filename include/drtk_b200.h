@@ -126,6 +126,22 @@ int drtk_b200_edge_grad_backward(const float* v_pix, const int64_t* v_strides, c
                                  int64_t F, int64_t C, int64_t H, int64_t W, float max_dp_dr,
                                  float* grad_v_pix_img, void* stream);
 
+/* edge_grad backward fused with the backward of the conduit `interpolate(v_pix, vi, index_img,
+ * bary_img.detach())` through which the reference routes dL/d(v_pix_img) to the vertices
+ * (drtk/edge_grad_estimator.py:165-180, src/edge_grad/edge_grad_module.cpp:139-169 followed by
+ * interpolate_cuda_backward with C = 3, src/interpolate/interpolate_kernel.cu:642-697).  Used when no
+ * `v_pix_img_hook` needs to see the [N,3,H,W] image.
+ *   bary_img   [N,3,H,W] (strides bary_strides[4])
+ *   grad_v_pix [N,V,3] out, dense; zero-filled by the callee, then accumulated                     */
+int drtk_b200_edge_grad_backward_fused(const float* v_pix, const int64_t* v_strides, const float* img,
+                                       const int64_t* img_strides, const int32_t* index_img,
+                                       const int64_t* index_strides, const int32_t* vi,
+                                       const int64_t* vi_strides, const float* grad_output,
+                                       const int64_t* grad_output_strides, const float* bary_img,
+                                       const int64_t* bary_strides, int64_t N, int64_t V, int64_t F,
+                                       int64_t C, int64_t H, int64_t W, float max_dp_dr,
+                                       float* grad_v_pix, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

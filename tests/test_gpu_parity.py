@@ -372,6 +372,48 @@ def test_pipeline_autograd_golden(name):
     assert_close(npy(attr.grad), g["grad_attr_full"], rtol=2e-5, what="grad_attr (pipeline)")
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_pipeline_autograd_golden_no_hook(name):
+    """Without a hook the fused edge_grad+conduit kernel runs; the vertex gradients are the same."""
+    g = load_golden(name)
+    H, W = map(int, g["HW"])
+    v = cu(g["v"]).requires_grad_(True)
+    attr = cu(g["attr"]).requires_grad_(True)
+    vi = cu(g["vi"])
+    index = drtk_b200.rasterize(v, vi, H, W)
+    depth, bary = drtk_b200.render(v, vi, index)
+    img = drtk_b200.interpolate(attr, vi, index, bary)
+    out = drtk_b200.edge_grad_estimator(v, vi, bary, img, index)
+    assert out.requires_grad and th.equal(out, img)
+    (out * cu(g["w_img"])).sum().backward()
+    assert_close(npy(v.grad), g["grad_v_full"], rtol=2e-5, what="grad_v (fused pipeline)")
+    assert_close(npy(attr.grad), g["grad_attr_full"], rtol=2e-5, what="grad_attr (fused pipeline)")
+
+
+@pytest.mark.parametrize("cfg,N,overdraw,expand_vi", [(3, 2, False, True), (3, 1, True, False), (4, 1, False, True)])
+def test_edge_grad_fused_equals_two_kernel_plan(cfg, N, overdraw, expand_vi):
+    """C-ABI level: drtk_b200_edge_grad_backward_fused == edge_grad_backward -> interpolate_backward(C=3)."""
+    v, vi, H, W = scenes.config_mesh(cfg, N=N, overdraw=overdraw, device=DEV)
+    vi = vi[None].expand(N, -1, -1)  # the _ops launchers take the batched [N,F,3] form
+    if not expand_vi:
+        vi = vi.contiguous()
+    index = drtk_b200.rasterize(v, vi, H, W)
+    _, bary = drtk_b200.render(v, vi, index)
+    attr = scenes.vertex_attributes(N, v.shape[1], 5, seed=3, device=DEV)
+    img = drtk_b200.interpolate(attr, vi, index, bary)
+    go = th.randn(img.shape, device=DEV, generator=th.Generator(device=DEV).manual_seed(11))
+    gimg = _ops.edge_grad_backward(v, img, index, vi, go, 1e4)
+    gv2, _ = _ops.interpolate_backward(gimg, v, vi, index, bary, True, False)
+    gv1 = _ops.edge_grad_backward_fused(v, img, index, vi, go, bary, 1e4)
+    assert float(gv2.abs().max()) > 0
+    assert_close(npy(gv1), npy(gv2), rtol=2e-5, what="fused grad_v_pix")
+    # non-contiguous bary / grad_output strides go through the same kernel
+    bary_nc = bary.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    go_nc = go.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    gv3 = _ops.edge_grad_backward_fused(v, img, index, vi, go_nc, bary_nc, 1e4)
+    assert_close(npy(gv3), npy(gv2), rtol=2e-5, what="fused grad_v_pix (strided)")
+
+
 def test_edge_grad_estimator_autograd_corner_cases():
     g = load_golden("grid_48")
     H, W = map(int, g["HW"])
