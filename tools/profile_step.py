@@ -22,6 +22,6 @@ for _ in range(a.steps):
     _, bary = api.render(vv, vi, index)
     img = api.interpolate(aa, vi, index, bary)
     img = api.edge_grad_estimator(vv, vi, bary, img, index)
-    (img * w).sum().backward()
+    img.backward(gradient=w)
 th.cuda.synchronize()
 print("done")
