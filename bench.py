@@ -60,7 +60,7 @@ ALGO_BYTES_PER_PX = {
 }
 # CUDA kernels launched by libdrtk_b200.so per op call (memsets are driver operations, not counted)
 KERNELS = {"rasterize": 4, "render_fwd": 1, "interpolate_fwd": 1, "edge_grad_bwd_fused": 1,
-           "interpolate_bwd": 1, "render_bwd": 1}
+           "interpolate_bwd": 1, "render_bwd": 3}
 
 
 def load_peaks():

@@ -35,9 +35,10 @@ PROTOTYPES = {
         _INT,
         [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P],
     ),
+    "drtk_b200_render_backward_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "drtk_b200_render_backward": (
         _INT,
-        [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P, _P],
+        [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _SZ, _P],
     ),
     "drtk_b200_interpolate_forward": (
         _INT,

@@ -113,12 +113,14 @@ def render_backward(v, vi, index_img, grad_depth, grad_bary):
         grad_bary = _f32(grad_bary, "render", "grad_bary_img")
     with torch.cuda.device(v.device):
         grad_v = torch.empty((N, V, 3), dtype=torch.float32, device=v.device)
+        nbytes = lib.drtk_b200_render_backward_workspace_bytes(N, V, F)
+        ws = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=v.device)
         rc = lib.drtk_b200_render_backward(
             _lib.ptr(v), _lib.strides(v), _lib.ptr(vi), _lib.strides(vi), _lib.ptr(index_img),
             _lib.strides(index_img), _lib.ptr(grad_depth),
             None if grad_depth is None else _lib.strides(grad_depth), _lib.ptr(grad_bary),
             None if grad_bary is None else _lib.strides(grad_bary), N, V, F, H, W, _lib.ptr(grad_v),
-            _stream(v.device))
+            _lib.ptr(ws), ws.numel(), _stream(v.device))
     _lib.check(rc, "render() backward")
     return grad_v
 

@@ -239,6 +239,153 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs b, float*
   }
 }
 
+// Walker variant of the backward (dense tensors, W % 8 == 0, 16-B aligned planes).
+//   1. tri_table_kernel: one thread per (image, triangle) derives the per-triangle constants of the backward
+//      once and stores them as one 64-B row (4 x 128-bit), so the hot kernel replaces the two-level dependent
+//      gather index -> vi (3 x 4 B) -> v (9 x 4 B) + ~40 setup instructions by four independent LDG.128.
+//   2. render_bwd_walk_kernel: one thread owns EIGHT consecutive pixels of a row, streams them with 128-bit
+//      loads and walks them in order; the nine partial derivatives of a run of equal ids are accumulated in
+//      registers and flushed when the id changes with THREE 128-bit reductions into a [N,V,4]-padded
+//      accumulator (rows 16-B aligned; red.global.add.v4.f32) -- no shuffles, 3 instead of 9 REDs per run.
+//   3. unpad_kernel: [N,V,4] -> grad_v [N,V,3].
+// The per-pixel kernel above spends ~310 thread-instructions per pixel, two thirds of them in the segmented
+// shuffle reduction and in re-deriving the triangle for every pixel.
+constexpr int kWalkPx = 8;
+
+struct RunSetup {  // per-triangle constants of the backward (:186-219 of the reference)
+  float p0x, p0y, v01x, v01y, v02x, v02y, rden, d0, d1, d2, rz0, rz1, rz2;  // rzk = 1/zk^2 (0 when zk was clamped)
+  bool den_clamped;
+  int i0, i1, i2;
+};
+
+// table row: {p0x,p0y,v01x,v01y} {v02x,v02y,rden,d0} {d1,d2,rz1,rz2} {rz0 | sign bit = den_clamped, i0,i1,i2}
+__global__ void __launch_bounds__(256) tri_table_kernel(RenderArgs a, float4* __restrict__ table) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (f >= a.F) return;
+  TriVerts t;
+  load_tri_dense(a.vi + (int64_t)n * a.vis.s0, a.v + (int64_t)n * a.V * 3, f, t);
+  const float v01x = t.p1x - t.p0x, v01y = t.p1y - t.p0y;
+  const float v02x = t.p2x - t.p0x, v02y = t.p2y - t.p0y;
+  const float den_raw = v01x * v02y - v01y * v02x;
+  const float den = epsclamp(den_raw);
+  const float z0e = epsclamp(t.z0), z1e = epsclamp(t.z1), z2e = epsclamp(t.z2);
+  const float rz0 = (z0e != t.z0) ? 0.f : rcp_approx(z0e * z0e);
+  const float rz1 = (z1e != t.z1) ? 0.f : rcp_approx(z1e * z1e);
+  const float rz2 = (z2e != t.z2) ? 0.f : rcp_approx(z2e * z2e);
+  float4* row = table + ((int64_t)n * a.F + f) * 4;
+  row[0] = make_float4(t.p0x, t.p0y, v01x, v01y);
+  row[1] = make_float4(v02x, v02y, rcp_approx(den), rcp_approx(z0e));
+  row[2] = make_float4(rcp_approx(z1e), rcp_approx(z2e), rz1, rz2);
+  row[3] = make_float4(__uint_as_float(__float_as_uint(rz0) | (den != den_raw ? 0x80000000u : 0u)),
+                       __int_as_float(t.i0), __int_as_float(t.i1), __int_as_float(t.i2));
+}
+
+__device__ __forceinline__ void run_setup(const float4* __restrict__ row, RunSetup& r) {
+  const float4 a = __ldg(row), b = __ldg(row + 1), c = __ldg(row + 2), d = __ldg(row + 3);
+  r.p0x = a.x; r.p0y = a.y; r.v01x = a.z; r.v01y = a.w;
+  r.v02x = b.x; r.v02y = b.y; r.rden = b.z; r.d0 = b.w;
+  r.d1 = c.x; r.d2 = c.y; r.rz1 = c.z; r.rz2 = c.w;
+  r.rz0 = fabsf(d.x); r.den_clamped = (__float_as_uint(d.x) >> 31) != 0u;
+  r.i0 = __float_as_int(d.y); r.i1 = __float_as_int(d.z); r.i2 = __float_as_int(d.w);
+}
+
+template <bool HAS_GB, bool HAS_GD>
+__global__ void __launch_bounds__(128) render_bwd_walk_kernel(RenderBwdArgs b, const float4* __restrict__ table,
+                                                              float* __restrict__ gpad) {
+  const RenderArgs& a = b.r;
+  const int HW = a.H * a.W;
+  const int n = blockIdx.y;
+  const int rem = (blockIdx.x * blockDim.x + threadIdx.x) * kWalkPx;
+  if (rem >= HW) return;
+  const int32_t* ip = a.index_img + (int64_t)n * HW + rem;
+  const int4 ia = ldg_stream_i4(ip), ib = ldg_stream_i4(ip + 4);
+  const int ids[kWalkPx] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+  if ((ia.x & ia.y & ia.z & ia.w & ib.x & ib.y & ib.z & ib.w) == -1) return;  // all empty
+  float gb0[kWalkPx], gb1[kWalkPx], gb2[kWalkPx], gdp[kWalkPx];
+  if (HAS_GB) {
+    const float* gp = b.grad_bary + (int64_t)n * 3 * HW + rem;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float4 x = ldg_stream_f4(gp + 4 * q), y = ldg_stream_f4(gp + HW + 4 * q),
+                   z = ldg_stream_f4(gp + 2 * (int64_t)HW + 4 * q);
+      gb0[4 * q] = x.x; gb0[4 * q + 1] = x.y; gb0[4 * q + 2] = x.z; gb0[4 * q + 3] = x.w;
+      gb1[4 * q] = y.x; gb1[4 * q + 1] = y.y; gb1[4 * q + 2] = y.z; gb1[4 * q + 3] = y.w;
+      gb2[4 * q] = z.x; gb2[4 * q + 1] = z.y; gb2[4 * q + 2] = z.z; gb2[4 * q + 3] = z.w;
+    }
+  }
+  if (HAS_GD) {
+    const float* gp = b.grad_depth + (int64_t)n * HW + rem;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float4 x = ldg_stream_f4(gp + 4 * q);
+      gdp[4 * q] = x.x; gdp[4 * q + 1] = x.y; gdp[4 * q + 2] = x.z; gdp[4 * q + 3] = x.w;
+    }
+  }
+  const int h = rem / a.W, w0 = rem - h * a.W;  // W % 8 == 0: the eight pixels share the row
+  const float4* tn = table + (int64_t)n * a.F * 4;
+  float* gvn = gpad + (int64_t)n * a.V * 4;
+
+  RunSetup r;
+  int cur = -1;
+  float acc[9];
+  auto flush = [&]() {
+    red_add_v4(gvn + (int64_t)r.i0 * 4, acc[0], acc[1], acc[2], 0.f);
+    red_add_v4(gvn + (int64_t)r.i1 * 4, acc[3], acc[4], acc[5], 0.f);
+    red_add_v4(gvn + (int64_t)r.i2 * 4, acc[6], acc[7], acc[8], 0.f);
+  };
+#pragma unroll
+  for (int j = 0; j < kWalkPx; ++j) {
+    const int id = ids[j];
+    if (id == -1) continue;
+    if (id != cur) {
+      if (cur != -1) flush();
+      run_setup(tn + (int64_t)id * 4, r);
+      cur = id;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+    }
+    const float qx = (float)(w0 + j) - r.p0x, qy = (float)h - r.p0y;
+    const float b1 = (qx * r.v02y - qy * r.v02x) * r.rden;
+    const float b2 = (qy * r.v01x - qx * r.v01y) * r.rden;
+    const float b0 = 1.f - b1 - b2;
+    const float dinv = r.d0 * b0 + r.d1 * b1 + r.d2 * b2;
+    const float dinv_e = epsclamp(dinv);
+    const float depth = rcp_approx(dinv_e);
+    const float g0 = HAS_GB ? gb0[j] : 0.f, g1 = HAS_GB ? gb1[j] : 0.f, g2 = HAS_GB ? gb2[j] : 0.f;
+    const float gd = HAS_GD ? gdp[j] : 0.f;
+    const float dL_depth = gd + (g0 * r.d0 * b0 + g1 * r.d1 * b1 + g2 * r.d2 * b2);
+    const float dL_dinv = (dinv_e != dinv) ? 0.f : (-dL_depth * rcp_approx(dinv * dinv));
+    const float dLd0 = g0 * b0 * depth + dL_dinv * b0;
+    const float dLd1 = g1 * b1 * depth + dL_dinv * b1;
+    const float dLd2 = g2 * b2 * depth + dL_dinv * b2;
+    acc[2] += -dLd0 * r.rz0; acc[5] += -dLd1 * r.rz1; acc[8] += -dLd2 * r.rz2;
+    const float dLb0 = g0 * r.d0 * depth + dL_dinv * r.d0;
+    const float dLb1 = g1 * r.d1 * depth + dL_dinv * r.d1;
+    const float dLb2 = g2 * r.d2 * depth + dL_dinv * r.d2;
+    const float e1 = (-dLb0 + dLb1) * r.rden, e2 = (-dLb0 + dLb2) * r.rden;
+    const float dL_den = r.den_clamped ? 0.f : -(e1 * b1 + e2 * b2);
+    const float dqx = e1 * r.v02y - e2 * r.v01y, dqy = -e1 * r.v02x + e2 * r.v01x;
+    const float dv02x = -e1 * qy - dL_den * r.v01y, dv02y = e1 * qx + dL_den * r.v01x;
+    const float dv01x = e2 * qy + dL_den * r.v02y, dv01y = -e2 * qx - dL_den * r.v02x;
+    acc[0] += -dv02x - dv01x - dqx; acc[1] += -dv02y - dv01y - dqy;
+    acc[3] += dv01x; acc[4] += dv01y; acc[6] += dv02x; acc[7] += dv02y;
+  }
+  if (cur != -1) flush();
+}
+
+__global__ void __launch_bounds__(256) unpad_kernel(const float4* __restrict__ gpad, float* __restrict__ grad_v, int64_t rows) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float4 g = gpad[i];
+  float* o = grad_v + i * 3;
+  o[0] = g.x; o[1] = g.y; o[2] = g.z;
+}
+
+// workspace of the walker path: the triangle table, then the padded accumulators
+inline size_t walk_table_bytes(int64_t N, int64_t F) { return (size_t)(N * F) * 64; }
+inline size_t walk_gpad_bytes(int64_t N, int64_t V) { return (size_t)(N * V) * 16; }
+
 inline unsigned grid_for(int64_t work_items, int threads, int ctas_per_sm) {
   const int64_t need = (work_items + threads - 1) / threads;
   const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
@@ -275,22 +422,29 @@ extern "C" int drtk_b200_render_forward(const float* v, const int64_t* v_strides
   return 0;
 }
 
+extern "C" size_t drtk_b200_render_backward_workspace_bytes(int64_t N, int64_t V, int64_t F) {
+  if (N <= 0 || V <= 0 || F <= 0) return 0;
+  return walk_table_bytes(N, F) + walk_gpad_bytes(N, V);
+}
+
 extern "C" int drtk_b200_render_backward(const float* v, const int64_t* v_strides, const int32_t* vi,
                                          const int64_t* vi_strides, const int32_t* index_img,
                                          const int64_t* index_strides, const float* grad_depth,
                                          const int64_t* grad_depth_strides, const float* grad_bary,
                                          const int64_t* grad_bary_strides, int64_t N, int64_t V,
-                                         int64_t F, int64_t H, int64_t W, float* grad_v, void* stream_) {
+                                         int64_t F, int64_t H, int64_t W, float* grad_v, void* workspace,
+                                         size_t workspace_bytes, void* stream_) {
   if (N < 0 || V < 0 || H < 0 || W < 0) return DRTK_B200_EINVAL;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (N * V > 0) {
-    if (!grad_v) return DRTK_B200_EINVAL;
-    DRTK_CUDA(cudaMemsetAsync(grad_v, 0, sizeof(float) * (size_t)(N * V * 3), stream));  // (:397)
-  }
+  if (N * V > 0 && !grad_v) return DRTK_B200_EINVAL;
   const int64_t npix = N * H * W;
-  if (npix == 0 || N * V == 0) return 0;
+  const bool trivial = npix == 0 || N * V == 0 || F == 0 || (!grad_depth && !grad_bary);  // zero grad_v
+  const auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  if (trivial) {
+    if (N * V > 0) DRTK_CUDA(cudaMemsetAsync(grad_v, 0, sizeof(float) * (size_t)(N * V * 3), stream));  // (:397)
+    return 0;
+  }
   if (!v || !vi || !index_img) return DRTK_B200_EINVAL;
-  if (!grad_depth && !grad_bary) return 0;  // all-zero upstream gradient -> zero grad_v
   if (H > (1 << 30) || W > (1 << 30) || N > (1 << 30)) return DRTK_B200_EUNSUPPORTED;
   RenderBwdArgs b;
   b.r.v = v; b.r.vs = make3(v_strides); b.r.vi = vi; b.r.vis = make3(vi_strides);
@@ -304,6 +458,23 @@ extern "C" int drtk_b200_render_backward(const float* v, const int64_t* v_stride
                      b.r.vis.s2 == 1 && b.r.vis.s1 == 3 && V * 3 < (int64_t)0x7FFFFFF0 && F * 3 < (int64_t)0x7FFFFFF0 &&
                      (!grad_depth || dense3(b.gds, H, W)) &&
                      (!grad_bary || (b.gbs.s3 == 1 && b.gbs.s2 == W && b.gbs.s1 == H * W && (N == 1 || b.gbs.s0 == 3 * H * W)));
+  if (dense && W % kWalkPx == 0 && al16(index_img) && (!grad_bary || al16(grad_bary)) && (!grad_depth || al16(grad_depth)) &&
+      F <= 65535LL * 256) {
+    const size_t tb = walk_table_bytes(N, F), gb = walk_gpad_bytes(N, V);
+    if (!workspace || workspace_bytes < tb + gb || !al16(workspace)) return DRTK_B200_EWORKSPACE;
+    float4* table = static_cast<float4*>(workspace);
+    float* gpad = reinterpret_cast<float*>(static_cast<char*>(workspace) + tb);
+    DRTK_CUDA(cudaMemsetAsync(gpad, 0, gb, stream));
+    tri_table_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)N), 256, 0, stream>>>(b.r, table);
+    const dim3 wgrid((unsigned)((H * W / kWalkPx + 127) / 128), (unsigned)N);
+    if (grad_bary && grad_depth) render_bwd_walk_kernel<true, true><<<wgrid, 128, 0, stream>>>(b, table, gpad);
+    else if (grad_bary) render_bwd_walk_kernel<true, false><<<wgrid, 128, 0, stream>>>(b, table, gpad);
+    else render_bwd_walk_kernel<false, true><<<wgrid, 128, 0, stream>>>(b, table, gpad);
+    unpad_kernel<<<(unsigned)((N * V + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(gpad), grad_v, N * V);
+    DRTK_CHECK_LAUNCH();
+    return 0;
+  }
+  DRTK_CUDA(cudaMemsetAsync(grad_v, 0, sizeof(float) * (size_t)(N * V * 3), stream));  // (:397)
   const dim3 grid((unsigned)((H * W + 255) / 256), (unsigned)N);
   if (dense) render_bwd_kernel<true><<<grid, 256, 0, stream>>>(b, grad_v);
   else render_bwd_kernel<false><<<grid, 256, 0, stream>>>(b, grad_v);

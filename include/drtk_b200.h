@@ -74,13 +74,18 @@ int drtk_b200_render_forward(const float* v, const int64_t* v_strides, const int
 
 /* render backward -- replaces render_cuda_backward (src/render/render_kernel.cu:382-436).
  *   grad_depth [N,H,W] (may be NULL = zeros), grad_bary [N,3,H,W] (may be NULL = zeros)
- *   grad_v     [N,V,3] f32 out, dense; zero-filled by the callee, then accumulated      */
+ *   grad_v     [N,V,3] f32 out, dense; every element written by the callee
+ *   workspace  16-B aligned scratch of at least drtk_b200_render_backward_workspace_bytes(N,V,F)
+ *              bytes (per-triangle setup table + 16-B padded accumulators of the fast path)       */
+size_t drtk_b200_render_backward_workspace_bytes(int64_t N, int64_t V, int64_t F);
+
 int drtk_b200_render_backward(const float* v, const int64_t* v_strides, const int32_t* vi,
                               const int64_t* vi_strides, const int32_t* index_img,
                               const int64_t* index_strides, const float* grad_depth,
                               const int64_t* grad_depth_strides, const float* grad_bary,
                               const int64_t* grad_bary_strides, int64_t N, int64_t V, int64_t F,
-                              int64_t H, int64_t W, float* grad_v, void* stream);
+                              int64_t H, int64_t W, float* grad_v, void* workspace,
+                              size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * interpolate forward -- replaces interpolate_cuda
