@@ -59,7 +59,7 @@ ALGO_BYTES_PER_PX = {
     "render_bwd": lambda C: 4 + 12,                 # index + grad_bary read (grad_depth undefined here)
 }
 # CUDA kernels launched by libdrtk_b200.so per op call (memsets are driver operations, not counted)
-KERNELS = {"rasterize": 4, "render_fwd": 1, "interpolate_fwd": 1, "edge_grad_bwd_fused": 1,
+KERNELS = {"rasterize": 4, "render_fwd": 1, "interpolate_fwd": 1, "edge_grad_bwd_fused": 2,
            "interpolate_bwd": 1, "render_bwd": 3}
 
 

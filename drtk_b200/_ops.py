@@ -247,10 +247,12 @@ def edge_grad_backward_fused(v_pix, img, index_img, vi, grad_output, bary_img, m
     C, H, W = img.size(1), img.size(2), img.size(3)
     with torch.cuda.device(v_pix.device):
         out = torch.empty((N, V, 3), dtype=torch.float32, device=v_pix.device)
+        nbytes = lib.drtk_b200_edge_grad_backward_fused_workspace_bytes(N, F)
+        ws = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=v_pix.device)
         rc = lib.drtk_b200_edge_grad_backward_fused(
             _lib.ptr(v_pix), _lib.strides(v_pix), _lib.ptr(img), _lib.strides(img), _lib.ptr(index_img),
             _lib.strides(index_img), _lib.ptr(vi), _lib.strides(vi), _lib.ptr(grad_output),
             _lib.strides(grad_output), _lib.ptr(bary_img), _lib.strides(bary_img), N, V, F, C, H, W,
-            float(max_dp_dr), _lib.ptr(out), _stream(v_pix.device))
+            float(max_dp_dr), _lib.ptr(out), _lib.ptr(ws), ws.numel(), _stream(v_pix.device))
     _lib.check(rc, "edge_grad_estimator() backward")
     return out

@@ -37,25 +37,40 @@ struct EdgeArgs {
 };
 
 struct Tri2 {  // screen-space part of a triangle (get_tri_info, :72-87)
-  int i0, i1, i2;
   float p0x, p0y, p1x, p1y, v01x, v01y, v02x, v02y, v12x, v12y, den;
 };
 
-__device__ __forceinline__ void fetch_tri(const EdgeArgs& a, int n, int id, Tri2& t) {
-  const int32_t* vip = a.vi + (int64_t)n * a.vis.s0 + (int64_t)id * a.vis.s1;
-  t.i0 = vip[0]; t.i1 = vip[a.vis.s2]; t.i2 = vip[2 * a.vis.s2];
-  const float* vp = a.v + (int64_t)n * a.vs.s0;
-  const float* q0 = vp + (int64_t)t.i0 * a.vs.s1;
-  const float* q1 = vp + (int64_t)t.i1 * a.vs.s1;
-  const float* q2 = vp + (int64_t)t.i2 * a.vs.s1;
-  t.p0x = q0[0]; t.p0y = q0[a.vs.s2];
-  t.p1x = q1[0]; t.p1y = q1[a.vs.s2];
-  const float p2x = q2[0], p2y = q2[a.vs.s2];
+__device__ __forceinline__ void derive_tri(float p0x, float p0y, float p1x, float p1y, float p2x, float p2y, Tri2& t) {
+  t.p0x = p0x; t.p0y = p0y; t.p1x = p1x; t.p1y = p1y;
   t.v01x = sub_rn(t.p1x, t.p0x); t.v01y = sub_rn(t.p1y, t.p0y);
   t.v02x = sub_rn(p2x, t.p0x);   t.v02y = sub_rn(p2y, t.p0y);
   t.v12x = sub_rn(p2x, t.p1x);   t.v12y = sub_rn(p2y, t.p1y);
   t.den = diff_of_products(t.v01x, t.v02y, t.v01y, t.v02x);
 }
+
+// two-level gather index -> vi -> v (any strides)
+struct GatherFetch {
+  const EdgeArgs& a;
+  int n;
+  __device__ __forceinline__ void operator()(int id, Tri2& t) const {
+    const int32_t* vip = a.vi + (int64_t)n * a.vis.s0 + (int64_t)id * a.vis.s1;
+    const int i0 = vip[0], i1 = vip[a.vis.s2], i2 = vip[2 * a.vis.s2];
+    const float* vp = a.v + (int64_t)n * a.vs.s0;
+    const float* q0 = vp + (int64_t)i0 * a.vs.s1;
+    const float* q1 = vp + (int64_t)i1 * a.vs.s1;
+    const float* q2 = vp + (int64_t)i2 * a.vs.s1;
+    derive_tri(q0[0], q0[a.vs.s2], q1[0], q1[a.vs.s2], q2[0], q2[a.vs.s2], t);
+  }
+};
+
+// one-level gather from the per-(image, triangle) table {p0x,p0y,p1x,p1y | p2x,p2y,-,-} built by xy_table_kernel
+struct TableFetch {
+  const float4* tn;  // table of image n
+  __device__ __forceinline__ void operator()(int id, Tri2& t) const {
+    const float4 u = __ldg(tn + (int64_t)id * 2), w = __ldg(tn + (int64_t)id * 2 + 1);
+    derive_tri(u.x, u.y, u.z, u.w, w.x, w.y, t);
+  }
+};
 
 // pix_in_tri (:30-70): top-left rule with plain (non-canonical) edge functions
 __device__ __forceinline__ bool pix_in_tri(const Tri2& t, int x, int y) {
@@ -82,11 +97,12 @@ __device__ __forceinline__ bool pix_in_tri(const Tri2& t, int x, int y) {
 }
 
 // get_tri_normal (:89-100): normalize(cross(p0 - p2, p1 - p0))
-__device__ __forceinline__ float3 tri_normal(const EdgeArgs& a, int n, const Tri2& t) {
+__device__ __forceinline__ float3 tri_normal(const EdgeArgs& a, int n, int id) {
+  const int32_t* vip = a.vi + (int64_t)n * a.vis.s0 + (int64_t)id * a.vis.s1;
   const float* vp = a.v + (int64_t)n * a.vs.s0;
-  const float* q0 = vp + (int64_t)t.i0 * a.vs.s1;
-  const float* q1 = vp + (int64_t)t.i1 * a.vs.s1;
-  const float* q2 = vp + (int64_t)t.i2 * a.vs.s1;
+  const float* q0 = vp + (int64_t)vip[0] * a.vs.s1;
+  const float* q1 = vp + (int64_t)vip[a.vis.s2] * a.vs.s1;
+  const float* q2 = vp + (int64_t)vip[2 * a.vis.s2] * a.vs.s1;
   const float ax = q0[0] - q2[0], ay = q0[a.vs.s2] - q2[a.vs.s2], az = q0[2 * a.vs.s2] - q2[2 * a.vs.s2];
   const float bx = q1[0] - q0[0], by = q1[a.vs.s2] - q0[a.vs.s2], bz = q1[2 * a.vs.s2] - q0[2 * a.vs.s2];
   const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
@@ -129,14 +145,15 @@ __device__ __forceinline__ float grad_dot(const EdgeArgs& a, int n, int xc, int 
 // Both sides of the pair (centre=(xc,yc) showing triangle ci, neighbour=(xn,yn) showing ni != ci).
 // axis: 0 = horizontal pair (x gradient), 1 = vertical pair (y gradient).
 // Returns (centre.axis, centre.z, neighbour.axis, neighbour.z) before the final negation.
+template <class Fetch>
 __device__ __forceinline__ float4 pair_eval(const EdgeArgs& a, int n, int ci, int ni, int xc, int yc,
-                                            int xn, int yn, int axis) {
+                                            int xn, int yn, int axis, const Fetch& fetch) {
   const bool cv = ci >= 0, nv = ni >= 0;      // (:290-292)
   bool c_in_n = false, n_in_c = false;
   Tri2 tc, tn;
   if (cv && nv) {                              // (:320-325)
-    fetch_tri(a, n, ci, tc);
-    fetch_tri(a, n, ni, tn);
+    fetch(ci, tc);
+    fetch(ni, tn);
     c_in_n = pix_in_tri(tn, xc, yc);
     n_in_c = pix_in_tri(tc, xn, yn);
   }
@@ -151,7 +168,7 @@ __device__ __forceinline__ float4 pair_eval(const EdgeArgs& a, int n, int ci, in
   }
   // intersection: both triangles valid (:394-406, :411-423)
   const float g = grad_dot(a, n, xc, yc, xn, yn);
-  const float3 nc = tri_normal(a, n, tc), nn = tri_normal(a, n, tn);
+  const float3 nc = tri_normal(a, n, ci), nn = tri_normal(a, n, ni);
   const float nca = axis == 0 ? nc.x : nc.y, nna = axis == 0 ? nn.x : nn.y;
   const float2 dc = dp_dr(nca, nc.z, nna, nn.z, a.max_dp_dr);
   const float2 dn = dp_dr(nna, nn.z, nca, nc.z, a.max_dp_dr);
@@ -239,7 +256,7 @@ __global__ void __launch_bounds__(kEThreads, 4) edge_grad_tile_kernel(EdgeArgs a
     const int nx = cx + (axis == 0), ny = cy + (axis == 1);
     const int ci = ids[ly * kEIW + lx];
     const int ni = axis == 0 ? ids[ly * kEIW + lx + 1] : ids[(ly + 1) * kEIW + lx];
-    const float4 r = pair_eval(a, n, ci, ni, cx, cy, nx, ny, axis);
+    const float4 r = pair_eval(a, n, ci, ni, cx, cy, nx, ny, axis, GatherFetch{a, n});
     // centre pixel inside the tile?
     if (lx >= 1 && ly >= 1) {
       const int o = (ly - 1) * kETW + (lx - 1);
@@ -285,6 +302,132 @@ __global__ void __launch_bounds__(kEThreads, 4) edge_grad_tile_kernel(EdgeArgs a
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused path, warp-strip formulation (dense index rows, W % 8 == 0).
+// Because grad_v_pix is LINEAR in the per-pixel gradient, the per-pixel sum over a pixel's <= 4 pairs
+// need not be formed at all: every evaluated pair scatters its (rare) non-zero contributions straight to
+// the vertices of the two pixels' triangles.  That removes the tile kernel's slots, its zero-fill, its
+// combine phase and all three CTA barriers; what remains is "find the pairs showing two different
+// triangles and classify them", done warp-privately:
+//   * a warp takes a strip of 256 consecutive pixels of one row: lane = 8 pixels, two LDG.128 for its own
+//     row and two for the row below (the right neighbour of a lane's last pixel comes from the next lane by
+//     shuffle), so the 16 candidate pairs of a lane are 16 register compares;
+//   * the lanes' jobs are compacted into a warp-private shared-memory queue (shuffle scan of the per-lane
+//     counts, no atomics, __syncwarp only), so the heavy pair classification runs with all lanes busy;
+//   * triangles come from a per-(image, triangle) xy table (2 x LDG.128, one dependent level) built by a
+//     pre-pass, instead of the index -> vi -> v two-level gather (3 + 6 scalar loads per triangle).
+constexpr int kStripPx = 256, kStripWarps = 8;
+
+__global__ void __launch_bounds__(256) xy_table_kernel(EdgeArgs a, float4* __restrict__ table) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (f >= a.F) return;
+  const int32_t* vip = a.vi + (int64_t)n * a.vis.s0 + (int64_t)f * a.vis.s1;
+  const float* vp = a.v + (int64_t)n * a.vs.s0;
+  const float* q0 = vp + (int64_t)vip[0] * a.vs.s1;
+  const float* q1 = vp + (int64_t)vip[a.vis.s2] * a.vs.s1;
+  const float* q2 = vp + (int64_t)vip[2 * a.vis.s2] * a.vs.s1;
+  float4* row = table + ((int64_t)n * a.F + f) * 2;
+  row[0] = make_float4(q0[0], q0[a.vs.s2], q1[0], q1[a.vs.s2]);
+  row[1] = make_float4(q2[0], q2[a.vs.s2], 0.f, 0.f);
+}
+
+// grad_v_pix[vi[id][k]] += (gx, gy, gz) * bary_k(x, y)  for the pixel (x, y) showing triangle id
+__device__ __forceinline__ void scatter_pixel(const EdgeArgs& a, const FusedArgs& fz, int n, int id, int x, int y,
+                                              int axis, float ga, float gz) {
+  if (id < 0 || (ga == 0.f && gz == 0.f)) return;
+  const int32_t* vip = a.vi + (int64_t)n * a.vis.s0 + (int64_t)id * a.vis.s1;
+  const float* bp = fz.bary + (int64_t)n * fz.bs.s0 + (int64_t)y * fz.bs.s2 + (int64_t)x * fz.bs.s3;
+  float* gv = fz.grad_v + (int64_t)n * a.V * 3;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float bk = bp[(int64_t)k * fz.bs.s1];
+    float* q = gv + (int64_t)vip[(int64_t)k * a.vis.s2] * 3;
+    if (ga != 0.f) red_add(q + axis, ga * bk);
+    if (gz != 0.f) red_add(q + 2, gz * bk);
+  }
+}
+
+__global__ void __launch_bounds__(kStripWarps * 32) edge_grad_strip_kernel(EdgeArgs a, FusedArgs fz,
+                                                                           const float4* __restrict__ table,
+                                                                           int strips_per_row, int64_t num_strips) {
+  __shared__ int s_own[kStripWarps][kStripPx + 1];
+  __shared__ int s_below[kStripWarps][kStripPx];
+  __shared__ unsigned short s_jobs[kStripWarps][2 * kStripPx];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int* own = s_own[wid];
+  int* below = s_below[wid];
+  unsigned short* jobs = s_jobs[wid];
+  const int64_t warp0 = (int64_t)blockIdx.x * kStripWarps + wid, nwarps = (int64_t)gridDim.x * kStripWarps;
+  const int64_t strips_per_img = (int64_t)strips_per_row * (a.H - 1);  // the last row holds no centre pixel (:270)
+
+  for (int64_t s = warp0; s < num_strips; s += nwarps) {
+    const int n = (int)(s / strips_per_img);
+    const int r = (int)(s - (int64_t)n * strips_per_img);
+    const int y = r / strips_per_row, sx = r - y * strips_per_row;
+    const int x = sx * kStripPx + lane * 8;
+    const int32_t* row = a.index_img + (int64_t)n * a.is.s0 + (int64_t)y * a.is.s1;
+    int id[9], dn[8];
+    const bool live = x < a.W;  // W % 8 == 0: a lane's eight pixels are all inside or all outside
+    if (live) {
+      const int4 p = ldg_stream_i4(row + x), q = ldg_stream_i4(row + x + 4);
+      const int4 u = __ldg(reinterpret_cast<const int4*>(row + a.is.s1 + x)),
+                 w = __ldg(reinterpret_cast<const int4*>(row + a.is.s1 + x + 4));  // re-read as "own" by the next row
+      id[0] = p.x; id[1] = p.y; id[2] = p.z; id[3] = p.w; id[4] = q.x; id[5] = q.y; id[6] = q.z; id[7] = q.w;
+      dn[0] = u.x; dn[1] = u.y; dn[2] = u.z; dn[3] = u.w; dn[4] = w.x; dn[5] = w.y; dn[6] = w.z; dn[7] = w.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { id[j] = -1; dn[j] = -1; }
+    }
+    id[8] = __shfl_down_sync(0xffffffffu, id[0], 1);
+    if (lane == 31) id[8] = (live && x + 8 < a.W) ? row[x + 8] : -1;
+    // candidate pairs: bit j = (j, j+1) horizontal, bit 8+j = (j, below) vertical; centres need x < W-1
+    unsigned m = 0;
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool centre = x + j < a.W - 1;
+        m |= (centre && id[j] != id[j + 1]) ? (1u << j) : 0u;
+        m |= (centre && id[j] != dn[j]) ? (0x100u << j) : 0u;
+      }
+    }
+    if (__all_sync(0xffffffffu, m == 0u)) continue;
+    // stage the ids for the job phase, compact the jobs
+    __syncwarp();  // previous strip's readers are done
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { own[lane * 8 + j] = id[j]; below[lane * 8 + j] = dn[j]; }
+    if (lane == 31) own[kStripPx] = id[8];
+    const int cnt = __popc(m);
+    int off = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, off, d);
+      if (lane >= d) off += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, off, 31);
+    off -= cnt;
+    while (m) {
+      const int bit = __ffs(m) - 1;
+      m &= m - 1;
+      jobs[off++] = (unsigned short)(((bit >> 3) << 8) | (lane * 8 + (bit & 7)));
+    }
+    __syncwarp();
+    const TableFetch fetch{table + (int64_t)n * a.F * 2};
+    for (int q = lane; q < total; q += 32) {
+      const int job = jobs[q];
+      const int axis = job >> 8, lx = job & 0xff;
+      const int ci = own[lx];
+      const int ni = axis == 0 ? own[lx + 1] : below[lx];
+      const int cx = sx * kStripPx + lx, cy = y;
+      const int nx = cx + (axis == 0), ny = cy + (axis == 1);
+      const float4 rr = pair_eval(a, n, ci, ni, cx, cy, nx, ny, axis, fetch);
+      // final negation of the reference (:431-445) folded in
+      scatter_pixel(a, fz, n, ci, cx, cy, axis, -rr.x, -rr.y);
+      scatter_pixel(a, fz, n, ni, nx, ny, axis, -rr.z, -rr.w);
+    }
+  }
+}
+
 }  // namespace
 }  // namespace drtk
 
@@ -295,7 +438,7 @@ static int edge_launch(const float* v_pix, const int64_t* v_strides, const float
                        const int64_t* vi_strides, const float* grad_output, const int64_t* grad_output_strides,
                        int64_t N, int64_t V, int64_t F, int64_t C, int64_t H, int64_t W, float max_dp_dr,
                        float* grad_v_pix_img, const float* bary_img, const int64_t* bary_strides, float* grad_v_pix,
-                       void* stream_) {
+                       void* workspace, size_t workspace_bytes, void* stream_) {
   if (N < 0 || C < 0 || H < 0 || W < 0) return DRTK_B200_EINVAL;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool fused = grad_v_pix != nullptr;
@@ -315,6 +458,22 @@ static int edge_launch(const float* v_pix, const int64_t* v_strides, const float
   if (grid.y > 65535) return DRTK_B200_EUNSUPPORTED;
   FusedArgs fz;
   fz.bary = bary_img; fz.bs = fused ? make4(bary_strides) : Strides4{0, 0, 0, 0}; fz.grad_v = grad_v_pix;
+  const auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  if (fused && F > 0 && W % 8 == 0 && H > 1 && a.is.s2 == 1 && a.is.s1 % 4 == 0 && a.is.s0 % 4 == 0 && al16(index_img) &&
+      F <= 65535LL * 256) {
+    const size_t tb = (size_t)(N * F) * 32;
+    if (!workspace || workspace_bytes < tb || !al16(workspace)) return DRTK_B200_EWORKSPACE;
+    float4* table = static_cast<float4*>(workspace);
+    xy_table_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)N), 256, 0, stream>>>(a, table);
+    const int strips_per_row = (int)((W + kStripPx - 1) / kStripPx);
+    const int64_t num_strips = N * (H - 1) * strips_per_row;
+    const int64_t need = (num_strips + kStripWarps - 1) / kStripWarps;
+    const int64_t cap = (int64_t)kNumSMs * 8 * 4;  // a few strips per warp: short tail, ids loads of neighbours overlap
+    edge_grad_strip_kernel<<<(unsigned)(need < cap ? need : cap), kStripWarps * 32, 0, stream>>>(a, fz, table, strips_per_row,
+                                                                                          num_strips);
+    DRTK_CHECK_LAUNCH();
+    return 0;
+  }
   if (fused) edge_grad_tile_kernel<true><<<grid, kEThreads, 0, stream>>>(a, nullptr, fz);
   else edge_grad_tile_kernel<false><<<grid, kEThreads, 0, stream>>>(a, grad_v_pix_img, fz);
   DRTK_CHECK_LAUNCH();
@@ -330,7 +489,7 @@ extern "C" int drtk_b200_edge_grad_backward(const float* v_pix, const int64_t* v
                                             float* grad_v_pix_img, void* stream_) {
   return edge_launch(v_pix, v_strides, img, img_strides, index_img, index_strides, vi, vi_strides, grad_output,
                      grad_output_strides, N, V, F, C, H, W, max_dp_dr, grad_v_pix_img, nullptr, nullptr, nullptr,
-                     stream_);
+                     nullptr, 0, stream_);
 }
 
 extern "C" int drtk_b200_edge_grad_backward_fused(
@@ -338,10 +497,14 @@ extern "C" int drtk_b200_edge_grad_backward_fused(
     const int32_t* index_img, const int64_t* index_strides, const int32_t* vi, const int64_t* vi_strides,
     const float* grad_output, const int64_t* grad_output_strides, const float* bary_img,
     const int64_t* bary_strides, int64_t N, int64_t V, int64_t F, int64_t C, int64_t H, int64_t W,
-    float max_dp_dr, float* grad_v_pix, void* stream_) {
+    float max_dp_dr, float* grad_v_pix, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!grad_v_pix && N * V > 0) return DRTK_B200_EINVAL;
   if (N * V == 0) return 0;
   return edge_launch(v_pix, v_strides, img, img_strides, index_img, index_strides, vi, vi_strides, grad_output,
                      grad_output_strides, N, V, F, C, H, W, max_dp_dr, nullptr, bary_img, bary_strides, grad_v_pix,
-                     stream_);
+                     workspace, workspace_bytes, stream_);
+}
+
+extern "C" size_t drtk_b200_edge_grad_backward_fused_workspace_bytes(int64_t N, int64_t F) {
+  return (N <= 0 || F <= 0) ? 0 : (size_t)(N * F) * 32;
 }

@@ -137,7 +137,11 @@ int drtk_b200_edge_grad_backward(const float* v_pix, const int64_t* v_strides, c
  * interpolate_cuda_backward with C = 3, src/interpolate/interpolate_kernel.cu:642-697).  Used when no
  * `v_pix_img_hook` needs to see the [N,3,H,W] image.
  *   bary_img   [N,3,H,W] (strides bary_strides[4])
- *   grad_v_pix [N,V,3] out, dense; zero-filled by the callee, then accumulated                     */
+ *   grad_v_pix [N,V,3] out, dense; zero-filled by the callee, then accumulated
+ *   workspace  16-B aligned scratch of at least drtk_b200_edge_grad_backward_fused_workspace_bytes(N,F)
+ *              bytes (per-triangle screen-space vertex table of the fast path)                        */
+size_t drtk_b200_edge_grad_backward_fused_workspace_bytes(int64_t N, int64_t F);
+
 int drtk_b200_edge_grad_backward_fused(const float* v_pix, const int64_t* v_strides, const float* img,
                                        const int64_t* img_strides, const int32_t* index_img,
                                        const int64_t* index_strides, const int32_t* vi,
@@ -145,7 +149,8 @@ int drtk_b200_edge_grad_backward_fused(const float* v_pix, const int64_t* v_stri
                                        const int64_t* grad_output_strides, const float* bary_img,
                                        const int64_t* bary_strides, int64_t N, int64_t V, int64_t F,
                                        int64_t C, int64_t H, int64_t W, float max_dp_dr,
-                                       float* grad_v_pix, void* stream);
+                                       float* grad_v_pix, void* workspace, size_t workspace_bytes,
+                                       void* stream);
 
 #ifdef __cplusplus
 }
