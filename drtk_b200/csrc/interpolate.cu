@@ -15,6 +15,8 @@
 //                head lane of each run issues one 128-bit vector reduction per vertex
 //                (red.global.add.v4.f32) -- no shared memory, no block barriers (the reference
 //                needs one barrier and up to three scalar atomics per channel per run).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -538,6 +540,313 @@ interp_bwd_tile_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// backward, tiled, v5 (C % 4 == 0): quad-lane walkers + packed triangle table + A/B warp teams
+// ------------------------------------------------------------------------------------------
+// What the ncu capture of the kernel above showed (profiles/r01_ncu_interp_bwd_v4_vs_v5.md): 20 warp
+// instructions per pixel -- 10.4 in the walkers (each lane carries ONE channel, so the per-pixel run test
+// and the 27-instruction run-boundary block are paid per channel, and the two walkers of a warp diverge at
+// their boundaries), 5.8 in phase B, 2.6 in per-tile bookkeeping (64-bit divisions) -- and the LSU data pipe
+// at 67 % (shared-memory wavefronts of the broadcast index/bary loads, three scalar vi loads per run).  Here:
+//   * a walker is FOUR lanes, each carrying four channels (12 accumulators): the run test, the boundary
+//     block and the broadcast index/bary loads are amortised over 4x the channels; a run is flushed with
+//     three red.global.add.v4.f32 per lane (the four lanes of a walker cover one 64-B vertex row);
+//   * triangle -> vertex ids come from a packed int4 table (one LDG.128 instead of three strided LDG.32
+//     plus their address arithmetic), built per call by a tiny kernel into a stream-ordered allocation;
+//   * a warp is 8 walkers x 16-pixel segments = 128 pixels.  The consumer warps of a CTA form two teams
+//     that swap roles every tile: one team walks (phase A), the other computes the barycentric gradients
+//     of the same tile (phase B, 2 x 64 pixels per warp);
+//   * tiles are 512 pixels and TWO CTAs of 8 consumer + 2 producer warps share an SM: two independent
+//     two-stage pipelines, so that one CTA computes while the other sits at its tile hand-over;
+//   * channel planes are staged with a 16-B skew per group of four planes, which makes the walkers'
+//     LDS.128 (lane = plane group, two walkers 64 B apart per quarter warp) bank-conflict free;
+//   * tile bookkeeping is 32-bit and incremental.
+constexpr int kQSeg = 16;       // pixels per walker
+constexpr int kQCh = 16;        // channels per pass over a tile
+constexpr int kQUnit = 128;     // pixels per warp: 8 walkers x kQSeg (phase A) = 2 x 32 lanes x 2 px (phase B)
+constexpr int kQProducers = 2;  // 20 bulk copies per tile at ~0.145 us each per issuing thread
+
+template <int TP>
+struct QStage {
+  float g[kQCh * TP + 16];  // plane c starts at c * TP + (c >> 2) * 4
+  float bary[3 * TP];
+  int idx[TP];
+};
+template <int TP>
+struct QSmem {
+  QStage<TP> st[kBwdStages];
+  unsigned long long full[kBwdStages];
+  unsigned long long empty[kBwdStages];
+};
+
+__global__ void __launch_bounds__(256) vi_table_kernel(const int32_t* __restrict__ vi, Strides3 vis, int F,
+                                                       int64_t total, int4* __restrict__ tab) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t n = i / F, f = i - n * F;
+  const int32_t* vip = vi + n * vis.s0 + f * vis.s1;
+  tab[i] = make_int4(vip[0], vip[vis.s2], vip[2 * vis.s2], 0);
+}
+
+// Phase A of one walker lane: 16 pixels, four channels.  gp: plane 4q of the stage at the segment start
+// (the next three planes follow at TP); ip/bp: index / bary planes at the segment start; vg: vertex
+// gradient table of the image offset by this lane's first channel; tab: packed triangle table of the image;
+// off_mask: 0 for a lane that carries channels, -1 for an idle lane (never flushes).
+// Must be entered from convergent control flow (see walk_runs).
+template <int TP>
+__device__ __forceinline__ void walk_runs_quad(const float* __restrict__ gp, const int* __restrict__ ip,
+                                               const float* __restrict__ bp, float* vg,
+                                               const int4* __restrict__ tab, unsigned Cs, int off_mask) {
+  int cur = -1;
+  int4 t = make_int4(0, 0, 0, 0);  // vertex ids of the current run: fetched at its first pixel, consumed
+                                   // (multiplied, added to the table base) only at its flush, so the load's
+                                   // latency hides behind the run's FMAs
+  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int x = 0; x < kQSeg; x += 4) {
+    const float4 G0 = *reinterpret_cast<const float4*>(gp + x);
+    const float4 G1 = *reinterpret_cast<const float4*>(gp + TP + x);
+    const float4 G2 = *reinterpret_cast<const float4*>(gp + 2 * TP + x);
+    const float4 G3 = *reinterpret_cast<const float4*>(gp + 3 * TP + x);
+    const int4 iq = *reinterpret_cast<const int4*>(ip + x);
+    const float4 p0q = *reinterpret_cast<const float4*>(bp + x);
+    const float4 p1q = *reinterpret_cast<const float4*>(bp + TP + x);
+    const float4 p2q = *reinterpret_cast<const float4*>(bp + 2 * TP + x);
+    const int ids[4] = {iq.x, iq.y, iq.z, iq.w};
+    const float g[4][4] = {{G0.x, G0.y, G0.z, G0.w}, {G1.x, G1.y, G1.z, G1.w},
+                           {G2.x, G2.y, G2.z, G2.w}, {G3.x, G3.y, G3.z, G3.w}};  // [channel][pixel]
+    const float q0[4] = {p0q.x, p0q.y, p0q.z, p0q.w};
+    const float q1[4] = {p1q.x, p1q.y, p1q.z, p1q.w};
+    const float q2[4] = {p2q.x, p2q.y, p2q.z, p2q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int id = ids[j];
+      if (id != cur) {  // run boundary (uniform across the four lanes of the walker)
+        if ((cur | off_mask) >= 0) {
+          red_add_v4(vg + (unsigned)t.x * Cs, a0[0], a0[1], a0[2], a0[3]);
+          red_add_v4(vg + (unsigned)t.y * Cs, a1[0], a1[1], a1[2], a1[3]);
+          red_add_v4(vg + (unsigned)t.z * Cs, a2[0], a2[1], a2[2], a2[3]);
+        }
+        t = tab[max(id, 0)];  // empty pixels read triangle 0 harmlessly; never flushed
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a0[k] = a1[k] = a2[k] = 0.f;
+        cur = id;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a0[k] = fmaf(g[k][j], q0[j], a0[k]);
+        a1[k] = fmaf(g[k][j], q1[j], a1[k]);
+        a2[k] = fmaf(g[k][j], q2[j], a2[k]);
+      }
+    }
+  }
+  if ((cur | off_mask) >= 0) {
+    red_add_v4(vg + (unsigned)t.x * Cs, a0[0], a0[1], a0[2], a0[3]);
+    red_add_v4(vg + (unsigned)t.y * Cs, a1[0], a1[1], a1[2], a1[3]);
+    red_add_v4(vg + (unsigned)t.z * Cs, a2[0], a2[1], a2[2], a2[3]);
+  }
+}
+
+// Phase B of one thread: two adjacent pixels, NC channels of the staged gradients against the three attribute
+// rows of each pixel's triangle (rows are shared when both pixels show the same triangle).  NC > 0: compile-
+// time channel count (full unroll, immediate offsets); NC == 0: nc channels at run time.
+template <int TP, int NC>
+__device__ __forceinline__ void bary_grad_pair(const float* __restrict__ gq_base, const float* __restrict__ an,
+                                               unsigned rs, int4 t0, int4 t1, bool same, int nc,
+                                               float (&g0)[3], float (&g1)[3]) {
+  const float* r00 = an + (unsigned)t0.x * rs; const float* r01 = an + (unsigned)t0.y * rs;
+  const float* r02 = an + (unsigned)t0.z * rs;
+  const float* r10 = an + (unsigned)t1.x * rs; const float* r11 = an + (unsigned)t1.y * rs;
+  const float* r12 = an + (unsigned)t1.z * rs;
+  auto group = [&](int cc) {
+    float2 gq[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) gq[k] = *reinterpret_cast<const float2*>(gq_base + (cc + k) * TP + (cc >> 2) * 4);
+    float4 A0 = *reinterpret_cast<const float4*>(r00 + cc);
+    float4 A1 = *reinterpret_cast<const float4*>(r01 + cc);
+    float4 A2 = *reinterpret_cast<const float4*>(r02 + cc);
+    g0[0] = fmaf(gq[3].x, A0.w, fmaf(gq[2].x, A0.z, fmaf(gq[1].x, A0.y, fmaf(gq[0].x, A0.x, g0[0]))));
+    g0[1] = fmaf(gq[3].x, A1.w, fmaf(gq[2].x, A1.z, fmaf(gq[1].x, A1.y, fmaf(gq[0].x, A1.x, g0[1]))));
+    g0[2] = fmaf(gq[3].x, A2.w, fmaf(gq[2].x, A2.z, fmaf(gq[1].x, A2.y, fmaf(gq[0].x, A2.x, g0[2]))));
+    if (!same) {
+      A0 = *reinterpret_cast<const float4*>(r10 + cc);
+      A1 = *reinterpret_cast<const float4*>(r11 + cc);
+      A2 = *reinterpret_cast<const float4*>(r12 + cc);
+    }
+    g1[0] = fmaf(gq[3].y, A0.w, fmaf(gq[2].y, A0.z, fmaf(gq[1].y, A0.y, fmaf(gq[0].y, A0.x, g1[0]))));
+    g1[1] = fmaf(gq[3].y, A1.w, fmaf(gq[2].y, A1.z, fmaf(gq[1].y, A1.y, fmaf(gq[0].y, A1.x, g1[1]))));
+    g1[2] = fmaf(gq[3].y, A2.w, fmaf(gq[2].y, A2.z, fmaf(gq[1].y, A2.y, fmaf(gq[0].y, A2.x, g1[2]))));
+  };
+  if (NC > 0) {
+#pragma unroll
+    for (int cc = 0; cc < NC; cc += 4) group(cc);
+  } else {
+#pragma unroll 1
+    for (int cc = 0; cc < nc; cc += 4) group(cc);
+  }
+}
+
+// MULTI: C > 16, i.e. several channel passes per tile (phase-B sums are then carried between passes)
+template <int TP, bool NEED_VERT, bool NEED_BARY, bool AVEC, bool MULTI>
+__global__ void __launch_bounds__(32 * (TP / kQUnit * 2 + kQProducers), (TP <= 512) ? 2 : 1)
+interp_bwd_quad_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __restrict__ bary_grad,
+                       const int4* __restrict__ tab, int tab_img_stride, int tiles_per_img, int num_tiles, int dbg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  QSmem<TP>& S = *reinterpret_cast<QSmem<TP>*>(smem_raw);
+  constexpr int TEAM = TP / kQUnit;        // warps per team
+  constexpr int CONSUMERS = 2 * TEAM;      // consumer warps
+  const InterpArgs& a = b.f;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int HW = a.H * a.W;
+  if (tid == 0) {
+    for (int s = 0; s < kBwdStages; ++s) {
+      mbar_init(reinterpret_cast<uint64_t*>(&S.full[s]), kQProducers);
+      mbar_init(reinterpret_cast<uint64_t*>(&S.empty[s]), CONSUMERS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int nchunks = MULTI ? (a.C + kQCh - 1) / kQCh : 1;
+  const int warp_role = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
+  // first tile of this CTA: image n, tile tl within the image; advanced incrementally (no division per tile)
+  const int step_n = (int)gridDim.x / tiles_per_img, step_t = (int)gridDim.x - step_n * tiles_per_img;
+  int n = (int)blockIdx.x / tiles_per_img, tl = (int)blockIdx.x - n * tiles_per_img;
+
+  if (warp_role >= CONSUMERS) {  // ---- producer warps: one bulk copy per plane ----
+    if (lane == 0) {
+      const int pw = warp_role - CONSUMERS;
+      int item = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int p0 = tl * TP;
+        const uint32_t bytes = (uint32_t)min(TP, HW - p0) * 4u;
+        for (int chunk = 0; chunk < nchunks; ++chunk, ++item) {
+          const int s = item & 1;
+          if (item >= kBwdStages)
+            mbar_wait_backoff(reinterpret_cast<uint64_t*>(&S.empty[s]), (uint32_t)((item / kBwdStages - 1) & 1), 100);
+          const int c0 = chunk * kQCh, nc = min(kQCh, a.C - c0);
+          const int ncopies = nc + (NEED_VERT ? 3 : 0) + 1;
+          uint64_t* bar = reinterpret_cast<uint64_t*>(&S.full[s]);
+          QStage<TP>& st = S.st[s];
+          const int mine = (ncopies - pw + kQProducers - 1) / kQProducers;
+          fence_proxy_async_smem();
+          mbar_arrive_expect_tx(bar, (uint32_t)mine * bytes);
+          for (int k = pw; k < ncopies; k += kQProducers) {
+            const void* src;
+            void* dst;
+            if (k < nc) {
+              src = b.grad_out + (int64_t)n * b.gs.s0 + (int64_t)(c0 + k) * b.gs.s1 + p0;
+              dst = st.g + k * TP + (k >> 2) * 4;
+            } else if (NEED_VERT && k < nc + 3) {
+              src = a.bary + (int64_t)n * a.bs.s0 + (int64_t)(k - nc) * a.bs.s1 + p0;
+              dst = st.bary + (k - nc) * TP;
+            } else {
+              src = a.index_img + (int64_t)n * a.is.s0 + p0;
+              dst = st.idx;
+            }
+            bulk_g2s(dst, src, bytes, bar);
+          }
+        }
+        n += step_n; tl += step_t;
+        if (tl >= tiles_per_img) { tl -= tiles_per_img; ++n; }
+      }
+    }
+    return;
+  }
+
+  // ---- consumer warps ----
+  const int team = warp_role / TEAM, unit = warp_role - team * TEAM;  // a unit is 128 pixels of the tile
+  uint32_t phase_bits = 0;
+  float gb[MULTI ? 2 : 1][2][3];  // phase-B accumulators: [pass][pixel][vertex], carried across channel passes (C > 16)
+  int item = 0, seq = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++seq) {
+    const int p0 = tl * TP;
+    const int npx = min(TP, HW - p0);
+    const bool a_team = ((team ^ seq) & 1) == 0;  // the teams swap roles every tile
+    const int4* tabn = tab + (size_t)((unsigned)n * (unsigned)tab_img_stride);
+    for (int chunk = 0; chunk < nchunks; ++chunk, ++item) {
+      const int s = item & 1;
+      const int c0 = chunk * kQCh, nc = min(kQCh, a.C - c0);
+      QStage<TP>& st = S.st[s];
+      mbar_wait_backoff(reinterpret_cast<uint64_t*>(&S.full[s]), (phase_bits >> s) & 1u, 32);
+      phase_bits ^= (1u << s);
+      if (npx < TP) {  // last tile of an image (uniform over the CTA): pad with "no triangle"
+        for (int i = npx + tid; i < TP; i += 32 * CONSUMERS) st.idx[i] = -1;
+        asm volatile("bar.sync 1, %0;" :: "n"(32 * CONSUMERS) : "memory");
+      }
+
+      if (NEED_VERT && a_team && !(dbg & 4)) {  // ---- phase A: 8 walkers x 16 pixels, lane = 4 channels ----
+        const int q = lane & 3, seg = unit * kQUnit + (lane >> 2) * kQSeg;
+        const bool c_on = 4 * q < nc;
+        const int qq = c_on ? q : 0;
+        walk_runs_quad<TP>(st.g + (4 * qq) * TP + qq * 4 + seg, st.idx + seg, st.bary + seg,
+                           vert_grad + ((size_t)n * (size_t)a.V * (size_t)a.C + (size_t)(c0 + 4 * qq)), tabn,
+                           (unsigned)a.C, (c_on && !(dbg & 1)) ? 0 : -1);
+      }
+
+      if (NEED_BARY && !a_team && !(dbg & 2)) {  // ---- phase B: 2 passes x (thread = 2 pixels) ----
+        // triangle rows of both passes are fetched up front (two dependent L2 round trips per pass otherwise)
+        int2 qids[2];
+        int4 t0s[2], t1s[2];
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          qids[pass] = *reinterpret_cast<const int2*>(st.idx + unit * kQUnit + pass * 64 + lane * 2);
+          t0s[pass] = tabn[max(qids[pass].x, 0)];
+          t1s[pass] = tabn[max(qids[pass].y, 0)];
+        }
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {  // unrolled: gb[pass] must stay in registers
+          const int x = unit * kQUnit + pass * 64 + lane * 2;
+          float g0[3], g1[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            g0[k] = (MULTI && chunk) ? gb[MULTI ? pass : 0][0][k] : 0.f;
+            g1[k] = (MULTI && chunk) ? gb[MULTI ? pass : 0][1][k] : 0.f;
+          }
+          const int2 qid = qids[pass];
+          const int4 t0 = t0s[pass], t1 = t1s[pass];
+          const bool same = qid.y == qid.x;
+          const float* gq_base = st.g + x;
+          if (AVEC) {
+            const float* an = a.attr + ((size_t)n * (size_t)a.as.s0 + (size_t)c0);  // s2 == 1 on this path
+            if (nc == kQCh) bary_grad_pair<TP, kQCh>(gq_base, an, (unsigned)a.as.s1, t0, t1, same, nc, g0, g1);
+            else bary_grad_pair<TP, 0>(gq_base, an, (unsigned)a.as.s1, t0, t1, same, nc, g0, g1);
+          } else {
+            const float* an = a.attr + (int64_t)n * a.as.s0 + (int64_t)c0 * a.as.s2;
+            const float* r00 = an + (int64_t)t0.x * a.as.s1; const float* r01 = an + (int64_t)t0.y * a.as.s1;
+            const float* r02 = an + (int64_t)t0.z * a.as.s1;
+            const float* r10 = an + (int64_t)t1.x * a.as.s1; const float* r11 = an + (int64_t)t1.y * a.as.s1;
+            const float* r12 = an + (int64_t)t1.z * a.as.s1;
+#pragma unroll 1
+            for (int cc = 0; cc < nc; ++cc) {
+              const float2 gq = *reinterpret_cast<const float2*>(gq_base + cc * TP + (cc >> 2) * 4);
+              const int64_t co = (int64_t)cc * a.as.s2;
+              g0[0] = fmaf(gq.x, r00[co], g0[0]); g0[1] = fmaf(gq.x, r01[co], g0[1]); g0[2] = fmaf(gq.x, r02[co], g0[2]);
+              g1[0] = fmaf(gq.y, r10[co], g1[0]); g1[1] = fmaf(gq.y, r11[co], g1[1]); g1[2] = fmaf(gq.y, r12[co], g1[2]);
+            }
+          }
+          if (!MULTI || chunk == nchunks - 1) {
+            if (x < npx) {
+              float* gp = bary_grad + ((size_t)n * 3 * (size_t)HW + (size_t)(p0 + x));
+              if (qid.x < 0) g0[0] = g0[1] = g0[2] = 0.f;  // (:282-297) zeros where empty
+              if (qid.y < 0) g1[0] = g1[1] = g1[2] = 0.f;
+#pragma unroll
+              for (int k = 0; k < 3; ++k) *reinterpret_cast<float2*>(gp + (size_t)k * HW) = make_float2(g0[k], g1[k]);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { gb[MULTI ? pass : 0][0][k] = g0[k]; gb[MULTI ? pass : 0][1][k] = g1[k]; }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&S.empty[s]));
+    }
+    n += step_n; tl += step_t;
+    if (tl >= tiles_per_img) { tl -= tiles_per_img; ++n; }
+  }
+}
+
 inline unsigned grid_for(int64_t work_items, int threads, int ctas_per_sm) {
   const int64_t need = (work_items + threads - 1) / threads;
   const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
@@ -633,8 +942,47 @@ extern "C" int drtk_b200_interpolate_backward(
       (!nb || reinterpret_cast<uintptr_t>(bary_img_grad) % 16 == 0);
   if (rows_ok) {
     const bool avec = nb && (C % 4 == 0) && b.f.as.s2 == 1 && (b.f.as.s1 % 4 == 0) && (b.f.as.s0 % 4 == 0) &&
-                      (reinterpret_cast<uintptr_t>(vert_attributes) % 16 == 0);
+                      (reinterpret_cast<uintptr_t>(vert_attributes) % 16 == 0) &&
+                      (V * (b.f.as.s1 > 0 ? b.f.as.s1 : 1) + C < (int64_t)0x7FFFFFF0) && b.f.as.s1 >= 0;
     int rc2 = 0;
+    // v5: quad-lane walkers + packed triangle table (needs whole groups of four channels)
+    constexpr int QTP = 512;
+    const int64_t tiles_q = N * ((H * W + QTP - 1) / QTP);
+    const int64_t tab_imgs = (b.f.vis.s0 == 0) ? 1 : N;
+    if ((C % 4 == 0) && tiles_q < (int64_t)0x7FFFFFF0 && tab_imgs * F < (int64_t)0x0FFFFFFF &&
+        (!nv || reinterpret_cast<uintptr_t>(vert_attributes_grad) % 16 == 0) && !getenv("DRTK_B200_BWD_V4")) {
+      int4* tab = nullptr;
+      DRTK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tab), sizeof(int4) * (size_t)(tab_imgs * F), stream));
+      const int64_t total = tab_imgs * F;
+      vi_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(vi, b.f.vis, (int)F, total, tab);
+      auto launch5 = [&](auto kern) {
+        const size_t smem = sizeof(QSmem<QTP>) + 128;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { rc2 = (int)e; return; }
+        const int tiles_per_img = (int)((H * W + QTP - 1) / QTP);
+        const int64_t ctas = 2 * kNumSMs;  // two co-resident CTAs per SM
+        const unsigned grid = (unsigned)(tiles_q < ctas ? tiles_q : ctas);
+        kern<<<grid, 32 * (QTP / kQUnit * 2 + kQProducers), smem, stream>>>(
+            b, vert_attributes_grad, bary_img_grad, tab, tab_imgs == 1 ? 0 : (int)F, tiles_per_img, (int)tiles_q,
+            getenv("DRTK_B200_DBG") ? atoi(getenv("DRTK_B200_DBG")) : 0);
+      };
+#define DRTK_Q5(MULTI)                                                                                     \
+      do {                                                                                                   \
+        if (nv && nb) { if (avec) launch5(interp_bwd_quad_kernel<QTP, true, true, true, MULTI>);             \
+                        else launch5(interp_bwd_quad_kernel<QTP, true, true, false, MULTI>); }               \
+        else if (nv) launch5(interp_bwd_quad_kernel<QTP, true, false, false, MULTI>);                        \
+        else { if (avec) launch5(interp_bwd_quad_kernel<QTP, false, true, true, MULTI>);                     \
+               else launch5(interp_bwd_quad_kernel<QTP, false, true, false, MULTI>); }                       \
+      } while (0)
+      if (C > kQCh) DRTK_Q5(true); else DRTK_Q5(false);
+#undef DRTK_Q5
+      cudaError_t e1 = cudaGetLastError();
+      cudaError_t e2 = cudaFreeAsync(tab, stream);
+      if (rc2) return rc2;
+      if (e1 != cudaSuccess) return (int)e1;
+      if (e2 != cudaSuccess) return (int)e2;
+      return 0;
+    }
     auto launch = [&](auto kern, size_t smem, int TP) {
       const int tiles_per_img = (int)((H * W + TP - 1) / TP);
       const int64_t num_tiles = N * (int64_t)tiles_per_img;

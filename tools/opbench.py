@@ -1,0 +1,65 @@
+"""A/B timing of single ops on config-4 tensors (CUDA events, L2-cold by construction: each op streams >1 GB).
+usage: python tools/opbench.py [--ops interp_bwd,...] [--iters 20]
+Environment switches read by the library per call are toggled in-process (DRTK_B200_*)."""
+import argparse, os, sys
+import torch as th
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import drtk_b200
+from drtk_b200 import scenes, _ops
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", type=int, default=4)
+ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--C", type=int, default=16)
+ap.add_argument("--ops", default="interp_bwd")
+ap.add_argument("--env", default="", help="comma list of VAR=VAL variants to compare, e.g. DRTK_B200_BWD_V4=1")
+a = ap.parse_args()
+dev = "cuda:0"
+v, vi, H, W = scenes.config_mesh(a.config, device=dev)
+N = v.shape[0]
+vi3 = vi[None].expand(N, -1, -1)
+attr = scenes.vertex_attributes(N, v.shape[1], a.C, seed=1, device=dev)
+w = th.rand((N, a.C, H, W), device=dev)
+depth, index = _ops.rasterize(v, vi3, H, W)
+_, bary = _ops.render_forward(v, vi3, index)
+img = _ops.interpolate_forward(attr, vi3, index, bary)
+
+def timeit(fn):
+    for _ in range(3): fn()
+    th.cuda.synchronize()
+    evs = []
+    for _ in range(a.iters):
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        e0.record(); out = fn(); e1.record(); evs.append((e0, e1))
+    th.cuda.synchronize()
+    ts = sorted(x.elapsed_time(y) for x, y in evs)
+    return ts[len(ts) // 2], ts[0], out
+
+OPS = {
+    "rasterize": lambda: _ops.rasterize(v, vi3, H, W),
+    "render_fwd": lambda: _ops.render_forward(v, vi3, index),
+    "interp_fwd": lambda: _ops.interpolate_forward(attr, vi3, index, bary),
+    "interp_bwd": lambda: _ops.interpolate_backward(w, attr, vi3, index, bary, True, True),
+    "interp_bwd_v": lambda: _ops.interpolate_backward(w, attr, vi3, index, bary, True, False),
+    "interp_bwd_b": lambda: _ops.interpolate_backward(w, attr, vi3, index, bary, False, True),
+    "render_bwd": lambda: _ops.render_backward(v, vi3, index, None, bary),
+    "edge_fused": lambda: _ops.edge_grad_backward_fused(v, img, index, vi3, w, bary, 1e4),
+}
+variants = [""] + [e for e in a.env.split(",") if e]
+for op in a.ops.split(","):
+    base = None
+    for var in variants:
+        if var:
+            k, val = var.split("="); os.environ[k] = val
+        med, mn, out = timeit(OPS[op])
+        if var:
+            del os.environ[var.split("=")[0]]
+        outs = [o for o in (out if isinstance(out, tuple) else (out,)) if o is not None]
+        msg = ""
+        if base is None:
+            base = outs
+        else:
+            for i, (x, y) in enumerate(zip(outs, base)):
+                d = (x.float() - y.float()).abs().max().item(); sc = y.float().abs().max().item()
+                msg += f" out{i}: maxdiff {d:.3e} (scale {sc:.3e})"
+        print(f"{op:14s} {var or 'default':28s} median {med:.4f} ms  min {mn:.4f} ms{msg}", flush=True)
