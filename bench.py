@@ -60,7 +60,7 @@ ALGO_BYTES_PER_PX = {
 }
 # CUDA kernels launched by libdrtk_b200.so per op call (memsets are driver operations, not counted)
 KERNELS = {"rasterize": 4, "render_fwd": 1, "interpolate_fwd": 1, "edge_grad_bwd_fused": 2,
-           "interpolate_bwd": 1, "render_bwd": 3}
+           "interpolate_bwd": 2, "render_bwd": 3}
 
 
 def load_peaks():
@@ -72,47 +72,71 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed regions (B200_PROFILING.md recipe), through NVML
+    in a background thread (every ~2 ms; an nvidia-smi subprocess takes longer to start than the 10-step
+    timed region lasts).  Falls back to one nvidia-smi query when pynvml is unavailable."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.stop_flag, self.h, self.index = [], False, None, index
+        self.windows = []
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except Exception:
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.h = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for nm, val in zip(names, r[3:7]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.perf_counter(), sm, rs))
             except Exception:
                 pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            time.sleep(0.002)
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
+    def stop(self):
+        if self.h is None:
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=10).stdout.split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "samples": 1, "reasons": [],
+                        "note": "pynvml unavailable: one nvidia-smi sample after the timed region"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml and nvidia-smi unavailable"]}
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        inside = [r for r in self.rows if any(a <= r[0] <= b for a, b in self.windows)] or self.rows
+        sm = [r[1] for r in inside]
+        mask = 0
+        for r in inside:
+            mask |= r[2]
+        reasons = sorted(nm for bit, nm in self.REASONS.items() if mask & bit)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.max_sm), "samples": len(sm),
+                "reasons": reasons}
 
 
 def make_inputs(cfg, device, seed_offset=0):
@@ -334,6 +358,7 @@ def main():
     def timed_region(step_fn, steps, finish=None):
         barrier()
         e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
             step_fn()
@@ -341,23 +366,38 @@ def main():
             finish()
         e1.record()
         barrier()
+        if sampler is not None:
+            sampler.window(w0, time.perf_counter())
         ms = th.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_device()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     timing_on[0] = True
     ms_step = timed_region(step_device, args.steps)
     timing_on[0] = False
-    clocks = sampler.stop() if sampler else None
 
     for _ in range(3):
         step_e2e()
     e2e_finish()
     ms_e2e = timed_region(step_e2e, args.steps, e2e_finish)
+    clocks = sampler.stop() if sampler else None
+
+    # host <-> device copy bandwidth of this box (context for e2e: 62 MB cross PCIe every step)
+    pcie = None
+    if rank == 0:
+        big_h = th.empty(64 << 20, dtype=th.uint8).pin_memory()
+        big_d = th.empty(64 << 20, dtype=th.uint8, device=dev)
+        def _bw(fn):
+            fn(); th.cuda.synchronize()
+            a0, a1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+            a0.record(); fn(); fn(); a1.record(); th.cuda.synchronize()
+            return round(2 * (64 << 20) / (a0.elapsed_time(a1) * 1e-3) / 1e9, 1)
+        pcie = {"h2d_GBps": _bw(lambda: big_d.copy_(big_h, non_blocking=True)),
+                "d2h_GBps": _bw(lambda: big_h.copy_(big_d, non_blocking=True))}
 
     total_px = npx_rank * world
     value = total_px / (ms_step * 1e-3) / 1e6
@@ -400,7 +440,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "Mpix/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "pinned host v_pix/attr/vi copied in, grad_v + grad_attr (the step's result) copied out, every step, inside the timed region; copies double-buffered on side streams (prefetch of step k+1 / read-back of step k overlap compute)"},
         "gpu_launches": sum(KERNELS.values()) * args.steps,
-        "clocks": clocks, "roofline": roofline, "per_op": breakdown,
+        "clocks": clocks, "roofline": roofline, "per_op": breakdown, "pcie": pcie,
         "pipeline_algorithmic_GB_per_step": round(sum(ALGO_BYTES_PER_PX[k](C_ATTR) for k in KERNELS) * npx_rank / 1e9, 3),
     }
 

@@ -566,6 +566,7 @@ constexpr int kQSeg = 16;       // pixels per walker
 constexpr int kQCh = 16;        // channels per pass over a tile
 constexpr int kQUnit = 128;     // pixels per warp: 8 walkers x kQSeg (phase A) = 2 x 32 lanes x 2 px (phase B)
 constexpr int kQProducers = 2;  // 20 bulk copies per tile at ~0.145 us each per issuing thread
+constexpr int kQChunk = 8;      // tiles per scheduling chunk (see the tile order comment in the kernel)
 
 template <int TP>
 struct QStage {
@@ -691,7 +692,7 @@ __device__ __forceinline__ void bary_grad_pair(const float* __restrict__ gq_base
 template <int TP, bool NEED_VERT, bool NEED_BARY, bool AVEC, bool MULTI>
 __global__ void __launch_bounds__(32 * (TP / kQUnit * 2 + kQProducers), (TP <= 512) ? 2 : 1)
 interp_bwd_quad_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __restrict__ bary_grad,
-                       const int4* __restrict__ tab, int tab_img_stride, int tiles_per_img, int num_tiles, int dbg) {
+                       const int4* __restrict__ tab, int tab_img_stride, int tiles_per_img, int num_tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   QSmem<TP>& S = *reinterpret_cast<QSmem<TP>*>(smem_raw);
   constexpr int TEAM = TP / kQUnit;        // warps per team
@@ -709,15 +710,22 @@ interp_bwd_quad_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
   __syncthreads();
   const int nchunks = MULTI ? (a.C + kQCh - 1) / kQCh : 1;
   const int warp_role = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
-  // first tile of this CTA: image n, tile tl within the image; advanced incrementally (no division per tile)
-  const int step_n = (int)gridDim.x / tiles_per_img, step_t = (int)gridDim.x - step_n * tiles_per_img;
-  int n = (int)blockIdx.x / tiles_per_img, tl = (int)blockIdx.x - n * tiles_per_img;
+  // Tile order: chunks of kQChunk consecutive tiles are dealt round-robin to the CTAs (consecutive tiles share
+  // triangle-table lines and attribute rows in this SM's L1; a vertical-neighbour order was measured and made
+  // no difference: the kernel is bound by L1 data-pipe throughput, not by L2 latency).
+  auto decode = [&](int t, int& n, int& tl) {
+    n = t / tiles_per_img;
+    tl = t - n * tiles_per_img;
+  };
 
   if (warp_role >= CONSUMERS) {  // ---- producer warps: one bulk copy per plane ----
     if (lane == 0) {
       const int pw = warp_role - CONSUMERS;
       int item = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int t0 = blockIdx.x * kQChunk; t0 < num_tiles; t0 += gridDim.x * kQChunk)
+      for (int tile = t0; tile < min(t0 + kQChunk, num_tiles); ++tile) {
+        int n, tl;
+        decode(tile, n, tl);
         const int p0 = tl * TP;
         const uint32_t bytes = (uint32_t)min(TP, HW - p0) * 4u;
         for (int chunk = 0; chunk < nchunks; ++chunk, ++item) {
@@ -747,8 +755,6 @@ interp_bwd_quad_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
             bulk_g2s(dst, src, bytes, bar);
           }
         }
-        n += step_n; tl += step_t;
-        if (tl >= tiles_per_img) { tl -= tiles_per_img; ++n; }
       }
     }
     return;
@@ -759,7 +765,10 @@ interp_bwd_quad_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
   uint32_t phase_bits = 0;
   float gb[MULTI ? 2 : 1][2][3];  // phase-B accumulators: [pass][pixel][vertex], carried across channel passes (C > 16)
   int item = 0, seq = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++seq) {
+  for (int t0 = blockIdx.x * kQChunk; t0 < num_tiles; t0 += gridDim.x * kQChunk)
+  for (int tile = t0; tile < min(t0 + kQChunk, num_tiles); ++tile, ++seq) {
+    int n, tl;
+    decode(tile, n, tl);
     const int p0 = tl * TP;
     const int npx = min(TP, HW - p0);
     const bool a_team = ((team ^ seq) & 1) == 0;  // the teams swap roles every tile
@@ -775,16 +784,16 @@ interp_bwd_quad_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
         asm volatile("bar.sync 1, %0;" :: "n"(32 * CONSUMERS) : "memory");
       }
 
-      if (NEED_VERT && a_team && !(dbg & 4)) {  // ---- phase A: 8 walkers x 16 pixels, lane = 4 channels ----
+      if (NEED_VERT && a_team) {  // ---- phase A: 8 walkers x 16 pixels, lane = 4 channels ----
         const int q = lane & 3, seg = unit * kQUnit + (lane >> 2) * kQSeg;
         const bool c_on = 4 * q < nc;
         const int qq = c_on ? q : 0;
         walk_runs_quad<TP>(st.g + (4 * qq) * TP + qq * 4 + seg, st.idx + seg, st.bary + seg,
                            vert_grad + ((size_t)n * (size_t)a.V * (size_t)a.C + (size_t)(c0 + 4 * qq)), tabn,
-                           (unsigned)a.C, (c_on && !(dbg & 1)) ? 0 : -1);
+                           (unsigned)a.C, c_on ? 0 : -1);
       }
 
-      if (NEED_BARY && !a_team && !(dbg & 2)) {  // ---- phase B: 2 passes x (thread = 2 pixels) ----
+      if (NEED_BARY && !a_team) {  // ---- phase B: 2 passes x (thread = 2 pixels) ----
         // triangle rows of both passes are fetched up front (two dependent L2 round trips per pass otherwise)
         int2 qids[2];
         int4 t0s[2], t1s[2];
@@ -842,8 +851,6 @@ interp_bwd_quad_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
       __syncwarp();
       if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&S.empty[s]));
     }
-    n += step_n; tl += step_t;
-    if (tl >= tiles_per_img) { tl -= tiles_per_img; ++n; }
   }
 }
 
@@ -961,10 +968,10 @@ extern "C" int drtk_b200_interpolate_backward(
         if (e != cudaSuccess) { rc2 = (int)e; return; }
         const int tiles_per_img = (int)((H * W + QTP - 1) / QTP);
         const int64_t ctas = 2 * kNumSMs;  // two co-resident CTAs per SM
-        const unsigned grid = (unsigned)(tiles_q < ctas ? tiles_q : ctas);
+        const int64_t chunks = (tiles_q + kQChunk - 1) / kQChunk;
+        const unsigned grid = (unsigned)(chunks < ctas ? chunks : ctas);
         kern<<<grid, 32 * (QTP / kQUnit * 2 + kQProducers), smem, stream>>>(
-            b, vert_attributes_grad, bary_img_grad, tab, tab_imgs == 1 ? 0 : (int)F, tiles_per_img, (int)tiles_q,
-            getenv("DRTK_B200_DBG") ? atoi(getenv("DRTK_B200_DBG")) : 0);
+            b, vert_attributes_grad, bary_img_grad, tab, tab_imgs == 1 ? 0 : (int)F, tiles_per_img, (int)tiles_q);
       };
 #define DRTK_Q5(MULTI)                                                                                     \
       do {                                                                                                   \
