@@ -348,7 +348,7 @@ __device__ __forceinline__ void scatter_pixel(const EdgeArgs& a, const FusedArgs
   }
 }
 
-__global__ void __launch_bounds__(kStripWarps * 32) edge_grad_strip_kernel(EdgeArgs a, FusedArgs fz,
+__global__ void __launch_bounds__(kStripWarps * 32, 4) edge_grad_strip_kernel(EdgeArgs a, FusedArgs fz,
                                                                            const float4* __restrict__ table,
                                                                            int strips_per_row, int64_t num_strips) {
   __shared__ int s_own[kStripWarps][kStripPx + 1];

@@ -359,8 +359,14 @@ __global__ void __launch_bounds__(kRasterThreads) raster_tiles_kernel(
       unsigned long long* zrow = zbuf + (ly << kTileLog) - x_lo;
       for (int x = gxs; x <= gxe; ++x) {
         uint32_t db;
-        if (sample(ox, ay, tl, rden, d0, d1, d2, (float)x, row, db))
-          atomicMin(zrow + x, ((unsigned long long)db << 32) | f);  // (:155-161)
+        if (sample(ox, ay, tl, rden, d0, d1, d2, (float)x, row, db)) {
+          // (:155-161) packed minimum.  The first write to a pixel is by far the common case: one native
+          // compare-and-swap against "empty" settles it without the load + compare + CAS loop that a 64-bit
+          // shared-memory atomicMin compiles to; only a pixel that is already taken pays for the loop.
+          const unsigned long long key = ((unsigned long long)db << 32) | f;
+          const unsigned long long old = atomicCAS(zrow + x, ~0ull, key);
+          if (old != ~0ull && key < old) atomicMin(zrow + x, key);
+        }
       }
     }
   }

@@ -1,28 +1,23 @@
-"""Per-source-line instruction / stall-sample digest of one kernel in an .ncu-rep (run here, no GPU).
-usage: python tools/ncu_lines.py rep kernel_regex [topN]"""
-import csv, io, os, subprocess, sys
+"""Per-CUDA-source-line digest (instructions executed, stall samples) of one kernel in an .ncu-rep (run here, no GPU).
+usage: python tools/ncu_lines.py rep kernel_regex [topN]   (all captured instances are summed)"""
+import collections, csv, io, subprocess, sys
 rep, sub = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda", "-k", f"regex:{sub}"],
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda", "--kernel-name", f"regex:{sub}"],
                      capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(out)))
-hdr, cur, body = None, "?", []
-for r in rows:
+hdr, fname, agg = None, "?", collections.OrderedDict()
+def num(x):
+    try: return float(x)
+    except ValueError: return 0.0
+for r in csv.reader(io.StringIO(out)):
     if not r: continue
-    if r[0] == "File Path": cur = os.path.basename(r[1]); continue
-    if r[0] == "Line No": hdr = r; continue
-    if hdr and r[0].isdigit() and len(r) >= len(hdr) - 1: body.append((cur, r))
-ci = {}
-for i, h in enumerate(hdr): ci.setdefault(h, i)
-def num(r, k):
-    try: return float(r[ci[k]])
-    except (ValueError, KeyError, IndexError): return 0.0
-tot_i = sum(num(r, "Instructions Executed") for _, r in body)
-tot_s = sum(num(r, "# Samples") for _, r in body)
-print(f"total warp instructions {tot_i:.0f}, samples {tot_s:.0f}")
-body.sort(key=lambda fr: -num(fr[1], "# Samples"))
-for f, r in body[:top]:
-    st = {k: num(r, k) for k in hdr if k.startswith("stall_") and "Not Issued" not in k}
-    top2 = sorted(st.items(), key=lambda kv: -kv[1])[:2]
-    print(f"{f[:14]:14s}{r[0]:>4} inst {100*num(r,'Instructions Executed')/max(tot_i,1):5.1f}% samp {100*num(r,'# Samples')/max(tot_s,1):5.1f}% "
-          f"{' '.join(f'{k[6:]}={v:.0f}' for k, v in top2):30s} | {r[1].strip()[:100]}")
+    if r[0] == "File Path": fname = r[1].split("/")[-1]; continue
+    if r[0] == "Line No": hdr = r; iE, iS = r.index("Instructions Executed"), r.index("# Samples"); continue
+    if hdr and r[0].isdigit():
+        k = (fname, int(r[0]))
+        if k not in agg: agg[k] = [0.0, 0.0, r[1]]
+        agg[k][0] += num(r[iE]); agg[k][1] += num(r[iS])
+totE = sum(v[0] for v in agg.values()) or 1; totS = sum(v[1] for v in agg.values()) or 1
+print(f"total warp instructions {totE:.0f}, samples {totS:.0f}")
+for (f, l), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    print(f"{f[:14]:14s} L{l:>4} inst {100*v[0]/totE:5.2f}% samp {100*v[1]/totS:5.2f}% | {v[2].strip()[:105]}")
