@@ -89,6 +89,16 @@ __device__ __forceinline__ void stg_stream_i4(int32_t* p, int4 v) {
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// 256-bit global load (sm_100+, SASS LDG.E.ENL2.256): address must be 32-B aligned
+struct float8 { float4 lo, hi; };
+__device__ __forceinline__ float8 ldg_f8(const float* p) {
+  float8 r;
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+               : "l"(p));
+  return r;
+}
+
 __device__ __forceinline__ void prefetch_l1(const void* p) {
   asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
 }

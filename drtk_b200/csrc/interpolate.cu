@@ -652,7 +652,7 @@ __device__ __forceinline__ void walk_runs_quad(const float* __restrict__ gp, con
 // Phase B of one thread: two adjacent pixels, NC channels of the staged gradients against the three attribute
 // rows of each pixel's triangle (rows are shared when both pixels show the same triangle).  NC > 0: compile-
 // time channel count (full unroll, immediate offsets); NC == 0: nc channels at run time.
-template <int TP, int NC>
+template <int TP, int NC, bool V8>
 __device__ __forceinline__ void bary_grad_pair(const float* __restrict__ gq_base, const float* __restrict__ an,
                                                unsigned rs, int4 t0, int4 t1, bool same, int nc,
                                                float (&g0)[3], float (&g1)[3]) {
@@ -679,7 +679,28 @@ __device__ __forceinline__ void bary_grad_pair(const float* __restrict__ gq_base
     g1[1] = fmaf(gq[3].y, A1.w, fmaf(gq[2].y, A1.z, fmaf(gq[1].y, A1.y, fmaf(gq[0].y, A1.x, g1[1]))));
     g1[2] = fmaf(gq[3].y, A2.w, fmaf(gq[2].y, A2.z, fmaf(gq[1].y, A2.y, fmaf(gq[0].y, A2.x, g1[2]))));
   };
-  if (NC > 0) {
+  // 256-bit row loads (attribute rows 32-B aligned; SASS LDG.E.ENL2.256): half the load instructions and L1
+  // tag requests of the gathers (0.779 -> 0.750 ms)
+  auto group8 = [&](int cc) {
+    float2 gq[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gq[k] = *reinterpret_cast<const float2*>(gq_base + (cc + k) * TP + ((cc + k) >> 2) * 4);
+    float8 A0 = ldg_f8(r00 + cc), A1 = ldg_f8(r01 + cc), A2 = ldg_f8(r02 + cc);
+    auto dot8 = [&](const float8& A, float acc, bool second) {
+      const float x0 = second ? gq[0].y : gq[0].x, x1 = second ? gq[1].y : gq[1].x, x2 = second ? gq[2].y : gq[2].x,
+                  x3 = second ? gq[3].y : gq[3].x, x4 = second ? gq[4].y : gq[4].x, x5 = second ? gq[5].y : gq[5].x,
+                  x6 = second ? gq[6].y : gq[6].x, x7 = second ? gq[7].y : gq[7].x;
+      acc = fmaf(x3, A.lo.w, fmaf(x2, A.lo.z, fmaf(x1, A.lo.y, fmaf(x0, A.lo.x, acc))));
+      return fmaf(x7, A.hi.w, fmaf(x6, A.hi.z, fmaf(x5, A.hi.y, fmaf(x4, A.hi.x, acc))));
+    };
+    g0[0] = dot8(A0, g0[0], false); g0[1] = dot8(A1, g0[1], false); g0[2] = dot8(A2, g0[2], false);
+    if (!same) { A0 = ldg_f8(r10 + cc); A1 = ldg_f8(r11 + cc); A2 = ldg_f8(r12 + cc); }
+    g1[0] = dot8(A0, g1[0], true); g1[1] = dot8(A1, g1[1], true); g1[2] = dot8(A2, g1[2], true);
+  };
+  if (NC > 0 && V8) {
+#pragma unroll
+    for (int cc = 0; cc < NC; cc += 8) group8(cc);
+  } else if (NC > 0) {
 #pragma unroll
     for (int cc = 0; cc < NC; cc += 4) group(cc);
   } else {
@@ -692,7 +713,7 @@ __device__ __forceinline__ void bary_grad_pair(const float* __restrict__ gq_base
 template <int TP, bool NEED_VERT, bool NEED_BARY, bool AVEC, bool MULTI>
 __global__ void __launch_bounds__(32 * (TP / kQUnit * 2 + kQProducers), (TP <= 512) ? 2 : 1)
 interp_bwd_quad_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __restrict__ bary_grad,
-                       const int4* __restrict__ tab, int tab_img_stride, int tiles_per_img, int num_tiles) {
+                       const int4* __restrict__ tab, int tab_img_stride, int tiles_per_img, int num_tiles, bool v8) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   QSmem<TP>& S = *reinterpret_cast<QSmem<TP>*>(smem_raw);
   constexpr int TEAM = TP / kQUnit;        // warps per team
@@ -818,8 +839,9 @@ interp_bwd_quad_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
           const float* gq_base = st.g + x;
           if (AVEC) {
             const float* an = a.attr + ((size_t)n * (size_t)a.as.s0 + (size_t)c0);  // s2 == 1 on this path
-            if (nc == kQCh) bary_grad_pair<TP, kQCh>(gq_base, an, (unsigned)a.as.s1, t0, t1, same, nc, g0, g1);
-            else bary_grad_pair<TP, 0>(gq_base, an, (unsigned)a.as.s1, t0, t1, same, nc, g0, g1);
+            if (nc == kQCh && v8) bary_grad_pair<TP, kQCh, true>(gq_base, an, (unsigned)a.as.s1, t0, t1, same, nc, g0, g1);
+            else if (nc == kQCh) bary_grad_pair<TP, kQCh, false>(gq_base, an, (unsigned)a.as.s1, t0, t1, same, nc, g0, g1);
+            else bary_grad_pair<TP, 0, false>(gq_base, an, (unsigned)a.as.s1, t0, t1, same, nc, g0, g1);
           } else {
             const float* an = a.attr + (int64_t)n * a.as.s0 + (int64_t)c0 * a.as.s2;
             const float* r00 = an + (int64_t)t0.x * a.as.s1; const float* r01 = an + (int64_t)t0.y * a.as.s1;
@@ -962,6 +984,9 @@ extern "C" int drtk_b200_interpolate_backward(
       DRTK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tab), sizeof(int4) * (size_t)(tab_imgs * F), stream));
       const int64_t total = tab_imgs * F;
       vi_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(vi, b.f.vis, (int)F, total, tab);
+      // 256-bit attribute-row loads need 32-B aligned rows
+      const bool v8 = avec && (b.f.as.s1 % 8 == 0) && (b.f.as.s0 % 8 == 0) && (C % 8 == 0) &&
+                      (reinterpret_cast<uintptr_t>(vert_attributes) % 32 == 0);
       auto launch5 = [&](auto kern) {
         const size_t smem = sizeof(QSmem<QTP>) + 128;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -971,7 +996,7 @@ extern "C" int drtk_b200_interpolate_backward(
         const int64_t chunks = (tiles_q + kQChunk - 1) / kQChunk;
         const unsigned grid = (unsigned)(chunks < ctas ? chunks : ctas);
         kern<<<grid, 32 * (QTP / kQUnit * 2 + kQProducers), smem, stream>>>(
-            b, vert_attributes_grad, bary_img_grad, tab, tab_imgs == 1 ? 0 : (int)F, tiles_per_img, (int)tiles_q);
+            b, vert_attributes_grad, bary_img_grad, tab, tab_imgs == 1 ? 0 : (int)F, tiles_per_img, (int)tiles_q, v8);
       };
 #define DRTK_Q5(MULTI)                                                                                     \
       do {                                                                                                   \
