@@ -49,8 +49,6 @@ def rasterize(v, vi, height, width, wireframe=False, algo=0):
     _chk(v.size(1) < 0x10000000, f"rasterize(): expected second dim of v to be less or eual to 268435456, but got {v.size(1)}")
     _chk(height > 0 and width > 0,
          f"rasterize(): both height and width have to be greater than zero, but got height: {height}, and width: {width}")
-    if wireframe:
-        raise NotImplementedError("rasterize(): wireframe mode is not implemented in drtk_b200 yet")
     lib = _lib.load()
     N, V, F = v.size(0), v.size(1), vi.size(1)
     H, W = int(height), int(width)

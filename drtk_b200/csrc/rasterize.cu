@@ -469,6 +469,182 @@ __global__ void __launch_bounds__(256) unpack_kernel(const unsigned long long* _
   depth_img[i] = d == 0xFFFFFFFFu ? 0.f : __uint_as_float(d);
 }
 
+// ------------------------------------------------------------------------------------------
+// wireframe (src/rasterize/rasterize_kernel.cu:171-400 of the reference)
+// ------------------------------------------------------------------------------------------
+// A pixel belongs to the wireframe when one of the (visible) edges of a triangle crosses the diamond
+// |dx| + |dy| = 0.5 around the pixel centre (:220-259); the triangle's interior still writes depth with id
+// 0xFFFFFFFF (= -1) so that it occludes lines behind it (:376-393).  Edge visibility = bits 0-2 of the top
+// nibble of vi[..., 0] (:293-303); bounding box padded by 2 and clamped to [1, W-2] x [1, H-2] (:333-337).
+//
+// Arithmetic: pinned with intrinsics to the reference build's compiled form (see below), like the fill path;
+// tests compare index_img / depth_img bit for bit with the reference CUDA kernel.
+// Organisation: one WARP per triangle, lanes stride over the padded bounding box (the reference walks it
+// with one thread), 64-bit global atomicMin into the packed image, then unpack_kernel.
+// The arithmetic of the diamond test is pinned to the reference build's sm_100 SASS (rasterize_lines_kernel
+// <float,int>, all .FTZ), like the fill path: a knife-edge crossing point decides whether a pixel carries a
+// triangle id, so the roundings must be the reference's (a version left to the compiler's own contraction
+// choices differed in 2 of 2 M pixels at config 3).  For a triangle edge (p1, p2) with line (:171-181)
+//   a1 = p1.y - p2.y,  b1 = p2.x - p1.x,  c1 = fma(p1.x, p2.y, -rn(p1.y * p2.x))
+// and a diamond side (s0, s1) with a2 = s0.y - s1.y, b2 = s1.x - s0.x, c2 (see DiamondSides):
+//   d  = fma(a1, b2, -rn(b1 * a2));  r = MUFU.RCP(d)
+//   cx = rn(fma(b1, c2, -rn(c1 * b2)) * r);  cy = rn(fma(c1, a2, -rn(a1 * c2)) * r)       (:193-203)
+//   d == 0  ->  (FLT_MAX, 0)
+struct Line { float a, b, c; };
+__device__ __forceinline__ Line line_through(float p1x, float p1y, float p2x, float p2y) {
+  Line l;
+  l.a = sub_rn(p1y, p2y);
+  l.b = sub_rn(p2x, p1x);
+  l.c = fma_rn(p1x, p2y, -mul_rn(p1y, p2x));
+  return l;
+}
+__device__ __forceinline__ bool within(float p1x, float p1y, float p2x, float p2y, float cx, float cy) {  // (:183-191)
+  return (((p2x >= cx) && (cx >= p1x)) || ((p2x <= cx) && (cx <= p1x))) &&
+         (((p2y >= cy) && (cy >= p1y)) || ((p2y <= cy) && (cy <= p1y)));
+}
+// the four sides of the diamond around (px, py), shared by the three edges of a triangle (:229-256):
+// side k runs s0 -> s1 with  1: (px, py-.5) -> (px+.5, py)   2: (px+.5, py) -> (px, py+.5)
+//                            3: (px, py+.5) -> (px-.5, py)   4: (px-.5, py) -> (px, py-.5)
+// c2 = s0.x * s1.y - s1.x * s0.y shares the rounded product pp = rn(py * px) between the sides.
+struct DiamondSides {
+  float s0x[4], s0y[4], s1x[4], s1y[4], a2[4], b2[4], c2[4];
+};
+__device__ __forceinline__ void diamond_sides(float px, float py, DiamondSides& s) {
+  const float xh = __fadd_rn(px, 0.5f), xl = __fadd_rn(px, -0.5f);
+  const float yh = __fadd_rn(py, 0.5f), yl = __fadd_rn(py, -0.5f);
+  const float pp = mul_rn(py, px);
+  s.s0x[0] = px; s.s0y[0] = yl; s.s1x[0] = xh; s.s1y[0] = py;
+  s.s0x[1] = xh; s.s0y[1] = py; s.s1x[1] = px; s.s1y[1] = yh;
+  s.s0x[2] = px; s.s0y[2] = yh; s.s1x[2] = xl; s.s1y[2] = py;
+  s.s0x[3] = xl; s.s0y[3] = py; s.s1x[3] = px; s.s1y[3] = yl;
+  s.a2[0] = sub_rn(yl, py); s.b2[0] = sub_rn(xh, px); s.c2[0] = fma_rn(-yl, xh, pp);
+  s.a2[1] = sub_rn(py, yh); s.b2[1] = sub_rn(px, xh); s.c2[1] = fma_rn(yh, xh, -pp);
+  s.a2[2] = sub_rn(yh, py); s.b2[2] = sub_rn(xl, px); s.c2[2] = fma_rn(-yh, xl, pp);
+  s.a2[3] = sub_rn(py, yl); s.b2[3] = sub_rn(px, xl); s.c2[3] = fma_rn(yl, xl, -pp);
+}
+__device__ __forceinline__ bool crosses_diamond(const Line& l, float p1x, float p1y, float p2x, float p2y,
+                                                const DiamondSides& s) {
+  bool hit = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float d = fma_rn(l.a, s.b2[k], -mul_rn(l.b, s.a2[k]));
+    float cx = 3.402823466e+38f, cy = 0.f;  // TVec2{max}: x = FLT_MAX, y = 0 (:198)
+    if (d != 0.f) {
+      const float r = rcp_approx(d);
+      cx = mul_rn(fma_rn(l.b, s.c2[k], -mul_rn(l.c, s.b2[k])), r);
+      cy = mul_rn(fma_rn(l.c, s.a2[k], -mul_rn(l.a, s.c2[k])), r);
+    }
+    hit |= within(s.s0x[k], s.s0y[k], s.s1x[k], s.s1y[k], cx, cy) && within(p1x, p1y, p2x, p2y, cx, cy);
+  }
+  return hit;
+}
+// edge_function(a -> b, p) = v_ap.y * v_ab.x - v_ap.x * v_ab.y (:19-27) as the reference build rounds it in THIS
+// kernel (read from the sm_100 SASS of rasterize_lines_kernel<float,int>): the product with the x-dependent
+// factor is rounded and the other one fused, fma(v_ab.x, v_ap.y, -rn(v_ab.y * v_ap.x)) -- except for edge 0 in
+// its canonical orientation, whose y product the compiler hoisted out of the x loop:
+// fma(-v_ab.y, v_ap.x, rn(v_ap.y * v_ab.x)) (the form of the fill kernel).
+__device__ __forceinline__ float edge_fn(float pax, float pay, float pbx, float pby, float px, float py) {
+  const float abx = sub_rn(pbx, pax), aby = sub_rn(pby, pay);
+  const float apx = sub_rn(px, pax), apy = sub_rn(py, pay);
+  return fma_rn(abx, apy, -mul_rn(aby, apx));
+}
+__device__ __forceinline__ float edge_fn_hoisted(float pax, float pay, float pbx, float pby, float px, float py) {
+  const float abx = sub_rn(pbx, pax), aby = sub_rn(pby, pay);
+  const float apx = sub_rn(px, pax), apy = sub_rn(py, pay);
+  return fma_rn(-aby, apx, mul_rn(apy, abx));
+}
+template <bool EDGE0>
+__device__ __forceinline__ float canon_edge_fn(int ia, int ib, float pax, float pay, float pbx, float pby, float px,
+                                               float py) {  // (:29-40)
+  if (ia <= ib) return EDGE0 ? edge_fn_hoisted(pax, pay, pbx, pby, px, py) : edge_fn(pax, pay, pbx, pby, px, py);
+  return -edge_fn(pbx, pby, pax, pay, px, py);
+}
+
+__global__ void __launch_bounds__(256) raster_lines_kernel(RasterArgs a, int64_t total,
+                                                           unsigned long long* __restrict__ packed_img) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t idx = warp0; idx < total; idx += nwarps) {
+    const int n = (int)(idx / a.F);
+    const int f = (int)(idx - (int64_t)n * a.F);
+    const int32_t* vip = a.vi + (int64_t)n * a.vis.s0 + (int64_t)f * a.vis.s1;
+    const uint32_t raw0 = (uint32_t)vip[0];
+    const int flag = (int)((raw0 & 0xF0000000u) >> 28);
+    const int i0 = (int)(raw0 & 0x0FFFFFFFu), i1 = vip[a.vis.s2], i2 = vip[2 * a.vis.s2];
+    if (i0 == i1 && i1 == i2) continue;  // (:296)
+    const bool vis0 = (flag & 1) != 0, vis1 = (flag & 2) != 0, vis2 = (flag & 4) != 0;
+    const float* vp = a.v + (int64_t)n * a.vs.s0;
+    const float* q0 = vp + (int64_t)i0 * a.vs.s1;
+    const float* q1 = vp + (int64_t)i1 * a.vs.s1;
+    const float* q2 = vp + (int64_t)i2 * a.vs.s1;
+    const float p0x = q0[0], p0y = q0[a.vs.s2], z0 = q0[2 * a.vs.s2];
+    const float p1x = q1[0], p1y = q1[a.vs.s2], z1 = q1[2 * a.vs.s2];
+    const float p2x = q2[0], p2y = q2[a.vs.s2], z2 = q2[2 * a.vs.s2];
+    if (!(z0 > 1e-8f && z1 > 1e-8f && z2 > 1e-8f)) continue;  // (:321)
+    const float mnx = fminf(fminf(p0x, p1x), p2x), mny = fminf(fminf(p0y, p1y), p2y);
+    const float mxx = fmaxf(fmaxf(p0x, p1x), p2x), mxy = fmaxf(fmaxf(p0y, p1y), p2y);
+    if (!(mnx <= (float)(a.W - 1) && mny <= (float)(a.H - 1) && mxx > 0.f && mxy > 0.f)) continue;  // (:322-323)
+    const float v01x = sub_rn(p1x, p0x), v01y = sub_rn(p1y, p0y);
+    const float v02x = sub_rn(p2x, p0x), v02y = sub_rn(p2y, p0y);
+    const float v12x = sub_rn(p2x, p1x), v12y = sub_rn(p2y, p1y);
+    const float den = diff_of_products(v01x, v02y, v01y, v02x);  // (:330)
+    if (den == 0.f) continue;
+    const int bx0 = max(1, (int)mnx - 2), by0 = max(1, (int)mny - 2);  // (:333-337)
+    const int bx1 = min(a.W - 2, (int)mxx + 2), by1 = min(a.H - 2, (int)mxy + 2);
+    if (bx0 > bx1 || by0 > by1) continue;
+    const float sgn = den > 0.f ? 1.f : (den < 0.f ? -1.f : 0.f);
+    bool tl0, tl1, tl2;  // (:361-369)
+    if (den > 0.f) {
+      tl0 = (v12y < 0.f) || (v12y == 0.f && v12x > 0.f);
+      tl1 = (v02y > 0.f) || (v02y == 0.f && v02x < 0.f);
+      tl2 = (v01y < 0.f) || (v01y == 0.f && v01x > 0.f);
+    } else {
+      tl0 = (v12y > 0.f) || (v12y == 0.f && v12x < 0.f);
+      tl1 = (v02y < 0.f) || (v02y == 0.f && v02x > 0.f);
+      tl2 = (v01y > 0.f) || (v01y == 0.f && v01x < 0.f);
+    }
+    const Line l01 = line_through(p0x, p0y, p1x, p1y), l12 = line_through(p1x, p1y, p2x, p2y),
+               l02 = line_through(p0x, p0y, p2x, p2y);
+    unsigned long long* img = packed_img + (int64_t)n * a.H * a.W;
+    // Work split: lane = (row within a block of 16 rows, left / right half of the row).
+    const int bw = bx1 - bx0 + 1, rows = by1 - by0 + 1, half = (bw + 1) >> 1;
+    const int xa = bx0 + (lane & 1) * half, xb = min(bx1, xa + half - 1);
+    for (int ry = lane >> 1; ry < rows; ry += 16) {
+      const int y = by0 + ry;
+      const float py = (float)y;
+      for (int x = xa; x <= xb; ++x) {
+      const float px = (float)x;
+      DiamondSides ds;
+      diamond_sides(px, py, ds);
+      bool hit = false;  // (:343-346)
+      hit |= crosses_diamond(l01, p0x, p0y, p1x, p1y, ds) && vis0;
+      hit |= crosses_diamond(l12, p1x, p1y, p2x, p2y, ds) && vis1;
+      hit |= crosses_diamond(l02, p0x, p0y, p2x, p2y, ds) && vis2;
+      float b0 = canon_edge_fn<true>(i1, i2, p1x, p1y, p2x, p2y, px, py);  // (:348-353)
+      float b1 = canon_edge_fn<false>(i2, i0, p2x, p2y, p0x, p0y, px, py);
+      float b2 = canon_edge_fn<false>(i0, i1, p0x, p0y, p1x, p1y, px, py);
+      b0 = mul_rn(b0, sgn); b1 = mul_rn(b1, sgn); b2 = mul_rn(b2, sgn);
+      const bool inside = (b0 >= 0.f) && (b1 >= 0.f) && (b2 >= 0.f);
+      const bool keep = inside && !((b0 == 0.f && !tl0) || (b1 == 0.f && !tl1) || (b2 == 0.f && !tl2));
+      if (keep || hit) {  // (:375-393)
+        // as compiled: FFMA.SAT(b, RCP(|den|), 0); (b0 + b1) + b2; b * RCP(sum); dot = FFMA(b2,d2, FFMA(b0,d0, FMUL(b1,d1)))
+        const float rad = rcp_approx(fabsf(den));
+        b0 = __saturatef(mul_rn(b0, rad)); b1 = __saturatef(mul_rn(b1, rad)); b2 = __saturatef(mul_rn(b2, rad));
+        const float rs = rcp_approx(__fadd_rn(b2, __fadd_rn(b0, b1)));
+        b0 = mul_rn(b0, rs); b1 = mul_rn(b1, rs); b2 = mul_rn(b2, rs);
+        const float d0 = rcp_approx(epsclamp(z0)), d1 = rcp_approx(epsclamp(z1)), d2 = rcp_approx(epsclamp(z2));
+        const float inv = fma_rn(b2, d2, fma_rn(b0, d0, mul_rn(b1, d1)));
+        const float depth = rcp_approx(epsclamp(inv));
+        const unsigned long long val = ((unsigned long long)__float_as_uint(depth) << 32) |
+                                       (hit ? (unsigned long long)(uint32_t)f : 0xFFFFFFFFull);
+        atomicMin(img + (int64_t)y * a.W + x, val);
+      }
+      }
+    }
+  }
+}
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct TiledWorkspace {
@@ -501,7 +677,9 @@ extern "C" size_t drtk_b200_rasterize_workspace_bytes(int64_t N, int64_t F, int6
                                                        int algo) {
   if (N <= 0 || H <= 0 || W <= 0 || F < 0) return 0;
   if (algo == 1) return sizeof(unsigned long long) * (size_t)(N * H * W) + 256;
-  return tiled_layout(N, F, H, W).total + 256;
+  const size_t lines = sizeof(unsigned long long) * (size_t)(N * H * W) + 256;  // wireframe mode uses the packed image
+  const size_t tiled = tiled_layout(N, F, H, W).total + 256;
+  return tiled > lines ? tiled : lines;
 }
 
 extern "C" int drtk_b200_rasterize(const float* v, const int64_t* v_strides, const int32_t* vi,
@@ -509,7 +687,6 @@ extern "C" int drtk_b200_rasterize(const float* v, const int64_t* v_strides, con
                                    int64_t H, int64_t W, int wireframe, int algo, float* depth_img,
                                    int32_t* index_img, void* workspace, size_t workspace_bytes,
                                    void* stream_) {
-  if (wireframe) return DRTK_B200_EUNSUPPORTED;
   if (N < 0 || F < 0 || V < 0 || H <= 0 || W <= 0) return DRTK_B200_EINVAL;
   if (N == 0) return 0;
   if (!depth_img || !index_img || !v_strides || !vi_strides) return DRTK_B200_EINVAL;
@@ -527,6 +704,21 @@ extern "C" int drtk_b200_rasterize(const float* v, const int64_t* v_strides, con
   a.tilesY = (int)((H + kTile - 1) >> kTileLog);
   const int64_t total = N * F;
   char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+
+  if (wireframe) {
+    unsigned long long* packed = reinterpret_cast<unsigned long long*>(ws);
+    const int64_t npx = N * H * W;
+    DRTK_CUDA(cudaMemsetAsync(packed, 0xFF, sizeof(unsigned long long) * (size_t)npx, stream));
+    if (total > 0) {
+      const int64_t want = (total * 32 + 255) / 256;
+      const int64_t cap = (int64_t)kNumSMs * 32;
+      raster_lines_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(a, total, packed);
+      DRTK_CHECK_LAUNCH();
+    }
+    unpack_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, stream>>>(packed, npx, depth_img, index_img);
+    DRTK_CHECK_LAUNCH();
+    return 0;
+  }
 
   if (algo == 1) {
     unsigned long long* packed = reinterpret_cast<unsigned long long*>(ws);

@@ -194,6 +194,138 @@ void FN(oracle_rasterize)(const REAL* v, const int32_t* vi, int64_t N, int64_t V
   }
 }
 
+/*
+ * rasterize, wireframe mode.  Restates rasterize_lines_kernel + unpack_kernel + memset
+ * (src/rasterize/rasterize_kernel.cu:171-400, :402-415, :484-488).  The reference has NO CPU twin for this
+ * mode (rasterize_kernel_cpu.cpp:257 raises), so this restatement follows the CUDA kernel -- with the FMA
+ * contractions of the reference's sm_100 build (noted per expression) and IEEE 1/x where the GPU uses
+ * MUFU.RCP -- and is pinned against tests/golden/wire_*.npz, which were written by the reference CUDA
+ * kernel on a B200 (tests/golden/make_golden_wireframe.py).  A pixel whose crossing point lands within
+ * rounding of a segment end may legitimately differ from the GPU (approximate reciprocal); the tests bound
+ * the number of such pixels and compare depths to a few ulp.
+ */
+static inline int FN(within)(REAL p1x, REAL p1y, REAL p2x, REAL p2y, REAL cx, REAL cy) { /* :183-191 */
+  return (((p2x >= cx) && (cx >= p1x)) || ((p2x <= cx) && (cx <= p1x))) &&
+         (((p2y >= cy) && (cy >= p1y)) || ((p2y <= cy) && (cy <= p1y)));
+}
+
+/* is_crossing_dimond (:220-259) for the edge (p1, p2) with line a1 x + b1 y + c1 = 0 (:171-181) */
+static inline int FN(crosses_diamond)(REAL a1, REAL b1, REAL c1, REAL p1x, REAL p1y, REAL p2x, REAL p2y,
+                                      REAL px, REAL py) {
+  const REAL h = (REAL)0.5;
+  const REAL xh = px + h, xl = px - h, yh = py + h, yl = py - h;
+  const volatile REAL pp = py * px;
+  /* side k: s0 -> s1 */
+  const REAL s0x[4] = {px, xh, px, xl}, s0y[4] = {yl, py, yh, py};
+  const REAL s1x[4] = {xh, px, xl, px}, s1y[4] = {py, yh, py, yl};
+  /* c2 = s0.x*s1.y - s1.x*s0.y: the product py*px is rounded, the other one fused */
+  const REAL c2[4] = {FMA(-yl, xh, pp), FMA(yh, xh, -pp), FMA(-yh, xl, pp), FMA(yl, xl, -pp)};
+  int hit = 0;
+  for (int k = 0; k < 4; ++k) {
+    const REAL a2 = s0y[k] - s1y[k], b2 = s1x[k] - s0x[k];
+    const volatile REAL t0 = b1 * a2;
+    const REAL d = FMA(a1, b2, -t0); /* :196 / :210 */
+    REAL cx = (sizeof(REAL) == 4) ? (REAL)3.402823466e+38f : (REAL)1.7976931348623157e308, cy = 0; /* :198 */
+    if (d != 0) {
+      const REAL r = (REAL)1 / d;
+      const volatile REAL t1 = c1 * b2;
+      const volatile REAL t2 = a1 * c2[k];
+      const volatile REAL nx = FMA(b1, c2[k], -t1), ny = FMA(c1, a2, -t2);
+      cx = nx * r; cy = ny * r;
+    }
+    hit |= FN(within)(s0x[k], s0y[k], s1x[k], s1y[k], cx, cy) && FN(within)(p1x, p1y, p2x, p2y, cx, cy);
+  }
+  return hit;
+}
+
+/* edge function as rounded in the lines kernel: fma(v_ab.x, v_ap.y, -rn(v_ab.y*v_ap.x)); `hoisted` selects
+ * the other contraction, used for edge 0 in canonical orientation (see drtk_b200/csrc/rasterize.cu)        */
+static inline REAL FN(edge_fn_lines)(REAL ax, REAL ay, REAL bx, REAL by, REAL px, REAL py, int hoisted) {
+  const REAL abx = bx - ax, aby = by - ay, apx = px - ax, apy = py - ay;
+  if (hoisted) { const volatile REAL t = apy * abx; return FMA(-aby, apx, t); }
+  const volatile REAL t = aby * apx;
+  return FMA(abx, apy, -t);
+}
+
+void FN(oracle_rasterize_lines)(const REAL* v, const int32_t* vi, int64_t N, int64_t V, int64_t F, int64_t H,
+                                int64_t W, int vi_batched, float* depth_img, int32_t* index_img) {
+  const int64_t HW = H * W;
+  for (int64_t n = 0; n < N; ++n) {
+    uint64_t* best = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)HW);
+    memset(best, 0xFF, sizeof(uint64_t) * (size_t)HW);
+    const REAL* vn = v + n * V * 3;
+    const int32_t* vin = vi + (vi_batched ? n * F * 3 : 0);
+    for (int64_t id = 0; id < F; ++id) {
+      const uint32_t raw0 = (uint32_t)vin[id * 3 + 0];
+      const int flag = (int)((raw0 & 0xF0000000u) >> 28);                                /* :293 */
+      const int32_t i0 = (int32_t)(raw0 & 0x0FFFFFFFu), i1 = vin[id * 3 + 1], i2 = vin[id * 3 + 2];
+      if (i0 == i1 && i1 == i2) continue;                                                /* :299 */
+      const int vis0 = (flag & 1) != 0, vis1 = (flag & 2) != 0, vis2 = (flag & 4) != 0;  /* :301-303 */
+      const REAL p0x = vn[i0 * 3 + 0], p0y = vn[i0 * 3 + 1], z0 = vn[i0 * 3 + 2];
+      const REAL p1x = vn[i1 * 3 + 0], p1y = vn[i1 * 3 + 1], z1 = vn[i1 * 3 + 2];
+      const REAL p2x = vn[i2 * 3 + 0], p2y = vn[i2 * 3 + 1], z2 = vn[i2 * 3 + 2];
+      if (!(z0 > (REAL)1e-8f && z1 > (REAL)1e-8f && z2 > (REAL)1e-8f)) continue;        /* :321 */
+      const REAL mnx = FMIN(FMIN(p0x, p1x), p2x), mny = FMIN(FMIN(p0y, p1y), p2y);
+      const REAL mxx = FMAX(FMAX(p0x, p1x), p2x), mxy = FMAX(FMAX(p0y, p1y), p2y);
+      if (!(mnx <= (REAL)(W - 1) && mny <= (REAL)(H - 1) && mxx > 0 && mxy > 0)) continue; /* :322-323 */
+      const REAL v01x = p1x - p0x, v01y = p1y - p0y, v02x = p2x - p0x, v02y = p2y - p0y;
+      const REAL v12x = p2x - p1x, v12y = p2y - p1y;
+      const volatile REAL tden = v01y * v02x;
+      const REAL den = FMA(v01x, v02y, -tden);                                           /* :330 */
+      if (den == 0) continue;
+      int64_t bx0 = (int64_t)FN(f2i_trunc)(mnx) - 2; if (bx0 < 1) bx0 = 1;               /* :333-337 */
+      int64_t by0 = (int64_t)FN(f2i_trunc)(mny) - 2; if (by0 < 1) by0 = 1;
+      int64_t bx1 = (int64_t)FN(f2i_trunc)(mxx) + 2; if (bx1 > W - 2) bx1 = W - 2;
+      int64_t by1 = (int64_t)FN(f2i_trunc)(mxy) + 2; if (by1 > H - 2) by1 = H - 2;
+      int tl[3];
+      FN(top_left)(den, v01x, v01y, v02x, v02y, v12x, v12y, tl);
+      const REAL s = FN(sgn)(den);
+      const REAL rad = (REAL)1 / (den < 0 ? -den : den);
+      const REAL d0 = (REAL)1 / FN(epsclamp)(z0), d1 = (REAL)1 / FN(epsclamp)(z1), d2 = (REAL)1 / FN(epsclamp)(z2);
+      /* lines of the three edges (:171-181): c = fma(p1.x, p2.y, -rn(p1.y*p2.x)) */
+      const volatile REAL tc01 = p0y * p1x, tc12 = p1y * p2x, tc02 = p0y * p2x;
+      const REAL a01 = p0y - p1y, b01 = p1x - p0x, c01 = FMA(p0x, p1y, -tc01);
+      const REAL a12 = p1y - p2y, b12 = p2x - p1x, c12 = FMA(p1x, p2y, -tc12);
+      const REAL a02 = p0y - p2y, b02 = p2x - p0x, c02 = FMA(p0x, p2y, -tc02);
+      for (int64_t y = by0; y <= by1; ++y) {
+        for (int64_t x = bx0; x <= bx1; ++x) {
+          const REAL px = (REAL)x, py = (REAL)y;
+          int hit = 0;                                                                  /* :343-346 */
+          hit |= FN(crosses_diamond)(a01, b01, c01, p0x, p0y, p1x, p1y, px, py) && vis0;
+          hit |= FN(crosses_diamond)(a12, b12, c12, p1x, p1y, p2x, p2y, px, py) && vis1;
+          hit |= FN(crosses_diamond)(a02, b02, c02, p0x, p0y, p2x, p2y, px, py) && vis2;
+          REAL b0 = (i1 <= i2) ? FN(edge_fn_lines)(p1x, p1y, p2x, p2y, px, py, 1) : -FN(edge_fn_lines)(p2x, p2y, p1x, p1y, px, py, 0);
+          REAL b1 = (i2 <= i0) ? FN(edge_fn_lines)(p2x, p2y, p0x, p0y, px, py, 0) : -FN(edge_fn_lines)(p0x, p0y, p2x, p2y, px, py, 0);
+          REAL b2 = (i0 <= i1) ? FN(edge_fn_lines)(p0x, p0y, p1x, p1y, px, py, 0) : -FN(edge_fn_lines)(p1x, p1y, p0x, p0y, px, py, 0);
+          b0 *= s; b1 *= s; b2 *= s;                                                     /* :354 */
+          const int inside = (b0 >= 0) && (b1 >= 0) && (b2 >= 0);
+          const int keep = inside && !((b0 == 0 && !tl[0]) || (b1 == 0 && !tl[1]) || (b2 == 0 && !tl[2]));
+          if (!(keep || hit)) continue;                                                  /* :375 */
+          b0 *= rad; b1 *= rad; b2 *= rad;                                               /* :376-379 */
+          b0 = b0 < 0 ? 0 : (b0 > 1 ? 1 : b0); b1 = b1 < 0 ? 0 : (b1 > 1 ? 1 : b1); b2 = b2 < 0 ? 0 : (b2 > 1 ? 1 : b2);
+          const volatile REAL s01 = b0 + b1;
+          const REAL rs = (REAL)1 / (b2 + s01);
+          b0 *= rs; b1 *= rs; b2 *= rs;
+          const volatile REAL t = b1 * d1;
+          const REAL inv = FMA(b2, d2, FMA(b0, d0, t));                                  /* :382-383 */
+          const float depth_f = (float)((REAL)1 / FN(epsclamp)(inv));
+          uint32_t dbits; memcpy(&dbits, &depth_f, 4);
+          const uint64_t packed = ((uint64_t)dbits << 32) | (hit ? (uint64_t)(uint32_t)id : 0xFFFFFFFFull); /* :386-388 */
+          const int64_t o = y * W + x;
+          if (packed < best[o]) best[o] = packed;
+        }
+      }
+    }
+    for (int64_t o = 0; o < HW; ++o) { /* unpack :409-413 */
+      const uint32_t du = (uint32_t)(best[o] >> 32);
+      float df; memcpy(&df, &du, 4);
+      depth_img[n * HW + o] = (du == 0xFFFFFFFFu) ? 0.0f : df;
+      index_img[n * HW + o] = (int32_t)(uint32_t)(best[o] & 0xFFFFFFFFu);
+    }
+    free(best);
+  }
+}
+
 /* Per-pixel triangle fetch shared by render/interpolate: vi rows are NOT nibble-masked there
  * (src/render/render_kernel.cu:69-72).                                                     */
 #define FETCH_TRI(vin, t, i0, i1, i2) \

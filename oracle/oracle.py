@@ -76,6 +76,18 @@ def rasterize(v, vi, H, W, mode=0, with_margin=False):
     return (depth, index, margin) if with_margin else (depth, index)
 
 
+def rasterize_lines(v, vi, H, W):
+    """Wireframe mode -> (depth_img f32 [N,H,W], index_img i32 [N,H,W]); edge flags in the top nibble of vi[...,0]."""
+    v = _c(v)
+    N, V, _ = v.shape
+    vi, vb, F = _prep_vi(vi, N)
+    depth = np.empty((N, H, W), np.float32)
+    index = np.empty((N, H, W), np.int32)
+    fn = getattr(lib(), "oracle_rasterize_lines" + _sfx(v.dtype))
+    fn(_p(v), _p(vi), I64(N), I64(V), I64(F), I64(H), I64(W), ctypes.c_int(vb), _p(depth), _p(index))
+    return depth, index
+
+
 def render_fwd(v, vi, index_img):
     v = _c(v)
     N, V, _ = v.shape

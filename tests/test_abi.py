@@ -51,8 +51,8 @@ def test_argument_errors_do_not_need_a_gpu():
     from drtk_b200 import _lib
     lib = _lib.load()
     s3 = (ctypes.c_int64 * 3)(0, 3, 1)
-    # wireframe is declared unsupported; negative sizes are invalid; both return before any CUDA call
-    assert lib.drtk_b200_rasterize(None, s3, None, s3, 1, 1, 1, 8, 8, 1, 0, None, None, None, 0, None) == -3
+    # null outputs / negative sizes are invalid; both return before any CUDA call (wireframe or not)
+    assert lib.drtk_b200_rasterize(None, s3, None, s3, 1, 1, 1, 8, 8, 1, 0, None, None, None, 0, None) == -1
     assert lib.drtk_b200_rasterize(None, s3, None, s3, 1, 1, 1, -8, 8, 0, 0, None, None, None, 0, None) == -1
     # empty problems are a successful no-op
     assert lib.drtk_b200_render_forward(None, s3, None, s3, None, s3, 0, 0, 0, 0, 0, None, None, None) == 0
