@@ -48,9 +48,14 @@ const char* drtk_b200_error_string(int code);
  *   vi         [N,F,3] i32, strides vi_strides[3] (batch stride 0 for a shared topology)
  *   depth_img  [N,H,W] f32 out (0 where empty);  index_img [N,H,W] i32 out (-1 where empty)
  *   workspace  scratch of at least drtk_b200_rasterize_workspace_bytes(...) bytes
+ *   wireframe  0 = filled triangles (rasterize_kernel, :42-168)
+ *              1 = wireframe (rasterize_lines_kernel, :261-400): a pixel carries a triangle id when a visible
+ *                  edge crosses the diamond |dx|+|dy| = 0.5 around its centre; edge visibility = bits 28-30 of
+ *                  vi[..., 0]; interiors still write depth with index -1 (occluders)
  *   algo       0 = tile-binned, shared-memory z-buffer (default)
  *              1 = triangle-parallel 64-bit global atomicMin (validation path; same bits)
- * Bit-exact contract: depth_img / index_img equal the reference CUDA kernels' output.
+ *              (ignored in wireframe mode: one warp per triangle, packed global z-buffer)
+ * Bit-exact contract: depth_img / index_img equal the reference CUDA kernels' output, in both modes.
  * ------------------------------------------------------------------------------------- */
 size_t drtk_b200_rasterize_workspace_bytes(int64_t N, int64_t F, int64_t H, int64_t W, int algo);
 
