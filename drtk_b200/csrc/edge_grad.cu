@@ -67,8 +67,8 @@ struct GatherFetch {
 struct TableFetch {
   const float4* tn;  // table of image n
   __device__ __forceinline__ void operator()(int id, Tri2& t) const {
-    const float4 u = __ldg(tn + (int64_t)id * 2), w = __ldg(tn + (int64_t)id * 2 + 1);
-    derive_tri(u.x, u.y, u.z, u.w, w.x, w.y, t);
+    const float8 r = ldg_f8(reinterpret_cast<const float*>(tn + (int64_t)id * 2));  // one 256-bit load per 32-B row
+    derive_tri(r.lo.x, r.lo.y, r.lo.z, r.lo.w, r.hi.x, r.hi.y, t);
   }
 };
 
@@ -462,8 +462,8 @@ static int edge_launch(const float* v_pix, const int64_t* v_strides, const float
   if (fused && F > 0 && W % 8 == 0 && H > 1 && a.is.s2 == 1 && a.is.s1 % 4 == 0 && a.is.s0 % 4 == 0 && al16(index_img) &&
       F <= 65535LL * 256) {
     const size_t tb = (size_t)(N * F) * 32;
-    if (!workspace || workspace_bytes < tb || !al16(workspace)) return DRTK_B200_EWORKSPACE;
-    float4* table = static_cast<float4*>(workspace);
+    if (!workspace || workspace_bytes < tb + 32) return DRTK_B200_EWORKSPACE;
+    float4* table = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(workspace) + 31) & ~uintptr_t(31));
     xy_table_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)N), 256, 0, stream>>>(a, table);
     const int strips_per_row = (int)((W + kStripPx - 1) / kStripPx);
     const int64_t num_strips = N * (H - 1) * strips_per_row;
@@ -506,5 +506,5 @@ extern "C" int drtk_b200_edge_grad_backward_fused(
 }
 
 extern "C" size_t drtk_b200_edge_grad_backward_fused_workspace_bytes(int64_t N, int64_t F) {
-  return (N <= 0 || F <= 0) ? 0 : (size_t)(N * F) * 32;
+  return (N <= 0 || F <= 0) ? 0 : (size_t)(N * F) * 32 + 32;  // + slack to align the table to 32 B (256-bit loads)
 }

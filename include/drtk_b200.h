@@ -80,7 +80,7 @@ int drtk_b200_render_forward(const float* v, const int64_t* v_strides, const int
 /* render backward -- replaces render_cuda_backward (src/render/render_kernel.cu:382-436).
  *   grad_depth [N,H,W] (may be NULL = zeros), grad_bary [N,3,H,W] (may be NULL = zeros)
  *   grad_v     [N,V,3] f32 out, dense; every element written by the callee
- *   workspace  16-B aligned scratch of at least drtk_b200_render_backward_workspace_bytes(N,V,F)
+ *   workspace  scratch of at least drtk_b200_render_backward_workspace_bytes(N,V,F)
  *              bytes (per-triangle setup table + 16-B padded accumulators of the fast path)       */
 size_t drtk_b200_render_backward_workspace_bytes(int64_t N, int64_t V, int64_t F);
 
@@ -143,7 +143,7 @@ int drtk_b200_edge_grad_backward(const float* v_pix, const int64_t* v_strides, c
  * `v_pix_img_hook` needs to see the [N,3,H,W] image.
  *   bary_img   [N,3,H,W] (strides bary_strides[4])
  *   grad_v_pix [N,V,3] out, dense; zero-filled by the callee, then accumulated
- *   workspace  16-B aligned scratch of at least drtk_b200_edge_grad_backward_fused_workspace_bytes(N,F)
+ *   workspace  scratch of at least drtk_b200_edge_grad_backward_fused_workspace_bytes(N,F)
  *              bytes (per-triangle screen-space vertex table of the fast path)                        */
 size_t drtk_b200_edge_grad_backward_fused_workspace_bytes(int64_t N, int64_t F);
 
