@@ -307,7 +307,9 @@ def test_interpolate_golden(name):
     assert_close(npy(bary.grad), g["grad_bary"], what="bary_img_grad")
 
 
-@pytest.mark.parametrize("C", [1, 2, 3, 5, 8, 16, 19])
+# C % 4 == 0 -> quad-walker kernel (4/12: partly idle walker lanes; 20/32/36: several channel passes per tile);
+# other C -> lane-per-channel tile kernel
+@pytest.mark.parametrize("C", [1, 2, 3, 4, 5, 8, 12, 16, 19, 20, 32, 36])
 @pytest.mark.parametrize("H,W", [(96, 128), (70, 260), (61, 97)])  # tiled path (two sizes) / generic path
 def test_interpolate_vs_oracle_channels(C, H, W):
     v, vi = scenes.grid_mesh(17, 13, H, W, 2, seed=31, overdraw=True)
@@ -335,6 +337,35 @@ def test_interpolate_vs_oracle_channels(C, H, W):
     out3 = drtk_b200.interpolate(cu(attr), cu(vi), cu(index), b3)
     (out3 * cu(w)).sum().backward()
     assert_close(npy(b3.grad), gb64, what=f"bary grad only C={C}")
+
+
+def test_interpolate_backward_batched_topology_and_strides():
+    """Per-image topology (vi [N,F,3] with different faces per image -> per-image triangle table) and a
+    channel-sliced (non-contiguous) attribute table / upstream gradient through the tiled backward."""
+    H, W, C, N = 64, 96, 8, 3
+    v, vi = scenes.grid_mesh(11, 9, H, W, N, seed=77, overdraw=True)
+    g = th.Generator().manual_seed(5)
+    vib = th.stack([vi[th.randperm(vi.shape[0], generator=g)] for _ in range(N)])  # different face order per image
+    _, index = O.rasterize(v.numpy(), vib.numpy(), H, W, mode=1)
+    _, bary = O.render_fwd(v.numpy(), vib.numpy(), index)
+    attr = scenes.vertex_attributes(N, v.shape[1], C, seed=3)
+    w = th.rand((N, C, H, W), generator=g)
+    ga64, gb64 = O.interpolate_bwd(w.double().numpy(), attr.double().numpy(), vib.numpy(), index, bary.astype(np.float64))
+    a = cu(attr).requires_grad_(True)
+    b = cu(bary).requires_grad_(True)
+    out = drtk_b200.interpolate(a, cu(vib), cu(index), b)
+    (out * cu(w)).sum().backward()
+    assert_close(npy(a.grad), ga64, rtol=2e-5, what="attr grad (batched vi)")
+    assert_close(npy(b.grad), gb64, what="bary grad (batched vi)")
+    # attribute table that is a channel slice of a wider tensor (row stride 2C): falls off the 128-bit row path
+    wide = th.zeros((N, v.shape[1], 2 * C), device=DEV)
+    wide[..., :C] = cu(attr)
+    a2 = wide[..., :C].detach().requires_grad_(True)
+    b2 = cu(bary).requires_grad_(True)
+    out2 = drtk_b200.interpolate(a2, cu(vib), cu(index), b2)
+    (out2 * cu(w)).sum().backward()
+    assert_close(npy(a2.grad), ga64, rtol=2e-5, what="attr grad (strided attributes)")
+    assert_close(npy(b2.grad), gb64, what="bary grad (strided attributes)")
 
 
 def test_interpolate_background_sweep_and_layouts():
