@@ -189,6 +189,101 @@ def interpolate_backward(grad_out, attr, vi, index_img, bary_img, need_attr_grad
 
 
 # ------------------------------------------------------------------------------------------
+def _check_matrix_inputs(who, vi, index_img, bary_img):
+    """Checks of interpolation_matrix_cuda / interpolation_normal_matrix_forward_with_pairs
+    (src/interpolate/interpolate_kernel.cu:703-727, src/interpolate/interpolate_module.cpp:266-299)."""
+    _chk(vi.device == index_img.device and vi.device == bary_img.device, f"{who}(): expected all inputs to be on same device")
+    _chk(bary_img.is_cuda, f"{who}(): drtk_b200 has no CPU path; expected all inputs to be on a cuda device")
+    _chk(vi.dtype == torch.int32, f"{who}(): expected vi to have int32 type, but vi has {vi.dtype}")
+    _chk(index_img.dtype == torch.int32, f"{who}(): expected index_img to have int32 type, but index_img has {index_img.dtype}")
+    _chk(bary_img.is_floating_point(), f"{who}(): expected bary_img to have floating point type, but has {bary_img.dtype}")
+    _chk(vi.dim() == 3 and index_img.dim() == 3 and bary_img.dim() == 4,
+         f"{who}(): expected vi.ndim == 3, index_img.ndim == 3, bary_img.ndim == 4")
+    _chk(vi.size(0) == index_img.size(0) and vi.size(0) == bary_img.size(0) and vi.size(2) == 3 and bary_img.size(1) == 3
+         and index_img.size(1) == bary_img.size(2) and index_img.size(2) == bary_img.size(3),
+         f"{who}(): expected vi, index_img and bary_img shapes to agree")
+
+
+def interpolation_matrix_forward(vi, index_img, bary_img):
+    """-> (crow_indices i64 [R+1], col_indices i64 [3R], values f32 [3R], row_pixels i64 [R])
+    (src/interpolate/interpolate_kernel.cu:699-762)."""
+    _check_matrix_inputs("interpolation_matrix", vi, index_img, bary_img)
+    bary_img = _f32(bary_img, "interpolation_matrix", "bary_img")
+    lib = _lib.load()
+    N, F = vi.size(0), vi.size(1)
+    H, W = index_img.size(1), index_img.size(2)
+    with torch.cuda.device(bary_img.device):
+        vi_c, idx_c, bary_c = vi.contiguous(), index_img.contiguous(), bary_img.contiguous()
+        # the list of foreground pixels sizes the outputs: a device -> host sync, as in the reference (at::nonzero, :735)
+        row_pixels = torch.nonzero(idx_c.reshape(-1).ne(-1)).reshape(-1)
+        R = row_pixels.numel()
+        crow = torch.arange(0, R * 3 + 1, 3, dtype=torch.int64, device=bary_img.device)
+        col = torch.empty((R * 3,), dtype=torch.int64, device=bary_img.device)
+        values = torch.empty((R * 3,), dtype=torch.float32, device=bary_img.device)
+        rc = lib.drtk_b200_interpolation_matrix(_lib.ptr(vi_c), _lib.ptr(idx_c), _lib.ptr(bary_c), _lib.ptr(row_pixels),
+                                                N, F, H, W, R, _lib.ptr(col), _lib.ptr(values), _stream(bary_img.device))
+    _lib.check(rc, "interpolation_matrix()")
+    return crow, col, values, row_pixels
+
+
+def interpolation_matrix_backward(grad_values, vi, index_img, row_pixels):
+    """-> bary_grad f32 [N,3,H,W] (src/interpolate/interpolate_kernel.cu:764-803)."""
+    lib = _lib.load()
+    N, F = vi.size(0), vi.size(1)
+    H, W = index_img.size(1), index_img.size(2)
+    with torch.cuda.device(index_img.device):
+        gv = _f32(grad_values, "interpolation_matrix", "grad_values").contiguous()
+        vi_c, idx_c, rp = vi.contiguous(), index_img.contiguous(), row_pixels.contiguous()
+        bary_grad = torch.empty((N, 3, H, W), dtype=torch.float32, device=index_img.device)
+        rc = lib.drtk_b200_interpolation_matrix_backward(_lib.ptr(gv), _lib.ptr(vi_c), _lib.ptr(idx_c), _lib.ptr(rp), N, F, H, W,
+                                                         rp.numel(), _lib.ptr(bary_grad), _stream(index_img.device))
+    _lib.check(rc, "interpolation_matrix() backward")
+    return bary_grad
+
+
+def interpolation_normal_matrix_values(pair_indices, index_img, bary_img, nnz):
+    """-> values f32 [nnz] (src/interpolate/interpolate_kernel.cu:805-860)."""
+    who = "interpolation_normal_matrix_values"
+    _chk(pair_indices.device == index_img.device and pair_indices.device == bary_img.device and bary_img.is_cuda,
+         f"{who}(): expected all inputs to be on same cuda device")
+    _chk(pair_indices.dtype == torch.int32, f"{who}(): expected pair_indices to have int32 type")
+    _chk(index_img.dtype == torch.int32, f"{who}(): expected index_img to have int32 type")
+    _chk(bary_img.is_floating_point(), f"{who}(): expected bary_img to have floating point type")
+    _chk(pair_indices.dim() == 3 and pair_indices.size(2) == 9 and index_img.dim() == 3 and bary_img.dim() == 4 and bary_img.size(1) == 3,
+         f"{who}(): expected pair_indices [N,F,9], index_img [N,H,W], bary_img [N,3,H,W]")
+    _chk(pair_indices.size(0) == index_img.size(0) and pair_indices.size(0) == bary_img.size(0)
+         and index_img.size(1) == bary_img.size(2) and index_img.size(2) == bary_img.size(3),
+         f"{who}(): expected pair_indices, index_img and bary_img shapes to agree")
+    bary_img = _f32(bary_img, who, "bary_img")
+    lib = _lib.load()
+    N, F = pair_indices.size(0), pair_indices.size(1)
+    H, W = index_img.size(1), index_img.size(2)
+    with torch.cuda.device(bary_img.device):
+        pc, idx_c, bary_c = pair_indices.contiguous(), index_img.contiguous(), bary_img.contiguous()
+        values = torch.empty((int(nnz),), dtype=torch.float32, device=bary_img.device)
+        rc = lib.drtk_b200_interpolation_normal_matrix_values(_lib.ptr(pc), _lib.ptr(idx_c), _lib.ptr(bary_c), N, F, H, W,
+                                                              int(nnz), _lib.ptr(values), _stream(bary_img.device))
+    _lib.check(rc, who + "()")
+    return values
+
+
+def interpolation_normal_matrix_values_backward(grad_values, pair_indices, index_img, bary_img):
+    """-> bary_grad f32 [N,3,H,W] (src/interpolate/interpolate_kernel.cu:862-900)."""
+    lib = _lib.load()
+    N, F = pair_indices.size(0), pair_indices.size(1)
+    H, W = index_img.size(1), index_img.size(2)
+    with torch.cuda.device(bary_img.device):
+        gv = _f32(grad_values, "interpolation_normal_matrix_values", "grad_values").contiguous()
+        pc, idx_c = pair_indices.contiguous(), index_img.contiguous()
+        bary_c = _f32(bary_img, "interpolation_normal_matrix_values", "bary_img").contiguous()
+        bary_grad = torch.empty((N, 3, H, W), dtype=torch.float32, device=bary_img.device)
+        rc = lib.drtk_b200_interpolation_normal_matrix_values_backward(_lib.ptr(gv), _lib.ptr(pc), _lib.ptr(idx_c), _lib.ptr(bary_c),
+                                                                       N, F, H, W, _lib.ptr(bary_grad), _stream(bary_img.device))
+    _lib.check(rc, "interpolation_normal_matrix_values() backward")
+    return bary_grad
+
+
+# ------------------------------------------------------------------------------------------
 def check_edge_grad(v_pix, v_pix_img, vi, img, index_img):
     """Argument checks of edge_grad_estimator_fwd (src/edge_grad/edge_grad_module.cpp:30-112)."""
     who = "edge_grad_estimator()"

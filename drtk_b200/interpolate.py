@@ -45,3 +45,143 @@ def interpolate(vert_attributes: th.Tensor, vi: th.Tensor, index_img: th.Tensor,
     if vi.ndim == 2:
         vi = vi[None].expand(vert_attributes.shape[0], -1, -1)
     return _InterpolateFn.apply(vert_attributes, vi, index_img, bary_img)
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse interpolation matrices (API mirror of the reference `drtk/interpolate.py:53-192`)
+# ------------------------------------------------------------------------------------------------
+class _InterpolationMatrixFn(th.autograd.Function):
+    """InterpolationMatrixFunction (`src/interpolate/interpolate_module.cpp:435-475`): the CSR indices and the row ->
+    pixel map are discrete (non-differentiable); the values are the barycentrics, so their gradient flows to bary_img."""
+
+    @staticmethod
+    def forward(ctx, vi, index_img, bary_img):
+        crow, col, values, row_pixels = _ops.interpolation_matrix_forward(vi, index_img, bary_img)
+        ctx.save_for_backward(vi, index_img, row_pixels)
+        ctx.bary_dtype = bary_img.dtype
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(crow, col, row_pixels)
+        return crow, col, values.to(bary_img.dtype), row_pixels
+
+    @staticmethod
+    def backward(ctx, g_crow, g_col, g_values, g_rows):
+        if g_values is None or not ctx.needs_input_grad[2]:
+            return None, None, None
+        vi, index_img, row_pixels = ctx.saved_tensors
+        return None, None, _ops.interpolation_matrix_backward(g_values, vi, index_img, row_pixels).to(ctx.bary_dtype)
+
+
+class _NormalMatrixValuesFn(th.autograd.Function):
+    """Values of A^T A and their product-rule gradient w.r.t. bary_img
+    (`src/interpolate/interpolate_module.cpp:486-560`, kernels `src/interpolate/interpolate_kernel.cu:378-452`)."""
+
+    @staticmethod
+    def forward(ctx, pair_indices, index_img, bary_img, nnz):
+        values = _ops.interpolation_normal_matrix_values(pair_indices, index_img, bary_img, nnz)
+        ctx.save_for_backward(pair_indices, index_img, bary_img)
+        ctx.set_materialize_grads(False)
+        return values.to(bary_img.dtype)
+
+    @staticmethod
+    def backward(ctx, g_values):
+        if g_values is None or not ctx.needs_input_grad[2]:
+            return None, None, None, None
+        pair_indices, index_img, bary_img = ctx.saved_tensors
+        gb = _ops.interpolation_normal_matrix_values_backward(g_values, pair_indices, index_img, bary_img.detach())
+        return None, None, gb.to(bary_img.dtype), None
+
+
+def _broadcast_vi(vi, n):
+    if vi.ndim == 2:
+        return vi[None].expand(n, -1, -1)
+    if vi.ndim == 3 and vi.shape[0] == 1 and n != 1:
+        return vi.expand(n, -1, -1)
+    return vi
+
+
+@th.compiler.disable
+def interpolation_matrix(vi: th.Tensor, index_img: th.Tensor, bary_img: th.Tensor, num_vertices: int) -> th.Tensor:
+    """Sparse CSR matrix A [num_valid_pixels, num_vertices] with `pixel_values = A @ X` for per-vertex attributes X:
+    one row per foreground pixel (flattened [N,H,W] order, background skipped), three entries per row = the pixel's
+    barycentrics at the triangle's vertex columns, columns ascending within a row.  Gradients flow to bary_img
+    through the values.  (Reference `drtk/interpolate.py:53-126`.)"""
+    vi = _broadcast_vi(vi, index_img.shape[0])
+    crow, col, values, row_pixels = _InterpolationMatrixFn.apply(vi, index_img, bary_img)
+    return th.sparse_csr_tensor(crow, col, values, size=(int(row_pixels.numel()), int(num_vertices)),
+                                device=values.device, dtype=values.dtype, check_invariants=False)
+
+
+# topology cache of interpolation_normal_matrix: CSR structure + per-face pair lookup, keyed like the reference's
+# NormalMatrixCacheKey (`src/interpolate/interpolate_module.cpp:36-118`): identity + version of the vi tensor, so
+# that iterative solvers that keep the same topology tensor never rebuild (or synchronise) again.
+import collections
+import threading
+
+_NM_CACHE_MAX = 128
+_nm_cache = collections.OrderedDict()
+_nm_lock = threading.Lock()
+
+
+def _nm_key(vi, num_vertices, device):
+    return (str(device), str(vi.device), vi.untyped_storage().data_ptr(), vi.data_ptr(), tuple(vi.shape), tuple(vi.stride()),
+            vi.storage_offset(), str(vi.dtype), int(num_vertices), vi._version)
+
+
+def _build_normal_matrix_structure(vi, num_vertices, device):
+    """crow_indices [V+1] i64, col_indices [nnz] i64, pair_indices [N,F,9] i32
+    (`src/interpolate/interpolate_module.cpp:120-222`: keys row*V+col of the nine directed vertex pairs of every
+    face, sorted unique keys -> CSR, lower_bound of every key -> pair slot).  Built with torch ops on the CPU like
+    the reference (a cache miss copies vi to the host)."""
+    if num_vertices < 0:
+        raise RuntimeError("interpolation_normal_matrix(): expected num_vertices to be non-negative")
+    if num_vertices > 2 ** 31 - 1:
+        raise RuntimeError("interpolation_normal_matrix(): expected num_vertices to fit in int32")
+    vi_cpu = vi.detach().to("cpu", th.int32).contiguous().to(th.int64)
+    N, F = vi_cpu.shape[0], vi_cpu.shape[1]
+    if N * F > 0 and num_vertices <= 0:
+        raise RuntimeError("interpolation_normal_matrix(): expected num_vertices to be positive when faces are present")
+    if N * F > 0 and (int(vi_cpu.min()) < 0 or int(vi_cpu.max()) >= num_vertices):
+        raise RuntimeError("interpolation_normal_matrix(): vi contains a vertex index outside [0, num_vertices)")
+    keys = (vi_cpu[:, :, :, None] * num_vertices + vi_cpu[:, :, None, :]).reshape(-1)  # [N*F*9], (i, j) -> i*3+j
+    unique_keys, inverse = th.unique(keys, sorted=True, return_inverse=True)
+    if unique_keys.numel() > 2 ** 31 - 1:
+        raise RuntimeError("interpolation_normal_matrix(): normal matrix has too many nonzeros for int32 value indices")
+    rows = th.div(unique_keys, max(num_vertices, 1), rounding_mode="floor")
+    col = unique_keys - rows * num_vertices
+    crow = th.zeros(num_vertices + 1, dtype=th.int64)
+    if unique_keys.numel():
+        crow[1:] = th.cumsum(th.bincount(rows, minlength=num_vertices), 0)
+    pair = inverse.to(th.int32).reshape(N, F, 9)
+    return crow.to(device), col.to(device), pair.to(device)
+
+
+def _normal_matrix_structure(vi, num_vertices, device):
+    key = _nm_key(vi, num_vertices, device)
+    with _nm_lock:
+        hit = _nm_cache.get(key)
+        if hit is not None:
+            _nm_cache.move_to_end(key)
+            return hit[1]
+    structure = _build_normal_matrix_structure(vi, num_vertices, device)  # outside the lock, like the reference
+    with _nm_lock:
+        hit = _nm_cache.get(key)
+        if hit is not None:
+            return hit[1]
+        while len(_nm_cache) >= _NM_CACHE_MAX:
+            _nm_cache.popitem(last=False)
+        _nm_cache[key] = (vi, structure)  # keeps vi alive so its pointers cannot be recycled into a stale hit
+    return structure
+
+
+@th.compiler.disable
+def interpolation_normal_matrix(vi: th.Tensor, index_img: th.Tensor, bary_img: th.Tensor, num_vertices: int) -> th.Tensor:
+    """Sparse CSR normal matrix A^T A [num_vertices, num_vertices] of :func:`interpolation_matrix`, assembled
+    directly: every foreground pixel adds the nine products bary_i * bary_j at the entries (vi[i], vi[j]) of its
+    triangle.  The sparsity pattern depends on the topology only and is cached per vi tensor (identity + version).
+    Differentiable w.r.t. bary_img.  (Reference `drtk/interpolate.py:129-192`.)"""
+    vi = _broadcast_vi(vi, index_img.shape[0])
+    _ops._check_matrix_inputs("interpolation_normal_matrix", vi, index_img, bary_img)
+    crow, col, pair = _normal_matrix_structure(vi, int(num_vertices), bary_img.device)
+    values = _NormalMatrixValuesFn.apply(pair, index_img, bary_img, int(col.numel()))
+    return th.sparse_csr_tensor(crow, col, values, size=(int(num_vertices), int(num_vertices)),
+                                device=values.device, dtype=values.dtype, check_invariants=False)

@@ -121,6 +121,40 @@ int drtk_b200_interpolate_backward(const float* grad_out, const int64_t* grad_ou
                                    void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Sparse interpolation matrices of a fixed rasterisation (dense, contiguous inputs, like the reference
+ * launchers which call .contiguous()):
+ *   interpolation_matrix -- replaces the kernel launch of interpolation_matrix_cuda
+ *     (src/interpolate/interpolate_kernel.cu:699-762; op `interpolate_ext::interpolation_matrix`,
+ *     src/interpolate/interpolate_module.cpp:635-636).  row_pixels [nrows] i64 = flattened indices of the
+ *     foreground pixels (the host computes them, as the reference does with at::nonzero); outputs
+ *     col_indices [3*nrows] i64 (ascending per row) and values [3*nrows] f32.
+ *   ..._backward -- replaces interpolation_matrix_cuda_backward (:764-803): bary_grad [N,3,H,W], zero-filled by
+ *     the callee, receives grad_values at the foreground pixels.
+ *   interpolation_normal_matrix_values -- replaces interpolation_normal_matrix_values_cuda (:805-860; op
+ *     `interpolate_ext::interpolation_normal_matrix_values`): values [nnz] (zero-filled by the callee) +=
+ *     b_i*b_j at slot pair_indices[n, tri, i*3+j] for every foreground pixel; pair_indices [N,F,9] i32.
+ *   ..._backward -- replaces interpolation_normal_matrix_values_cuda_backward (:862-900): bary_grad [N,3,H,W],
+ *     every pixel written.
+ * ------------------------------------------------------------------------------------- */
+int drtk_b200_interpolation_matrix(const int32_t* vi, const int32_t* index_img, const float* bary_img,
+                                   const int64_t* row_pixels, int64_t N, int64_t F, int64_t H, int64_t W,
+                                   int64_t nrows, int64_t* col_indices, float* values, void* stream);
+
+int drtk_b200_interpolation_matrix_backward(const float* grad_values, const int32_t* vi,
+                                            const int32_t* index_img, const int64_t* row_pixels, int64_t N,
+                                            int64_t F, int64_t H, int64_t W, int64_t nrows, float* bary_grad,
+                                            void* stream);
+
+int drtk_b200_interpolation_normal_matrix_values(const int32_t* pair_indices, const int32_t* index_img,
+                                                 const float* bary_img, int64_t N, int64_t F, int64_t H,
+                                                 int64_t W, int64_t nnz, float* values, void* stream);
+
+int drtk_b200_interpolation_normal_matrix_values_backward(const float* grad_values, const int32_t* pair_indices,
+                                                          const int32_t* index_img, const float* bary_img,
+                                                          int64_t N, int64_t F, int64_t H, int64_t W,
+                                                          float* bary_grad, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * edge_grad backward -- replaces edge_grad_estimator_cuda_backward
  * (src/edge_grad/edge_grad_kernel.cu:475-506), the backward of op
  * `edge_grad_ext::edge_grad_estimator(...)` (src/edge_grad/edge_grad_module.cpp:205-208;

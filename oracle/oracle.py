@@ -161,3 +161,61 @@ def edge_grad_bwd(v_pix, img, index_img, vi, grad_output, max_dp_dr=1e4):
     fn(_p(v_pix), _p(img), _p(index_img), _p(vi), _p(grad_output), I64(N), I64(V), I64(F), I64(C),
        I64(H), I64(W), ctypes.c_int(vb), real(max_dp_dr), _p(out))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse interpolation matrices (numpy restatement; small cases only)
+#   interpolation_matrix         src/interpolate/interpolate_kernel.cu:301-338 (+ launcher :699-762)
+#   interpolation_normal_matrix  structure: src/interpolate/interpolate_module.cpp:120-222,
+#                                values: src/interpolate/interpolate_kernel.cu:378-416
+# ------------------------------------------------------------------------------------------------
+def interpolation_matrix(vi, index_img, bary_img, num_vertices):
+    """-> dict(crow, col, values, row_pixels, dense): CSR of A [R, V] and its dense form (float64)."""
+    index_img = np.asarray(index_img, np.int32)
+    N, H, W = index_img.shape
+    vi = np.asarray(vi, np.int32)
+    if vi.ndim == 2:
+        vi = np.broadcast_to(vi[None], (N,) + vi.shape)
+    flat = index_img.reshape(-1)
+    row_pixels = np.flatnonzero(flat != -1).astype(np.int64)          # :733-735
+    R = row_pixels.size
+    n = row_pixels // (H * W)
+    hw = row_pixels % (H * W)
+    cols3 = vi[n, flat[row_pixels]].astype(np.int64)                  # [R,3] corner order
+    b3 = np.asarray(bary_img).reshape(N, 3, H * W)[n, :, hw]          # [R,3]
+    order = np.argsort(cols3, axis=1, kind="stable")                  # ascending columns (:17-36)
+    col = np.take_along_axis(cols3, order, 1).reshape(-1)
+    values = np.take_along_axis(b3, order, 1).reshape(-1)
+    crow = np.arange(0, 3 * R + 1, 3, dtype=np.int64)
+    dense = np.zeros((R, num_vertices), np.float64)
+    np.add.at(dense, (np.repeat(np.arange(R), 3), col), values.astype(np.float64))
+    return dict(crow=crow, col=col, values=values, row_pixels=row_pixels, dense=dense, order=order)
+
+
+def interpolation_normal_matrix(vi, index_img, bary_img, num_vertices):
+    """-> dict(crow, col, values, pair, dense): CSR of A^T A on the topology's sparsity pattern (values float64)."""
+    index_img = np.asarray(index_img, np.int32)
+    N, H, W = index_img.shape
+    vi = np.asarray(vi, np.int32)
+    if vi.ndim == 2:
+        vi = np.broadcast_to(vi[None], (N,) + vi.shape)
+    v64 = vi.astype(np.int64)
+    keys = (v64[:, :, :, None] * num_vertices + v64[:, :, None, :]).reshape(-1)   # module.cpp:166-170
+    unique_keys, inverse = np.unique(keys, return_inverse=True)                   # :177-179, :213-217
+    rows = unique_keys // max(num_vertices, 1)
+    col = unique_keys - rows * num_vertices
+    crow = np.zeros(num_vertices + 1, np.int64)
+    crow[1:] = np.cumsum(np.bincount(rows, minlength=num_vertices))
+    pair = inverse.reshape(N, -1, 9).astype(np.int32)
+    values = np.zeros(unique_keys.size, np.float64)
+    b = np.asarray(bary_img, np.float64)
+    for n in range(N):                                                            # kernel.cu:392-414
+        ys, xs = np.nonzero(index_img[n] != -1)
+        tri = index_img[n, ys, xs]
+        bb = b[n][:, ys, xs]                                                      # [3, P]
+        for i in range(3):
+            for j in range(3):
+                np.add.at(values, pair[n, tri, i * 3 + j], bb[i] * bb[j])
+    dense = np.zeros((num_vertices, num_vertices), np.float64)
+    dense[rows, col] = values
+    return dict(crow=crow, col=col, values=values, pair=pair, dense=dense)

@@ -387,6 +387,92 @@ def test_interpolate_background_sweep_and_layouts():
 
 
 # ------------------------------------------------------------------------------------------------
+# sparse interpolation matrices (src/interpolate/interpolate_kernel.cu:301-452, interpolate_module.cpp:28-308)
+# ------------------------------------------------------------------------------------------------
+def _mat_files():
+    import glob
+    return sorted(glob.glob(os.path.join(GOLDEN, "mat_*.npz")))
+
+
+def test_interpolation_matrix_golden():
+    files = _mat_files()
+    assert len(files) >= 2
+    for fn in files:
+        z = np.load(fn)
+        V = int(z["V"])
+        b = cu(z["bary_img"]).requires_grad_(True)
+        A = drtk_b200.interpolation_matrix(cu(z["vi"]), cu(z["index_img"]), b, V)
+        assert A.layout == th.sparse_csr and tuple(A.shape) == (z["row_pixels"].size, V)
+        assert (npy(A.crow_indices()) == z["crow"]).all() and (npy(A.col_indices()) == z["col"]).all()
+        assert (npy(A.values()) == z["values"]).all()
+        (A.values() * cu(z["w_values"])).sum().backward()
+        assert (npy(b.grad) == z["grad_bary"]).all()
+        # pixel_values = A @ X reproduces interpolate() at the foreground pixels
+        N, H, W = z["index_img"].shape
+        X = th.rand((V, 5), generator=th.Generator().manual_seed(1))
+        px = (A.detach() @ cu(X))
+        img = drtk_b200.interpolate(cu(X)[None].expand(N, -1, -1).contiguous(), cu(z["vi"]), cu(z["index_img"]), cu(z["bary_img"]))
+        ref = img.permute(0, 2, 3, 1).reshape(-1, 5)[cu(z["row_pixels"])]
+        assert_close(npy(px), npy(ref), what="A @ X vs interpolate")
+
+
+def test_interpolation_normal_matrix_golden_and_cache():
+    for fn in _mat_files():
+        z = np.load(fn)
+        V = int(z["V"])
+        vi = cu(z["vi"])
+        b = cu(z["bary_img"]).requires_grad_(True)
+        M = drtk_b200.interpolation_normal_matrix(vi, cu(z["index_img"]), b, V)
+        assert M.layout == th.sparse_csr and tuple(M.shape) == (V, V)
+        assert (npy(M.crow_indices()) == z["n_crow"]).all() and (npy(M.col_indices()) == z["n_col"]).all()
+        assert_close(npy(M.values()), z["n_values"], rtol=2e-5, what="normal matrix values")
+        (M.values() * cu(z["n_w_values"])).sum().backward()
+        assert_close(npy(b.grad), z["n_grad_bary"], rtol=2e-5, what="normal matrix bary grad")
+        # the topology structure is cached per vi tensor (identity + version): second call reuses the same buffers
+        M2 = drtk_b200.interpolation_normal_matrix(vi, cu(z["index_img"]), cu(z["bary_img"]), V)
+        assert M2.crow_indices().data_ptr() == M.crow_indices().data_ptr()
+        vi.add_(0)  # in-place edit bumps the version counter -> rebuild
+        M3 = drtk_b200.interpolation_normal_matrix(vi, cu(z["index_img"]), cu(z["bary_img"]), V)
+        assert M3.crow_indices().data_ptr() != M.crow_indices().data_ptr()
+        assert (npy(M3.col_indices()) == z["n_col"]).all()
+    with pytest.raises(RuntimeError, match="outside"):
+        drtk_b200.interpolation_normal_matrix(cu(np.array([[0, 1, 9]], np.int32)), cu(np.full((1, 4, 4), -1, np.int32)),
+                                              th.zeros((1, 3, 4, 4), device=DEV), 4)
+
+
+@needs_ref
+@pytest.mark.parametrize("scene", SMALL[:3], ids=SMALL_IDS[:3])
+def test_interpolation_matrices_vs_reference_cuda(scene):
+    R.load()
+    _, v, vi, H, W = scene
+    N, V = v.shape[0], v.shape[1]
+    vin = cu(vi)[None].expand(N, -1, -1).contiguous()
+    index = drtk_b200.rasterize(cu(v), vin, H, W)
+    _, bary = drtk_b200.render(cu(v), vin, index)
+    g = th.Generator(device=DEV).manual_seed(3)
+    # A
+    b0, b1 = bary.clone().requires_grad_(True), bary.clone().requires_grad_(True)
+    A = drtk_b200.interpolation_matrix(vin, index, b0, V)
+    crow, col, val, rows = th.ops.interpolate_ext.interpolation_matrix(vin, index, b1)
+    assert bool((A.crow_indices() == crow).all()) and bool((A.col_indices() == col).all()) and bool((A.values() == val).all())
+    w = th.rand(val.shape, device=DEV, generator=g)
+    (A.values() * w).sum().backward(); (val * w).sum().backward()
+    assert bool((b0.grad == b1.grad).all())
+    # A^T A
+    b2, b3 = bary.clone().requires_grad_(True), bary.clone().requires_grad_(True)
+    M = drtk_b200.interpolation_normal_matrix(vin, index, b2, V)
+    ncrow, ncol, nval = th.ops.interpolate_ext.interpolation_normal_matrix(vin, index, b3, V)
+    assert bool((M.crow_indices() == ncrow).all()) and bool((M.col_indices() == ncol).all())
+    assert_close(npy(M.values()), npy(nval), rtol=2e-5, what="normal matrix values vs reference CUDA")
+    w2 = th.rand(nval.shape, device=DEV, generator=g)
+    (M.values() * w2).sum().backward(); (nval * w2).sum().backward()
+    assert_close(npy(b2.grad), npy(b3.grad), rtol=2e-5, what="normal matrix bary grad vs reference CUDA")
+    # against the dense oracle
+    o = O.interpolation_normal_matrix(npy(vin), npy(index), npy(bary), V)
+    assert_close(npy(M.to_dense()), o["dense"], rtol=2e-5, what="A^T A dense")
+
+
+# ------------------------------------------------------------------------------------------------
 # edge_grad_estimator
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", CASES)

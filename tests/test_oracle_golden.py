@@ -164,3 +164,49 @@ def test_wireframe_oracle_edge_flags():
         assert int((d > 0).sum()) > 100  # the interior occludes whatever the flags say
     assert counts[0] == 0 and counts[7] > counts[1] > 0 and counts[7] > counts[2] > 0 and counts[7] > counts[4] > 0
     assert counts[7] <= counts[1] + counts[2] + counts[4]  # shared corner pixels are counted once
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse interpolation matrices: numpy oracle vs the reference's CPU implementation (tests/golden/mat_*.npz,
+# written by tests/golden/make_golden_matrix.py from oracle/_ref)
+# ------------------------------------------------------------------------------------------------
+def _mat_files():
+    import glob
+    files = sorted(glob.glob(os.path.join(GOLDEN, "mat_*.npz")))
+    assert len(files) >= 2
+    return files
+
+
+def test_interpolation_matrix_oracle_against_reference_cpu():
+    for fn in _mat_files():
+        z = np.load(fn)
+        o = O.interpolation_matrix(z["vi"], z["index_img"], z["bary_img"], int(z["V"]))
+        np.testing.assert_array_equal(o["row_pixels"], z["row_pixels"])
+        np.testing.assert_array_equal(o["crow"], z["crow"])
+        np.testing.assert_array_equal(o["col"], z["col"])
+        np.testing.assert_array_equal(o["values"], z["values"])  # a pure permutation of the barycentrics
+        assert (np.diff(o["col"].reshape(-1, 3), axis=1) > 0).all()  # ascending within a row
+        # rows of A sum to 1 up to rounding (perspective-corrected barycentrics)
+        np.testing.assert_allclose(o["dense"].sum(1), 1.0, atol=1e-5)
+        # gradient of sum(values * w) w.r.t. bary: w scattered back through the same permutation
+        N, H, W = z["index_img"].shape
+        gb = np.zeros((N, 3, H * W), np.float32)
+        n, hw = o["row_pixels"] // (H * W), o["row_pixels"] % (H * W)
+        wv = z["w_values"].reshape(-1, 3)
+        for k in range(3):
+            gb[n, o["order"][:, k], hw] = wv[:, k]
+        np.testing.assert_array_equal(gb.reshape(N, 3, H, W), z["grad_bary"])
+
+
+def test_interpolation_normal_matrix_oracle_against_reference_cpu():
+    for fn in _mat_files():
+        z = np.load(fn)
+        V = int(z["V"])
+        o = O.interpolation_normal_matrix(z["vi"], z["index_img"], z["bary_img"], V)
+        np.testing.assert_array_equal(o["crow"], z["n_crow"])
+        np.testing.assert_array_equal(o["col"], z["n_col"])
+        np.testing.assert_allclose(o["values"], z["n_values"], rtol=2e-5, atol=2e-5 * np.abs(z["n_values"]).max())
+        # A^T A of the interpolation matrix, and symmetric
+        A = O.interpolation_matrix(z["vi"], z["index_img"], z["bary_img"], V)["dense"]
+        np.testing.assert_allclose(o["dense"], A.T @ A, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(o["dense"], o["dense"].T, rtol=0, atol=1e-12)

@@ -9,9 +9,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def golden_cases():
-    # wire_*.npz are the wireframe fixtures (reference CUDA outputs), handled by their own tests
+    # wire_*.npz (wireframe, reference CUDA outputs) and mat_*.npz (interpolation matrices, reference CPU outputs)
+    # are handled by their own tests
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not os.path.basename(p).startswith("wire_"))
+                  if not os.path.basename(p).startswith(("wire_", "mat_")))
 
 
 def load_golden(name):

@@ -45,6 +45,23 @@ OPS = {
     "render_bwd": lambda: _ops.render_backward(v, vi3, index, None, bary),
     "edge_fused": lambda: _ops.edge_grad_backward_fused(v, img, index, vi3, w, bary, 1e4),
 }
+if any(o.startswith("nm_") or o.startswith("imat") for o in a.ops.split(",")):
+    import importlib
+    I = importlib.import_module("drtk_b200.interpolate")
+    crow, col, pair = I._normal_matrix_structure(vi3, v.shape[1], th.device(dev))
+    nnz = int(col.numel())
+    gvals = th.rand((nnz,), device=dev)
+    OPS["nm_values"] = lambda: _ops.interpolation_normal_matrix_values(pair, index, bary, nnz)
+    OPS["nm_values_bwd"] = lambda: _ops.interpolation_normal_matrix_values_backward(gvals, pair, index, bary)
+    OPS["imat"] = lambda: _ops.interpolation_matrix_forward(vi3, index, bary)[2]
+    try:
+        from oracle import ref as R
+        R.load()
+        vic = vi3.contiguous()
+        OPS["nm_values_ref"] = lambda: th.ops.interpolate_ext.interpolation_normal_matrix_values(pair, index, bary, nnz)
+        OPS["imat_ref"] = lambda: th.ops.interpolate_ext.interpolation_matrix(vic, index, bary)[2]
+    except Exception as ex:  # noqa: BLE001
+        print("reference ops unavailable:", ex)
 variants = [""] + [e for e in a.env.split(",") if e]
 for op in a.ops.split(","):
     base = None
