@@ -18,16 +18,16 @@ import sys
 from . import _lib
 from ._lib import build  # noqa: F401
 from .edge_grad_estimator import edge_grad_estimator  # noqa: F401
-from .interpolate import interpolate, interpolation_matrix, interpolation_normal_matrix  # noqa: F401
+from .interpolate import interpolate, interpolate_ref, interpolation_matrix, interpolation_normal_matrix  # noqa: F401
 from .rasterize import rasterize, rasterize_with_depth  # noqa: F401
-from .render import render  # noqa: F401
+from .render import render, render_ref  # noqa: F401
 from .transform import transform, transform_with_v_cam  # noqa: F401
 
 __version__ = "0.1.0"
 
 __all__ = [
     "rasterize", "rasterize_with_depth", "render", "interpolate", "interpolation_matrix", "interpolation_normal_matrix",
-    "edge_grad_estimator",
+    "edge_grad_estimator", "render_ref", "interpolate_ref",
     "transform", "transform_with_v_cam", "build", "install_as_drtk", "native_library_path",
 ]
 

@@ -185,3 +185,23 @@ def interpolation_normal_matrix(vi: th.Tensor, index_img: th.Tensor, bary_img: t
     values = _NormalMatrixValuesFn.apply(pair, index_img, bary_img, int(col.numel()))
     return th.sparse_csr_tensor(crow, col, values, size=(int(num_vertices), int(num_vertices)),
                                 device=values.device, dtype=values.dtype, check_invariants=False)
+
+
+def interpolate_ref(vert_attributes: th.Tensor, vi: th.Tensor, index_img: th.Tensor, bary_img: th.Tensor) -> th.Tensor:
+    """Pure-PyTorch, float64, differentiable statement of :func:`interpolate` (any device), for tests and debugging
+    -- the counterpart of the reference's `interpolate_ref` (`drtk/interpolate.py:195-261`): same values, same
+    coordinate sweep on empty pixels.  `vi` is [F,3]."""
+    dt = vert_attributes.dtype
+    a, b = vert_attributes.double(), bary_img.double()
+    N, H, W = index_img.shape
+    C = a.shape[-1]
+    tri = index_img.clamp(min=0).long()                       # [N,H,W]
+    corners = vi.long()[tri]                                  # [N,H,W,3]
+    rows = th.gather(a, 1, corners.reshape(N, -1, 1).expand(-1, -1, C)).reshape(N, H, W, 3, C)
+    img = (rows * b.permute(0, 2, 3, 1)[..., None]).sum(3)    # [N,H,W,C]
+    xs = (th.arange(W, device=a.device, dtype=th.float64) * 2 + 1) / W - 1
+    ys = (th.arange(H, device=a.device, dtype=th.float64) * 2 + 1) / H - 1
+    sweep = th.stack((xs[None, :].expand(H, W), ys[:, None].expand(H, W)), -1)        # even channels x, odd y
+    sweep = sweep.repeat(1, 1, (C + 1) // 2)[..., :C]
+    img = th.where((index_img == -1)[..., None], sweep[None].expand(N, -1, -1, -1), img)
+    return img.permute(0, 3, 1, 2).to(dt)

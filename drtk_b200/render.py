@@ -39,3 +39,33 @@ def render(v: th.Tensor, vi: th.Tensor, index_img: th.Tensor) -> Tuple[th.Tensor
     if vi.ndim == 2:
         vi = vi[None].expand(v.shape[0], -1, -1)
     return _RenderFn.apply(v, vi, index_img)
+
+
+def render_ref(v: th.Tensor, vi: th.Tensor, index_img: th.Tensor):
+    """Pure-PyTorch, float64, differentiable statement of :func:`render` (any device), for tests and debugging -- the
+    counterpart of the reference's `render_ref` (`drtk/render.py:66-132`).  `vi` is [F,3].
+    Returns (depth_img [N,H,W], bary_img [N,3,H,W]); zeros where index_img == -1."""
+    dt = v.dtype
+    v64 = v.double()
+    N, H, W = index_img.shape
+    mask = index_img != -1
+    tri = index_img.clamp(min=0).long()
+    corners = vi.long()[tri]                                                          # [N,H,W,3]
+    p = th.gather(v64, 1, corners.reshape(N, -1, 1).expand(-1, -1, 3)).reshape(N, H, W, 3, 3)   # [.., corner, xyz]
+    p0, p1, p2 = p[..., 0, :], p[..., 1, :], p[..., 2, :]
+
+    def epsclamp(x):
+        return th.where(x < 0, x.clamp(max=-1e-16), x.clamp(min=1e-16))
+
+    ys, xs = th.meshgrid(th.arange(H, device=v.device, dtype=th.float64), th.arange(W, device=v.device, dtype=th.float64),
+                         indexing="ij")
+    e01, e02 = p1 - p0, p2 - p0
+    den = epsclamp(e01[..., 0] * e02[..., 1] - e01[..., 1] * e02[..., 0])
+    qx, qy = xs[None] - p0[..., 0], ys[None] - p0[..., 1]
+    l1 = (qx * e02[..., 1] - qy * e02[..., 0]) / den
+    l2 = (qy * e01[..., 0] - qx * e01[..., 1]) / den
+    l0 = 1.0 - l1 - l2
+    w0, w1, w2 = l0 / epsclamp(p0[..., 2]), l1 / epsclamp(p1[..., 2]), l2 / epsclamp(p2[..., 2])
+    depth = 1.0 / epsclamp(w0 + w1 + w2)
+    bary = th.stack((w0 * depth, w1 * depth, w2 * depth), 1) * mask[:, None]
+    return (depth * mask).to(dt), bary.to(dt)
