@@ -920,13 +920,23 @@ extern "C" int drtk_b200_interpolate_forward(const float* vert_attributes, const
   const bool avec = (C % 4 == 0) && a.as.s2 == 1 && (a.as.s1 % 4 == 0) && (a.as.s0 % 4 == 0) && a.as.s1 > 0 &&
                     (V * a.as.s1 + C < (int64_t)0x7FFFFFF0) && (reinterpret_cast<uintptr_t>(vert_attributes) % 16 == 0);
   if (H * W >= (int64_t)0x7FFFFFF0 || N > 65535) return DRTK_B200_EUNSUPPORTED;
-  const int per_img = (int)((8 + N - 1) / N);
-  const unsigned gx = grid_for(vec ? H * W / 4 : H * W, 256, per_img > 0 ? per_img : 1);
-  const dim3 grid(gx, (unsigned)N);
-  if (vec && avec) interp_fwd_kernel<true, true><<<grid, 256, 0, stream>>>(a, out);
-  else if (vec) interp_fwd_kernel<true, false><<<grid, 256, 0, stream>>>(a, out);
-  else if (avec) interp_fwd_kernel<false, true><<<grid, 256, 0, stream>>>(a, out);
-  else interp_fwd_kernel<false, false><<<grid, 256, 0, stream>>>(a, out);
+  // Grid: one wave of co-resident CTAs (grid-stride loops inside).  The CTAs of all images together must not
+  // exceed what is resident at once -- 148 SMs x occupancy -- or the last, partly filled wave costs up to a
+  // third of the kernel (measured at config 4: 1184 CTAs on 444 slots = 2.67 waves).
+  auto launch = [&](auto kern) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0) != cudaSuccess || occ < 1) occ = 1;
+    const int64_t slots = (int64_t)kNumSMs * occ;
+    const int64_t need = ((vec ? H * W / 4 : H * W) + 255) / 256;
+    int64_t gx = slots / N;
+    if (gx < 1) gx = 1;
+    if (gx > need) gx = need;
+    kern<<<dim3((unsigned)gx, (unsigned)N), 256, 0, stream>>>(a, out);
+  };
+  if (vec && avec) launch(interp_fwd_kernel<true, true>);
+  else if (vec) launch(interp_fwd_kernel<true, false>);
+  else if (avec) launch(interp_fwd_kernel<false, true>);
+  else launch(interp_fwd_kernel<false, false>);
   DRTK_CHECK_LAUNCH();
   return 0;
 }

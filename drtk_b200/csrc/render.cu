@@ -416,11 +416,20 @@ extern "C" int drtk_b200_render_forward(const float* v, const int64_t* v_strides
   a.N = (int)N; a.V = (int)V; a.F = (int)F; a.H = (int)H; a.W = (int)W;
   const bool vec = VecOk::image(index_img, W, a.is.s2, a.is.s1, a.is.s0);
   if (H * W >= (int64_t)0x7FFFFFF0 || N > 65535) return DRTK_B200_EUNSUPPORTED;
-  // grid.y = image; grid.x sized so that the whole grid is ~8 CTAs of 256 threads per SM
+  // grid.y = image; grid.x sized so that all CTAs of all images are co-resident (one wave, grid-stride loops
+  // inside): a partly filled last wave cost 8 % in interp_fwd_kernel
   const int64_t items = vec ? H * W / 4 : H * W;
-  const unsigned gx = grid_for(items, 256, (int)((8 + N - 1) / N > 0 ? (8 + N - 1) / N : 1));
-  if (vec) render_fwd_kernel<true><<<dim3(gx, (unsigned)N), 256, 0, stream>>>(a, depth_img, bary_img);
-  else render_fwd_kernel<false><<<dim3(gx, (unsigned)N), 256, 0, stream>>>(a, depth_img, bary_img);
+  auto launch = [&](auto kern) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0) != cudaSuccess || occ < 1) occ = 1;
+    int64_t gx = (int64_t)kNumSMs * occ / N;
+    const int64_t need = (items + 255) / 256;
+    if (gx < 1) gx = 1;
+    if (gx > need) gx = need;
+    kern<<<dim3((unsigned)gx, (unsigned)N), 256, 0, stream>>>(a, depth_img, bary_img);
+  };
+  if (vec) launch(render_fwd_kernel<true>);
+  else launch(render_fwd_kernel<false>);
   DRTK_CHECK_LAUNCH();
   return 0;
 }
