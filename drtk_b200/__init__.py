@@ -22,13 +22,14 @@ from .interpolate import interpolate, interpolate_ref, interpolation_matrix, int
 from .rasterize import rasterize, rasterize_with_depth  # noqa: F401
 from .render import render, render_ref  # noqa: F401
 from .transform import transform, transform_with_v_cam  # noqa: F401
+from . import utils  # noqa: F401,E402
 
 __version__ = "0.1.0"
 
 __all__ = [
     "rasterize", "rasterize_with_depth", "render", "interpolate", "interpolation_matrix", "interpolation_normal_matrix",
     "edge_grad_estimator", "render_ref", "interpolate_ref",
-    "transform", "transform_with_v_cam", "build", "install_as_drtk", "native_library_path",
+    "transform", "transform_with_v_cam", "utils", "build", "install_as_drtk", "native_library_path",
 ]
 
 
@@ -43,5 +44,5 @@ def install_as_drtk() -> None:
     if "drtk" in sys.modules and sys.modules["drtk"] is not this:
         raise RuntimeError("a different `drtk` package is already imported")
     sys.modules["drtk"] = this
-    for sub in ("rasterize", "render", "interpolate", "edge_grad_estimator", "transform"):
+    for sub in ("rasterize", "render", "interpolate", "edge_grad_estimator", "transform", "utils"):
         sys.modules[f"drtk.{sub}"] = sys.modules[f"{__name__}.{sub}"]

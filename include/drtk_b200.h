@@ -191,6 +191,41 @@ int drtk_b200_edge_grad_backward_fused(const float* v_pix, const int64_t* v_stri
                                        float* grad_v_pix, void* workspace, size_t workspace_bytes,
                                        void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * transform -- the world -> pixel projection in front of the rasteriser.  The reference
+ * has no native op here: `drtk.transform` (drtk/transform.py:14-119) runs `project_points`
+ * (drtk/utils/projection.py:486-646) as ~20 stock torch kernels forward and as many again backward; these two
+ * entry points do each direction in ONE kernel.
+ *   v     [N,V,3] f32, strides v_strides[3]
+ *   cam   [N,28] f32 dense, one block per batch item:
+ *         [0:3] campos  [3:12] camrot row-major  [12:16] focal row-major  [16:18] princpt
+ *         [18:26] distortion coefficients (zero-padded)  [26] fov (max normalised radius)  [27] unused
+ *   mode  DRTK_B200_DIST_*; `modes` (device, [N] i32) overrides it per batch item when not NULL
+ *         PINHOLE            project_pinhole             (projection.py:33-53)
+ *         RADIAL_TANGENTIAL  project_pinhole_distort_rt  (:56-136)  D = k1 k2 p1 p2 [k3 [k4 k5 k6]]
+ *         FISHEYE            project_fisheye_distort     (:139-186) D = k0..k3
+ *         FISHEYE62          project_fisheye_distort_62  (:189-276, without the LUT) D = k0..k5 p0 p1
+ *   cull_outside_fov  fisheye62 only: vertices with |p| > fov get z = -1 (projection.py:624-644)
+ *   v_pix [N,V,3] out = (x_pix, y_pix, z_cam);  v_cam [N,V,3] out or NULL
+ * backward: grad_v_pix / grad_v_cam [N,V,3] (either may be NULL = zeros, any strides);
+ *   grad_v [N,V,3] out or NULL (every element written); grad_cam [N,28] out or NULL (zero-filled by the
+ *   callee, then accumulated; slots 26, 27 stay 0: fov is not differentiated)
+ * ------------------------------------------------------------------------------------- */
+#define DRTK_B200_DIST_PINHOLE 0
+#define DRTK_B200_DIST_RADIAL_TANGENTIAL 1
+#define DRTK_B200_DIST_FISHEYE 2
+#define DRTK_B200_DIST_FISHEYE62 3
+
+int drtk_b200_transform_forward(const float* v, const int64_t* v_strides, const float* cam,
+                                const int32_t* modes, int mode, int cull_outside_fov, int64_t N, int64_t V,
+                                float* v_pix, float* v_cam, void* stream);
+
+int drtk_b200_transform_backward(const float* v, const int64_t* v_strides, const float* cam,
+                                 const int32_t* modes, int mode, int cull_outside_fov,
+                                 const float* grad_v_pix, const int64_t* grad_v_pix_strides,
+                                 const float* grad_v_cam, const int64_t* grad_v_cam_strides, int64_t N,
+                                 int64_t V, float* grad_v, float* grad_cam, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

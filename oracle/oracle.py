@@ -219,3 +219,103 @@ def interpolation_normal_matrix(vi, index_img, bary_img, num_vertices):
     dense = np.zeros((num_vertices, num_vertices), np.float64)
     dense[rows, col] = values
     return dict(crow=crow, col=col, values=values, pair=pair, dense=dense)
+
+
+# ---- transform: numpy restatement of the reference's project_points -----------------
+def _zsafe(z):
+    return np.where(z < 0, np.minimum(z, -1e-8), np.maximum(z, 1e-8))
+
+
+def _distort(p, mode, D, fov):
+    """One batch item.  p [V,2]; D [k]; fov scalar.  Follows drtk/utils/projection.py:
+    radial-tangential :56-136, fisheye :139-186, fisheye62 :189-276 (without the LUT)."""
+    if mode in (None, "pinhole"):
+        return p
+    x, y = p[:, 0], p[:, 1]
+    if mode == "radial-tangential":
+        r2 = np.minimum(x * x + y * y, fov * fov)
+        xc, yc = np.clip(x, -fov, fov), np.clip(y, -fov, fov)
+        R = 1 + D[0] * r2 + D[1] * r2**2
+        if len(D) >= 5:
+            R = R + D[4] * r2**3
+        if len(D) == 8:
+            R = R / (1 + D[5] * r2 + D[6] * r2**2 + D[7] * r2**3)
+        q = p * R[:, None]
+        q = q + 2 * (xc * yc)[:, None] * np.array([D[2], D[3]])
+        q = q + r2[:, None] * np.array([D[3], D[2]])
+        q = q + np.stack((2 * D[3] * xc**2, 2 * D[2] * yc**2), -1)
+        return q
+    r = np.sqrt(x * x + y * y)
+    r = np.minimum(np.maximum(r, 1e-8), fov)
+    th_ = np.arctan(r)
+    nk = 4 if mode == "fisheye" else 6
+    thd = th_ * (1 + sum(D[i] * th_ ** (2 * i + 2) for i in range(nk)))
+    q = p * (thd / np.maximum(r, 1e-8))[:, None]
+    if nk == 6:
+        q = np.clip(q, -fov, fov)
+        xr, yr = q[:, 0], q[:, 1]
+        rr2 = xr * xr + yr * yr
+        q = q + np.stack(((2 * xr * xr + rr2) * D[6] + 2 * xr * yr * D[7],
+                          2 * xr * yr * D[6] + (2 * yr * yr + rr2) * D[7]), -1)
+    return q
+
+
+def transform_fwd(v, campos, camrot, focal, princpt, modes=None, D=None, fov=None, cull=False):
+    """-> (v_pix, v_cam) float64.  `modes`: one string or a list of N strings; `fov` [N] or [N,1] (required for
+    the distorted models: the FOV estimators are host logic, tested separately); `cull`: fisheye62 with a
+    user-given fov marks vertices beyond it with z = -1 (projection.py:624-644)."""
+    v = np.asarray(v, np.float64)
+    N = v.shape[0]
+    if not isinstance(modes, (list, tuple)):
+        modes = [modes] * N
+    v_pix, v_cam = np.empty_like(v), np.empty_like(v)
+    for n in range(N):
+        vc = (v[n] - np.asarray(campos[n], np.float64)) @ np.asarray(camrot[n], np.float64).T  # :536
+        z = vc[:, 2:3]
+        p = vc[:, :2] / _zsafe(z)
+        f = None if fov is None else float(np.asarray(fov, np.float64).reshape(N)[n])
+        q = _distort(p, modes[n], None if D is None else np.asarray(D[n], np.float64), f)
+        pix = q @ np.asarray(focal[n], np.float64).T + np.asarray(princpt[n], np.float64)
+        zc = z
+        if cull and modes[n] in ("fisheye62", "fisheye62_lut"):
+            zc = np.where(np.sqrt((p**2).sum(-1, keepdims=True)) > f, -1.0, z)
+        v_pix[n] = np.concatenate((pix, zc), -1)
+        v_cam[n] = vc
+    return v_pix, v_cam
+
+
+def transform_vjp_fd(w_pix, w_cam, v, campos, camrot, focal, princpt, modes=None, D=None, fov=None, cull=False,
+                     h=1e-6):
+    """Gradients of L = sum(w_pix*v_pix) + sum(w_cam*v_cam) by central differences in float64 (small cases).
+    -> dict with v, campos, camrot, focal, princpt, D."""
+    args = dict(v=np.asarray(v, np.float64), campos=np.asarray(campos, np.float64),
+                camrot=np.asarray(camrot, np.float64), focal=np.asarray(focal, np.float64),
+                princpt=np.asarray(princpt, np.float64))
+    if D is not None:
+        args["D"] = np.asarray(D, np.float64)
+
+    def per_item_loss(a):
+        vp, vc = transform_fwd(a["v"], a["campos"], a["camrot"], a["focal"], a["princpt"], modes, a.get("D"), fov, cull)
+        return (w_pix * vp).sum((1, 2)) + (w_cam * vc).sum((1, 2)), (w_pix * vp), (w_cam * vc)
+
+    out = {}
+    for name, x in args.items():
+        g = np.zeros_like(x)
+        if name == "v":  # each vertex only feeds its own outputs: perturb one coordinate of all vertices at once
+            for k in range(3):
+                lo, hi = dict(args), dict(args)
+                d = np.zeros_like(x); d[..., k] = h
+                hi["v"], lo["v"] = x + d, x - d
+                _, ap, ac = per_item_loss(hi)
+                _, bp, bc = per_item_loss(lo)
+                g[..., k] = ((ap - bp).sum(-1) + (ac - bc).sum(-1)) / (2 * h)
+        else:  # per-item parameters: perturb one entry of every item at once
+            flat = x.reshape(x.shape[0], -1)
+            gf = g.reshape(x.shape[0], -1)
+            for k in range(flat.shape[1]):
+                d = np.zeros_like(flat); d[:, k] = h
+                lo, hi = dict(args), dict(args)
+                hi[name], lo[name] = (flat + d).reshape(x.shape), (flat - d).reshape(x.shape)
+                gf[:, k] = (per_item_loss(hi)[0] - per_item_loss(lo)[0]) / (2 * h)
+        out[name] = g
+    return out

@@ -54,9 +54,10 @@ def test_transform_matches_manual_projection_and_Rt_K_forms():
     assert th.allclose(out, out2, rtol=1e-10, atol=1e-8)
     with pytest.raises(ValueError):
         drtk_b200.transform(v, campos=c, camrot=R, focal=f, princpt=pp, K=K)
-    with pytest.raises(NotImplementedError):
-        drtk_b200.transform(v, campos=c, camrot=R, focal=f, princpt=pp, distortion_mode="fisheye",
-                            distortion_coeff=th.zeros(N, 4))
+    # zero distortion coefficients: the fisheye model reduces to theta/r scaling of the pinhole image plane
+    fe = drtk_b200.transform(v, campos=c, camrot=R, focal=f, princpt=pp, distortion_mode="fisheye",
+                             distortion_coeff=th.zeros(N, 4, dtype=th.float64))
+    assert fe.shape == out.shape and th.allclose(fe[..., 2], out[..., 2])
 
 
 def test_transform_is_differentiable():
