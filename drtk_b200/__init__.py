@@ -18,7 +18,9 @@ import sys
 from . import _lib
 from ._lib import build  # noqa: F401
 from .edge_grad_estimator import edge_grad_estimator  # noqa: F401
+from .grid_scatter import grid_scatter, grid_scatter_ref  # noqa: F401
 from .interpolate import interpolate, interpolate_ref, interpolation_matrix, interpolation_normal_matrix  # noqa: F401
+from .mipmap_grid_sample import mipmap_grid_sample, mipmap_grid_sample_ref  # noqa: F401
 from .rasterize import rasterize, rasterize_with_depth  # noqa: F401
 from .render import render, render_ref  # noqa: F401
 from .transform import transform, transform_with_v_cam  # noqa: F401
@@ -28,7 +30,8 @@ __version__ = "0.1.0"
 
 __all__ = [
     "rasterize", "rasterize_with_depth", "render", "interpolate", "interpolation_matrix", "interpolation_normal_matrix",
-    "edge_grad_estimator", "render_ref", "interpolate_ref",
+    "edge_grad_estimator", "render_ref", "interpolate_ref", "grid_scatter", "grid_scatter_ref", "mipmap_grid_sample",
+    "mipmap_grid_sample_ref",
     "transform", "transform_with_v_cam", "utils", "build", "install_as_drtk", "native_library_path",
 ]
 
@@ -44,5 +47,6 @@ def install_as_drtk() -> None:
     if "drtk" in sys.modules and sys.modules["drtk"] is not this:
         raise RuntimeError("a different `drtk` package is already imported")
     sys.modules["drtk"] = this
-    for sub in ("rasterize", "render", "interpolate", "edge_grad_estimator", "transform", "utils"):
+    for sub in ("rasterize", "render", "interpolate", "edge_grad_estimator", "transform", "utils", "grid_scatter",
+                "mipmap_grid_sample"):
         sys.modules[f"drtk.{sub}"] = sys.modules[f"{__name__}.{sub}"]

@@ -57,6 +57,15 @@ PROTOTYPES = {
     "drtk_b200_interpolation_matrix_backward": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P, _P]),
     "drtk_b200_interpolation_normal_matrix_values": (_INT, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P, _P]),
     "drtk_b200_interpolation_normal_matrix_values_backward": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _P, _P]),
+    "drtk_b200_mipmap_grid_sample_forward": (
+        _INT, [_P, _P, _P, _INT, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _INT, _INT, _INT, _P, _P]),
+    "drtk_b200_mipmap_grid_sample_backward": (
+        _INT, [_P, _P, _P, _P, _P, _INT, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _INT, _INT, _INT,
+               _P, _P, _P]),
+    "drtk_b200_grid_scatter_forward": (
+        _INT, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _P, _P]),
+    "drtk_b200_grid_scatter_backward": (
+        _INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _P, _P, _P]),
     "drtk_b200_transform_forward": (_INT, [_P, _P, _P, _P, _INT, _INT, _I64, _I64, _P, _P, _P]),
     "drtk_b200_transform_backward": (
         _INT, [_P, _P, _P, _P, _INT, _INT, _P, _P, _P, _P, _I64, _I64, _P, _P, _P]),

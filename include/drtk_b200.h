@@ -226,6 +226,60 @@ int drtk_b200_transform_backward(const float* v, const int64_t* v_strides, const
                                  const float* grad_v_cam, const int64_t* grad_v_cam_strides, int64_t N,
                                  int64_t V, float* grad_v, float* grad_cam, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Texture samplers either side of `interpolate`.  Enumerations as in the reference ops:
+ *   padding_mode 0 zeros, 1 border, 2 reflection;  interpolation_mode 0 bilinear, 2 bicubic
+ *   (drtk/mipmap_grid_sample.py:100-113, drtk/grid_scatter.py:79-92); coordinates in [-1, 1] as grid_sample.
+ *
+ * mipmap_grid_sample forward -- replaces mipmap_aniso_grid_sampler_2d_cuda
+ * (src/mipmap_grid_sampler/mipmap_grid_sampler_kernel.cu:900-1097), op
+ * `mipmap_grid_sampler_ext::mipmap_grid_sampler_2d(Tensor[] input, Tensor grid, Tensor vt_dxdy_img, int max_aniso,
+ * int padding_mode, int interpolation_mode, bool align_corners, bool force_max_ansio, bool clip_grad) -> Tensor`
+ * (src/mipmap_grid_sampler/mipmap_grid_sampler_module.cpp:252-256).
+ *   levels        HOST array of num_levels (1..11) device pointers, level l = [N,C,H_l,W_l] f32
+ *   level_hw      HOST [num_levels][2] = (H_l, W_l);  level_strides HOST [num_levels][4] element strides
+ *   grid          [N,H,W,2] f32 (strides grid_strides[4]);  vt_dxdy_img [N,H,W,2,2] f32 (strides vt_strides[5])
+ *   out           [N,C,H,W] f32 dense, every element written
+ * Like the reference kernel (:423) the FORWARD ignores align_corners (always false); the backward honours it.
+ * backward -- replaces mipmap_aniso_grid_sampler_2d_cuda_backward (:1099-1249):
+ *   grad_levels   HOST array of num_levels device pointers to dense [N,C,H_l,W_l] accumulators (zero-filled by
+ *                 the callee), or NULL when no texture needs a gradient
+ *   grad_grid     [N,H,W,2] dense, every element written, or NULL.   vt_dxdy_img receives no gradient.
+ *
+ * grid_scatter forward -- replaces grid_scatter_2d_cuda (src/grid_scatter/grid_scatter_kernel.cu:624-729), op
+ * `grid_scatter_ext::grid_scatter_2d(Tensor input, Tensor grid, int output_height, int output_width,
+ * int padding_mode, int interpolation_mode, bool align_corners) -> Tensor` (src/grid_scatter/grid_scatter_module.cpp:137-140):
+ *   input [N,C,H,W], grid [N,H,W,2] -> out [N,C,out_H,out_W] dense (zero-filled by the callee, then accumulated)
+ * backward -- replaces grid_scatter_2d_cuda_backward (:731-788): grad_input [N,C,H,W] dense or NULL,
+ *   grad_grid [N,H,W,2] dense or NULL; every element written.
+ * ------------------------------------------------------------------------------------- */
+int drtk_b200_mipmap_grid_sample_forward(const float* const* levels, const int64_t* level_hw,
+                                         const int64_t* level_strides, int num_levels, const float* grid,
+                                         const int64_t* grid_strides, const float* vt_dxdy_img,
+                                         const int64_t* vt_strides, int64_t N, int64_t C, int64_t H, int64_t W,
+                                         int max_aniso, int padding_mode, int interpolation_mode, int align_corners,
+                                         int force_max_aniso, int clip_grad, float* out, void* stream);
+
+int drtk_b200_mipmap_grid_sample_backward(const float* grad_out, const int64_t* grad_out_strides,
+                                          const float* const* levels, const int64_t* level_hw,
+                                          const int64_t* level_strides, int num_levels, const float* grid,
+                                          const int64_t* grid_strides, const float* vt_dxdy_img,
+                                          const int64_t* vt_strides, int64_t N, int64_t C, int64_t H, int64_t W,
+                                          int max_aniso, int padding_mode, int interpolation_mode, int align_corners,
+                                          int force_max_aniso, int clip_grad, float* const* grad_levels,
+                                          float* grad_grid, void* stream);
+
+int drtk_b200_grid_scatter_forward(const float* input, const int64_t* input_strides, const float* grid,
+                                   const int64_t* grid_strides, int64_t N, int64_t C, int64_t H, int64_t W,
+                                   int64_t out_H, int64_t out_W, int padding_mode, int interpolation_mode,
+                                   int align_corners, float* out, void* stream);
+
+int drtk_b200_grid_scatter_backward(const float* grad_out, const int64_t* grad_out_strides, const float* input,
+                                    const int64_t* input_strides, const float* grid, const int64_t* grid_strides,
+                                    int64_t N, int64_t C, int64_t H, int64_t W, int64_t out_H, int64_t out_W,
+                                    int padding_mode, int interpolation_mode, int align_corners, float* grad_input,
+                                    float* grad_grid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

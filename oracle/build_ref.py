@@ -16,6 +16,7 @@ one shared object per extension:
     oracle/_ref/render_ext.so      <- src/render/...
     oracle/_ref/interpolate_ext.so <- src/interpolate/...
     oracle/_ref/edge_grad_ext.so   <- src/edge_grad/...
+    oracle/_ref/grid_scatter_ext.so, mipmap_grid_sampler_ext.so <- src/grid_scatter/..., src/mipmap_grid_sampler/...
 
 The reference's setup.py is NOT run (it builds four unrelated extensions too and wants a
 writable source tree); ninja + nvcc/g++ are driven through torch.utils.cpp_extension.load
@@ -40,6 +41,9 @@ EXTS = {
     "render": ["render_module.cpp", "render_kernel.cu", "render_kernel_cpu.cpp"],
     "interpolate": ["interpolate_module.cpp", "interpolate_kernel.cu", "interpolate_kernel_cpu.cpp"],
     "edge_grad": ["edge_grad_module.cpp", "edge_grad_kernel.cu", "edge_grad_kernel_cpu.cpp"],
+    # the samplers either side of interpolate in real pipelines (CUDA only, no CPU twins)
+    "grid_scatter": ["grid_scatter_module.cpp", "grid_scatter_kernel.cu"],
+    "mipmap_grid_sampler": ["mipmap_grid_sampler_module.cpp", "mipmap_grid_sampler_kernel.cu"],
 }
 
 HERE = os.path.dirname(os.path.abspath(__file__))

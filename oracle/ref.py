@@ -16,7 +16,9 @@ import torch as th
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REF = os.path.join(_HERE, "_ref")
 _NAMES = ("rasterize", "render", "interpolate", "edge_grad")
+_SAMPLERS = ("grid_scatter", "mipmap_grid_sampler")
 _loaded = False
+_samplers_loaded = False
 
 
 def available() -> bool:
@@ -67,3 +69,38 @@ def edge_grad_estimator(v_pix, vi, bary_img, img, index_img, v_pix_img_hook=None
     if v_pix_img_hook is not None:
         v_pix_img.register_hook(v_pix_img_hook)
     return out
+
+
+# ---- samplers: CUDA-only ops of the reference --------------------------------------
+_MODE = {"bilinear": 0, "bicubic": 2}
+_PAD = {"zeros": 0, "border": 1, "reflection": 2}
+
+
+def samplers_available() -> bool:
+    return all(os.path.exists(os.path.join(_REF, f"{n}_ext.so")) for n in _SAMPLERS)
+
+
+def _load_samplers() -> None:
+    global _samplers_loaded
+    if not _samplers_loaded:
+        if not samplers_available():
+            raise RuntimeError("oracle/_ref sampler extensions missing: run `python oracle/build_ref.py`")
+        for n in _SAMPLERS:
+            th.ops.load_library(os.path.join(_REF, f"{n}_ext.so"))
+        _samplers_loaded = True
+
+
+def grid_scatter(input, grid, output_height, output_width, mode="bilinear", padding_mode="border", align_corners=None):
+    """`drtk/grid_scatter.py:18-105` around `grid_scatter_ext::grid_scatter_2d`."""
+    _load_samplers()
+    return th.ops.grid_scatter_ext.grid_scatter_2d(input, grid, output_height, output_width, _PAD[padding_mode],
+                                                   _MODE[mode], bool(align_corners))
+
+
+def mipmap_grid_sample(input, grid, vt_dxdy_img, max_aniso, mode="bilinear", padding_mode="zeros", align_corners=None,
+                       force_max_aniso=False, clip_grad=False):
+    """`drtk/mipmap_grid_sample.py:18-127` around `mipmap_grid_sampler_ext::mipmap_grid_sampler_2d`."""
+    _load_samplers()
+    return th.ops.mipmap_grid_sampler_ext.mipmap_grid_sampler_2d(
+        list(input), grid, vt_dxdy_img, max_aniso, _PAD[padding_mode], _MODE[mode], bool(align_corners),
+        bool(force_max_aniso), bool(clip_grad))
