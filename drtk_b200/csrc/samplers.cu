@@ -232,6 +232,9 @@ mipmap_fwd_kernel(TexList tex, PixelArgs a, float* __restrict__ out) {
         for (int lv = 0; lv < nlev; ++lv) {
           const Tex& T = tex.t[f.d1 + lv];
           const float alpha = (lv == 0 ? 1.f - f.a : f.a) * inv_n;
+          // a magnified texture (footprint below one texel) has a == 0: the coarser level would be fetched only to
+          // be multiplied by zero, as the reference does (:505-528); skipped here (identical for finite texels)
+          if (alpha == 0.f) continue;
           const float* base = T.p + n * T.sN + c0 * T.sC;
           // reference quirk: the forward kernel overrides align_corners with false (:423)
           if (!BICUBIC) {
@@ -293,6 +296,7 @@ mipmap_bwd_kernel(TexList tex, PixelArgs a, const float* __restrict__ gout, Stri
       for (int lv = 0; lv < nlev; ++lv) {
         const Tex& T = tex.t[f.d1 + lv];
         const float alpha = (lv == 0 ? 1.f - f.a : f.a) * inv_n;
+        if (alpha == 0.f) continue;  // contributes exact zeros to every gradient
         const float* base = T.p + n * T.sN;
         const int64_t tplane = int64_t(T.H) * T.W;
         float* gbase = T.g ? T.g + int64_t(n) * a.C * tplane : nullptr;
