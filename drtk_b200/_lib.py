@@ -19,6 +19,7 @@ _P = ctypes.c_void_p
 _I64 = ctypes.c_int64
 _INT = ctypes.c_int
 _F32 = ctypes.c_float
+_F64 = ctypes.c_double
 _SZ = ctypes.c_size_t
 
 # name -> (restype, argtypes); kept in sync with include/drtk_b200.h (tests/test_abi.py checks
@@ -66,6 +67,17 @@ PROTOTYPES = {
         _INT, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _P, _P]),
     "drtk_b200_grid_scatter_backward": (
         _INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _P, _P, _P]),
+    "drtk_b200_rasterize_f64_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
+    "drtk_b200_rasterize_f64": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _SZ, _P]),
+    "drtk_b200_render_forward_f64": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P]),
+    "drtk_b200_render_backward_f64": (
+        _INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P, _P]),
+    "drtk_b200_interpolate_forward_f64": (
+        _INT, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _P]),
+    "drtk_b200_interpolate_backward_f64": (
+        _INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _P, _P]),
+    "drtk_b200_edge_grad_backward_f64": (
+        _INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _F64, _P, _P]),
     "drtk_b200_transform_forward": (_INT, [_P, _P, _P, _P, _INT, _INT, _I64, _I64, _P, _P, _P]),
     "drtk_b200_transform_backward": (
         _INT, [_P, _P, _P, _P, _INT, _INT, _P, _P, _P, _P, _I64, _I64, _P, _P, _P]),

@@ -31,12 +31,27 @@ def _f32(t, who, name):
     return t
 
 
+def _real(t, who, name):
+    """float32 and float64 are served natively (fp32: the optimised kernels; fp64: the plain double-precision
+    kernels of csrc/fp64.cu, like the reference's AT_DISPATCH_FLOATING_TYPES); half/bfloat16 only under autocast."""
+    _chk(t.is_floating_point(), f"{who}(): expected {name} to have floating point type, but {name} has {t.dtype}")
+    return t if t.dtype == torch.float64 else _f32(t, who, name)
+
+
+def _like(t, ref):
+    return None if t is None else (t if t.dtype == ref.dtype else t.to(ref.dtype))
+
+
+def _sfx(t):
+    return "_f64" if t.dtype == torch.float64 else ""
+
+
 # ------------------------------------------------------------------------------------------
 def rasterize(v, vi, height, width, wireframe=False, algo=0):
     """-> (depth_img f32 [N,H,W], index_img i32 [N,H,W]); checks of src/rasterize/rasterize_kernel.cu:423-468."""
     _chk(isinstance(v, torch.Tensor) and isinstance(vi, torch.Tensor), "rasterize(): expected all inputs to be defined")
     _chk(v.device == vi.device and v.is_cuda, "rasterize(): expected all inputs to be on same cuda device")
-    v = _f32(v, "rasterize", "v")
+    v = _real(v, "rasterize", "v")
     _chk(vi.dtype == torch.int32, f"rasterize(): expected vi to have int32 type, but vi has {vi.dtype}")
     _chk(v.layout == torch.strided and vi.layout == torch.strided, "rasterize(): expected all inputs to have torch.strided layout")
     _chk(v.dim() == 3 and vi.dim() == 3,
@@ -55,6 +70,13 @@ def rasterize(v, vi, height, width, wireframe=False, algo=0):
     with torch.cuda.device(v.device):
         depth = torch.empty((N, H, W), dtype=torch.float32, device=v.device)
         index = torch.empty((N, H, W), dtype=torch.int32, device=v.device)
+        if v.dtype == torch.float64:  # depth_img stays float32 (src/rasterize/rasterize_kernel.cu:481)
+            ws = torch.empty((max(int(lib.drtk_b200_rasterize_f64_workspace_bytes(N, H, W)), 1),), dtype=torch.uint8, device=v.device)
+            rc = lib.drtk_b200_rasterize_f64(
+                _lib.ptr(v), _lib.strides(v), _lib.ptr(vi), _lib.strides(vi), N, V, F, H, W, int(bool(wireframe)),
+                _lib.ptr(depth), _lib.ptr(index), _lib.ptr(ws), ws.numel(), _stream(v.device))
+            _lib.check(rc, "rasterize()")
+            return depth, index
         nbytes = lib.drtk_b200_rasterize_workspace_bytes(N, F, H, W, algo)
         ws = torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=v.device)
         rc = lib.drtk_b200_rasterize(
@@ -84,15 +106,15 @@ def _check_render(v, vi, index_img):
 
 def render_forward(v, vi, index_img):
     """-> (depth_img [N,H,W], bary_img [N,3,H,W]); checks of src/render/render_kernel.cu:285-336."""
-    v = _f32(v, "render", "v")
+    v = _real(v, "render", "v")
     _check_render(v, vi, index_img)
     lib = _lib.load()
     N, V, F = v.size(0), v.size(1), vi.size(1)
     H, W = index_img.size(1), index_img.size(2)
     with torch.cuda.device(v.device):
-        depth = torch.empty((N, H, W), dtype=torch.float32, device=v.device)
-        bary = torch.empty((N, 3, H, W), dtype=torch.float32, device=v.device)
-        rc = lib.drtk_b200_render_forward(
+        depth = torch.empty((N, H, W), dtype=v.dtype, device=v.device)
+        bary = torch.empty((N, 3, H, W), dtype=v.dtype, device=v.device)
+        rc = getattr(lib, "drtk_b200_render_forward" + _sfx(v))(
             _lib.ptr(v), _lib.strides(v), _lib.ptr(vi), _lib.strides(vi), _lib.ptr(index_img),
             _lib.strides(index_img), N, V, F, H, W, _lib.ptr(depth), _lib.ptr(bary), _stream(v.device))
     _lib.check(rc, "render()")
@@ -105,6 +127,17 @@ def render_backward(v, vi, index_img, grad_depth, grad_bary):
     lib = _lib.load()
     N, V, F = v.size(0), v.size(1), vi.size(1)
     H, W = index_img.size(1), index_img.size(2)
+    if v.dtype == torch.float64:
+        grad_depth, grad_bary = _like(grad_depth, v), _like(grad_bary, v)
+        with torch.cuda.device(v.device):
+            grad_v = torch.empty((N, V, 3), dtype=torch.float64, device=v.device)
+            rc = lib.drtk_b200_render_backward_f64(
+                _lib.ptr(v), _lib.strides(v), _lib.ptr(vi), _lib.strides(vi), _lib.ptr(index_img),
+                _lib.strides(index_img), _lib.ptr(grad_depth), None if grad_depth is None else _lib.strides(grad_depth),
+                _lib.ptr(grad_bary), None if grad_bary is None else _lib.strides(grad_bary), N, V, F, H, W,
+                _lib.ptr(grad_v), _stream(v.device))
+        _lib.check(rc, "render() backward")
+        return grad_v
     if grad_depth is not None:
         grad_depth = _f32(grad_depth, "render", "grad_depth_img")
     if grad_bary is not None:
@@ -153,14 +186,14 @@ def interpolate_forward(attr, vi, index_img, bary_img):
         attr = attr.float() if attr.dtype != torch.float32 else attr
         bary_img = bary_img.float() if bary_img.dtype != torch.float32 else bary_img
     _check_interp(attr, vi, index_img, bary_img)
-    attr = _f32(attr, "interpolate", "vert_attributes")
+    attr = _real(attr, "interpolate", "vert_attributes")
     lib = _lib.load()
     N, V, C = attr.shape
     F = vi.size(1)
     H, W = bary_img.size(2), bary_img.size(3)
     with torch.cuda.device(attr.device):
-        out = torch.empty((N, C, H, W), dtype=torch.float32, device=attr.device)
-        rc = lib.drtk_b200_interpolate_forward(
+        out = torch.empty((N, C, H, W), dtype=attr.dtype, device=attr.device)
+        rc = getattr(lib, "drtk_b200_interpolate_forward" + _sfx(attr))(
             _lib.ptr(attr), _lib.strides(attr), _lib.ptr(vi), _lib.strides(vi), _lib.ptr(index_img),
             _lib.strides(index_img), _lib.ptr(bary_img), _lib.strides(bary_img), N, V, F, C, H, W,
             _lib.ptr(out), _stream(attr.device))
@@ -176,11 +209,11 @@ def interpolate_backward(grad_out, attr, vi, index_img, bary_img, need_attr_grad
     N, V, C = attr.shape
     F = vi.size(1)
     H, W = bary_img.size(2), bary_img.size(3)
-    grad_out = _f32(grad_out, "interpolate", "grad_out")
+    grad_out = _like(grad_out, attr) if attr.dtype == torch.float64 else _f32(grad_out, "interpolate", "grad_out")
     with torch.cuda.device(attr.device):
-        ga = torch.empty((N, V, C), dtype=torch.float32, device=attr.device) if need_attr_grad else None
-        gb = torch.empty((N, 3, H, W), dtype=torch.float32, device=attr.device) if need_bary_grad else None
-        rc = lib.drtk_b200_interpolate_backward(
+        ga = torch.empty((N, V, C), dtype=attr.dtype, device=attr.device) if need_attr_grad else None
+        gb = torch.empty((N, 3, H, W), dtype=attr.dtype, device=attr.device) if need_bary_grad else None
+        rc = getattr(lib, "drtk_b200_interpolate_backward" + _sfx(attr))(
             _lib.ptr(grad_out), _lib.strides(grad_out), _lib.ptr(attr), _lib.strides(attr), _lib.ptr(vi),
             _lib.strides(vi), _lib.ptr(index_img), _lib.strides(index_img), _lib.ptr(bary_img),
             _lib.strides(bary_img), N, V, F, C, H, W, _lib.ptr(ga), _lib.ptr(gb), _stream(attr.device))
@@ -309,15 +342,18 @@ def edge_grad_backward(v_pix, img, index_img, vi, grad_output, max_dp_dr):
     """-> grad_v_pix_img [N,3,H,W] (src/edge_grad/edge_grad_kernel.cu:475-506)."""
     _chk(vi.dim() == 3 and vi.size(2) == 3, "drtk_b200: internal launchers expect vi as [N,F,3]")
     lib = _lib.load()
-    v_pix = _f32(v_pix, "edge_grad_estimator", "v_pix")
-    img = _f32(img, "edge_grad_estimator", "img")
-    grad_output = _f32(grad_output, "edge_grad_estimator", "grad_output")
+    v_pix = _real(v_pix, "edge_grad_estimator", "v_pix")
+    if v_pix.dtype == torch.float64:
+        img, grad_output = _like(img, v_pix), _like(grad_output, v_pix)
+    else:
+        img = _f32(img, "edge_grad_estimator", "img")
+        grad_output = _f32(grad_output, "edge_grad_estimator", "grad_output")
     N, V = v_pix.size(0), v_pix.size(1)
     F = vi.size(1)
     C, H, W = img.size(1), img.size(2), img.size(3)
     with torch.cuda.device(v_pix.device):
-        out = torch.empty((N, 3, H, W), dtype=torch.float32, device=v_pix.device)
-        rc = lib.drtk_b200_edge_grad_backward(
+        out = torch.empty((N, 3, H, W), dtype=v_pix.dtype, device=v_pix.device)
+        rc = getattr(lib, "drtk_b200_edge_grad_backward" + _sfx(v_pix))(
             _lib.ptr(v_pix), _lib.strides(v_pix), _lib.ptr(img), _lib.strides(img), _lib.ptr(index_img),
             _lib.strides(index_img), _lib.ptr(vi), _lib.strides(vi), _lib.ptr(grad_output),
             _lib.strides(grad_output), N, V, F, C, H, W, float(max_dp_dr), _lib.ptr(out),
@@ -330,6 +366,9 @@ def edge_grad_backward_fused(v_pix, img, index_img, vi, grad_output, bary_img, m
     """-> grad_v_pix [N,V,3]: edge_grad backward followed by the C = 3 interpolate backward of the conduit,
     in one kernel (no [N,3,H,W] gradient image)."""
     _chk(vi.dim() == 3 and vi.size(2) == 3, "drtk_b200: internal launchers expect vi as [N,F,3]")
+    if v_pix.dtype == torch.float64:  # fp64: the two plain kernels back to back, as the reference does
+        g_img = edge_grad_backward(v_pix, img, index_img, vi, grad_output, max_dp_dr)
+        return interpolate_backward(g_img, v_pix, vi, index_img, _like(bary_img, v_pix), True, False)[0]
     lib = _lib.load()
     v_pix = _f32(v_pix, "edge_grad_estimator", "v_pix")
     img = _f32(img, "edge_grad_estimator", "img")

@@ -48,8 +48,9 @@ class _VPixImgConduit(th.autograd.Function):
         if grad_v_pix_img is None or not ctx.needs_input_grad[0]:
             return None, None, None, None
         v_pix, vi, index_img, bary_img = ctx.saved_tensors
-        v32 = v_pix.detach() if v_pix.dtype == th.float32 else v_pix.detach().float()
-        b32 = bary_img.detach() if bary_img.dtype == th.float32 else bary_img.detach().float()
+        native = (th.float32, th.float64)
+        v32 = v_pix.detach() if v_pix.dtype in native else v_pix.detach().float()
+        b32 = bary_img.detach().to(v32.dtype)
         ga, _ = _ops.interpolate_backward(grad_v_pix_img, v32, vi, index_img, b32, True, False)
         return ga.to(v_pix.dtype), None, None, None
 

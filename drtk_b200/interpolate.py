@@ -23,8 +23,9 @@ class _InterpolateFn(th.autograd.Function):
         if grad_out is None or not (need_attr or need_bary):
             return None, None, None, None
         attr, vi, index_img, bary_img = ctx.saved_tensors
-        a32 = attr.detach() if attr.dtype == th.float32 else attr.detach().float()
-        b32 = bary_img.detach() if bary_img.dtype == th.float32 else bary_img.detach().float()
+        native = (th.float32, th.float64)
+        a32 = attr.detach() if attr.dtype in native else attr.detach().float()
+        b32 = bary_img.detach() if bary_img.dtype in native else bary_img.detach().float()
         ga, gb = _ops.interpolate_backward(grad_out, a32, vi, index_img, b32, need_attr, need_bary)
         if ga is not None:
             ga = ga.to(attr.dtype)

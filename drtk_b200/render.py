@@ -24,8 +24,8 @@ class _RenderFn(th.autograd.Function):
         if not ctx.needs_input_grad[0]:
             return None, None, None
         v, vi, index_img = ctx.saved_tensors
-        grad_v = _ops.render_backward(v.detach().float() if v.dtype != th.float32 else v.detach(), vi,
-                                      index_img, grad_depth, grad_bary)
+        vd = v.detach() if v.dtype in (th.float32, th.float64) else v.detach().float()
+        grad_v = _ops.render_backward(vd, vi, index_img, grad_depth, grad_bary)
         return grad_v.to(v.dtype), None, None
 
 

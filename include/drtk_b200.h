@@ -280,6 +280,48 @@ int drtk_b200_grid_scatter_backward(const float* grad_out, const int64_t* grad_o
                                     int padding_mode, int interpolation_mode, int align_corners, float* grad_input,
                                     float* grad_grid, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * float64 dispatch of the six hot-path launchers (the reference instantiates every kernel for float and double,
+ * src/include/kernel_utils.h:47-57).  Same arguments and contracts as the float entry points above, with double
+ * data; no workspace except the packed 64-bit z-buffer of the rasteriser; `rasterize_f64` still writes a float
+ * depth_img (src/rasterize/rasterize_kernel.cu:481) and does not offer wireframe mode.  Plain kernels (thread per
+ * pixel, atomicAdd(double)): fp64 is for gradient checks, not throughput.
+ * ------------------------------------------------------------------------------------- */
+size_t drtk_b200_rasterize_f64_workspace_bytes(int64_t N, int64_t H, int64_t W);
+
+int drtk_b200_rasterize_f64(const double* v, const int64_t* v_strides, const int32_t* vi, const int64_t* vi_strides,
+                            int64_t N, int64_t V, int64_t F, int64_t H, int64_t W, int wireframe, float* depth_img,
+                            int32_t* index_img, void* workspace, size_t workspace_bytes, void* stream);
+
+int drtk_b200_render_forward_f64(const double* v, const int64_t* v_strides, const int32_t* vi,
+                                 const int64_t* vi_strides, const int32_t* index_img, const int64_t* index_strides,
+                                 int64_t N, int64_t V, int64_t F, int64_t H, int64_t W, double* depth_img,
+                                 double* bary_img, void* stream);
+
+int drtk_b200_render_backward_f64(const double* v, const int64_t* v_strides, const int32_t* vi,
+                                  const int64_t* vi_strides, const int32_t* index_img, const int64_t* index_strides,
+                                  const double* grad_depth, const int64_t* grad_depth_strides, const double* grad_bary,
+                                  const int64_t* grad_bary_strides, int64_t N, int64_t V, int64_t F, int64_t H,
+                                  int64_t W, double* grad_v, void* stream);
+
+int drtk_b200_interpolate_forward_f64(const double* vert_attributes, const int64_t* attr_strides, const int32_t* vi,
+                                      const int64_t* vi_strides, const int32_t* index_img, const int64_t* index_strides,
+                                      const double* bary_img, const int64_t* bary_strides, int64_t N, int64_t V,
+                                      int64_t F, int64_t C, int64_t H, int64_t W, double* out, void* stream);
+
+int drtk_b200_interpolate_backward_f64(const double* grad_out, const int64_t* grad_out_strides,
+                                       const double* vert_attributes, const int64_t* attr_strides, const int32_t* vi,
+                                       const int64_t* vi_strides, const int32_t* index_img, const int64_t* index_strides,
+                                       const double* bary_img, const int64_t* bary_strides, int64_t N, int64_t V,
+                                       int64_t F, int64_t C, int64_t H, int64_t W, double* vert_attributes_grad,
+                                       double* bary_img_grad, void* stream);
+
+int drtk_b200_edge_grad_backward_f64(const double* v_pix, const int64_t* v_strides, const double* img,
+                                     const int64_t* img_strides, const int32_t* index_img, const int64_t* index_strides,
+                                     const int32_t* vi, const int64_t* vi_strides, const double* grad_output,
+                                     const int64_t* grad_output_strides, int64_t N, int64_t V, int64_t F, int64_t C,
+                                     int64_t H, int64_t W, double max_dp_dr, double* grad_v_pix_img, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
