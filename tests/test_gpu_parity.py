@@ -104,7 +104,7 @@ def test_rasterize_bit_exact_vs_reference_cuda(scene):
 
 
 @needs_ref
-@pytest.mark.parametrize("cfg,N,overdraw", [(3, 8, False), (3, 2, True), (4, 2, False), (4, 1, True)])
+@pytest.mark.parametrize("cfg,N,overdraw", [(3, 8, False), (3, 2, True), (4, 2, False), (4, 1, True), (5, 1, False)])
 def test_rasterize_bit_exact_vs_reference_cuda_baseline_sizes(cfg, N, overdraw):
     v, vi, H, W = scenes.config_mesh(cfg, N=N, overdraw=overdraw, device=DEV)
     d_ref, i_ref = R.rasterize_with_depth(v, vi, H, W)
@@ -571,6 +571,32 @@ def test_pipeline_autograd_golden_no_hook(name):
     (out * cu(g["w_img"])).sum().backward()
     assert_close(npy(v.grad), g["grad_v_full"], rtol=2e-5, what="grad_v (fused pipeline)")
     assert_close(npy(attr.grad), g["grad_attr_full"], rtol=2e-5, what="grad_attr (fused pipeline)")
+
+
+@needs_ref
+def test_config5_slice_vs_reference_cuda():
+    """One image of BASELINE config 5 (1 002 528 triangles, 4096 x 4096, 16 attributes): the whole forward + backward
+    against the reference's CUDA kernels, compared on the device (2^30 output elements: 64-bit image offsets)."""
+    N, C = 1, 16
+    v, vi, H, W = scenes.config_mesh(5, N=N, device=DEV)
+    attr = scenes.vertex_attributes(N, v.shape[1], C, seed=5, device=DEV)
+    w = th.rand((N, C, H, W), device=DEV, generator=th.Generator(device=DEV).manual_seed(6))
+    res = {}
+    for tag, api in (("ref", R), ("new", drtk_b200)):
+        vv, aa = v.clone().requires_grad_(True), attr.clone().requires_grad_(True)
+        index = api.rasterize(vv, vi, H, W)
+        depth, bary = api.render(vv, vi, index)
+        img = api.interpolate(aa, vi, index, bary)
+        out = api.edge_grad_estimator(vv, vi, bary, img, index)
+        out.backward(gradient=w)
+        res[tag] = (index, depth.detach(), bary.detach(), img.detach(), vv.grad, aa.grad)
+        del out, img, bary, depth
+    r, n = res["ref"], res["new"]
+    assert th.equal(r[0], n[0]), "index_img"
+    for k, name, tol in ((1, "depth", 1e-5), (2, "bary", 1e-5), (3, "img", 1e-5), (4, "grad_v", 5e-5), (5, "grad_attr", 5e-5)):
+        scale = float(r[k].abs().max())
+        bad = ((n[k] - r[k]).abs() > tol * r[k].abs() + tol * scale)
+        assert not bool(bad.any()), f"{name}: {int(bad.sum())} elements out of tolerance"
 
 
 @pytest.mark.parametrize("cfg,N,overdraw,expand_vi", [(3, 2, False, True), (3, 1, True, False), (4, 1, False, True)])
