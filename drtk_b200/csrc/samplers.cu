@@ -22,13 +22,17 @@ namespace {
 constexpr int kMaxLevels = 11;  // max_mipmap_count, mipmap_grid_sampler_kernel.cu:16
 constexpr int kZeros = 0, kBorder = 1, kReflection = 2;
 
+// I = int32_t when every offset into every level fits 31 bits (the common case; like the reference's
+// canUse32BitIndexMath dispatch), else int64_t: 64-bit multiplies cost four integer instructions each on the SM
+template <typename I>
 struct Tex {
   const float* p;
   float* g;  // gradient accumulator (dense NCHW) or nullptr
   int H, W;
-  int64_t sN, sC, sH, sW;
+  I sN, sC, sH, sW;
 };
-struct TexList { Tex t[kMaxLevels]; };
+template <typename I>
+struct TexList { Tex<I> t[kMaxLevels]; };
 
 // ---- grid_sample coordinate helpers -------------------------------------------------------
 __device__ __forceinline__ float unnormalize(float c, int size, bool align, float* mult) {
@@ -136,8 +140,9 @@ struct Bilinear {
     inside = unsigned(bx0 && by0) | unsigned(bx1 && by0) << 1 | unsigned(bx0 && by1) << 2 | unsigned(bx1 && by1) << 3;
   }
   __device__ __forceinline__ bool in(int q) const { return (inside >> q) & 1u; }
-  __device__ __forceinline__ int64_t off(int q, int64_t sH, int64_t sW) const {
-    return int64_t(y0 + (q >> 1)) * sH + int64_t(x0 + (q & 1)) * sW;
+  template <typename I>
+  __device__ __forceinline__ I off(int q, I sH, I sW) const {
+    return I(y0 + (q >> 1)) * sH + I(x0 + (q & 1)) * sW;
   }
 };
 
@@ -163,7 +168,8 @@ struct Bicubic {
     }
   }
   __device__ __forceinline__ bool in(int q, int j) const { return (xi[q] | yi[j]) >= 0; }
-  __device__ __forceinline__ int64_t off(int q, int j, int64_t sH, int64_t sW) const { return yi[j] * sH + xi[q] * sW; }
+  template <typename I>
+  __device__ __forceinline__ I off(int q, int j, I sH, I sW) const { return I(yi[j]) * sH + I(xi[q]) * sW; }
 };
 
 // ---- mip level selection (mipmap_grid_sampler_kernel.cu:441-498) ---------------------------
@@ -173,7 +179,8 @@ struct Footprint {
   float a;       // blend towards level d1 + 1
 };
 __device__ __forceinline__ Footprint select_levels(float dudx, float dvdx, float dudy, float dvdy, int W0, int H0,
-                                                   int levels, int max_aniso, bool force_max, bool clip_grad) {
+                                                   int levels, float lmax, int max_aniso, bool force_max,
+                                                   bool clip_grad) {
   const float ax = dudx * float(W0), bx = dvdx * float(H0), ay = dudy * float(W0), by = dvdy * float(H0);
   const float px = sqrtf(ax * ax + bx * bx + 1e-12f), py = sqrtf(ay * ay + by * by + 1e-12f);
   const float pmax = fmaxf(px, py), pmin = fminf(px, py);
@@ -181,8 +188,8 @@ __device__ __forceinline__ Footprint select_levels(float dudx, float dvdx, float
   if (pmin == 0.f || N == 0.f) N = 1.f;
   float lambda = log2f(pmax / N);
   if (isnan(lambda) || isinf(lambda)) lambda = 0.f;
-  // the reference evaluates `mipmaps - 1 - 1e-6` in double and rounds to float
-  float l = fminf(lambda, float(double(levels - 1) - 1e-6));
+  // lmax = float(double(levels - 1) - 1e-6), rounded on the host the way the reference's mixed float/double `min` does
+  float l = fminf(lambda, lmax);
   if (clip_grad && lambda > float(levels - 1)) {  // missing coarse levels: shrink the footprint instead
     const float s = exp2f(l) * N / pmax;
     dudx *= s; dvdx *= s; dudy *= s; dvdy *= s;
@@ -197,23 +204,24 @@ __device__ __forceinline__ Footprint select_levels(float dudx, float dvdx, float
   f.dv = major_x ? dvdx : dvdy;
   return f;
 }
-__device__ __forceinline__ float sample_pos(int i, int n) {  // (i+1)/(n+1)*2-1, evaluated in double like the reference
-  return float((double(i) + 1.0) / (double(n) + 1.0) * 2.0 - 1.0);
-}
+// position of sample i of n along the major axis, (i+1)/(n+1)*2-1 = (2i+1-n)/(n+1).  The reference evaluates it in
+// double (:500-501); one float division instead keeps fp64 instructions (1/64 rate on B200) out of the tap loop
+__device__ __forceinline__ float sample_pos(int i, int n) { return float(2 * i + 1 - n) / float(n + 1); }
 
 struct PixelArgs {
   const float* grid; Strides4 gs;
   const float* jac; int64_t js[5];
   int N, C, H, W;
   int levels, max_aniso, pad;
+  float lmax;
   bool align, force_max, clip_grad;
 };
 
 constexpr int kCh = 4;  // channels kept in registers per pass
 
-template <bool BICUBIC>
+template <bool BICUBIC, typename I>
 __global__ void __launch_bounds__(256)
-mipmap_fwd_kernel(TexList tex, PixelArgs a, float* __restrict__ out) {
+mipmap_fwd_kernel(TexList<I> tex, PixelArgs a, float* __restrict__ out) {
   const int64_t total = int64_t(a.N) * a.H * a.W, plane = int64_t(a.H) * a.W;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
     const int w = int(idx % a.W), h = int((idx / a.W) % a.H), n = int(idx / plane);
@@ -221,7 +229,7 @@ mipmap_fwd_kernel(TexList tex, PixelArgs a, float* __restrict__ out) {
     const float u = __ldg(pg), v = __ldg(pg + a.gs.s3);
     const float* pj = a.jac + n * a.js[0] + h * a.js[1] + w * a.js[2];
     const Footprint f = select_levels(__ldg(pj), __ldg(pj + a.js[4]), __ldg(pj + a.js[3]), __ldg(pj + a.js[3] + a.js[4]),
-                                      tex.t[0].W, tex.t[0].H, a.levels, a.max_aniso, a.force_max, a.clip_grad);
+                                      tex.t[0].W, tex.t[0].H, a.levels, a.lmax, a.max_aniso, a.force_max, a.clip_grad);
     const int nlev = a.levels > 1 ? 2 : 1;
     const float inv_n = 1.f / float(f.n);
     float* po = out + int64_t(n) * a.C * plane + int64_t(h) * a.W + w;
@@ -230,12 +238,12 @@ mipmap_fwd_kernel(TexList tex, PixelArgs a, float* __restrict__ out) {
       for (int i = 0; i < f.n; ++i) {
         const float t = sample_pos(i, f.n), su = u + f.du * t, sv = v + f.dv * t;
         for (int lv = 0; lv < nlev; ++lv) {
-          const Tex& T = tex.t[f.d1 + lv];
+          const Tex<I>& T = tex.t[f.d1 + lv];
           const float alpha = (lv == 0 ? 1.f - f.a : f.a) * inv_n;
           // a magnified texture (footprint below one texel) has a == 0: the coarser level would be fetched only to
           // be multiplied by zero, as the reference does (:505-528); skipped here (identical for finite texels)
           if (alpha == 0.f) continue;
-          const float* base = T.p + n * T.sN + c0 * T.sC;
+          const float* base = T.p + I(n) * T.sN + I(c0) * T.sC;
           // reference quirk: the forward kernel overrides align_corners with false (:423)
           if (!BICUBIC) {
             const Bilinear b(su, sv, T.H, T.W, a.pad, false);
@@ -245,7 +253,7 @@ mipmap_fwd_kernel(TexList tex, PixelArgs a, float* __restrict__ out) {
                 float s = 0.f;
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                  if (b.in(q)) s += __ldg(base + k * T.sC + b.off(q, T.sH, T.sW)) * b.w[q];
+                  if (b.in(q)) s += __ldg(base + I(k) * T.sC + b.off(q, T.sH, T.sW)) * b.w[q];
                 acc[k] += s * alpha;
               }
             }
@@ -260,7 +268,7 @@ mipmap_fwd_kernel(TexList tex, PixelArgs a, float* __restrict__ out) {
                   float r = 0.f;
 #pragma unroll
                   for (int q = 0; q < 4; ++q)
-                    if (b.in(q, j)) r += __ldg(base + k * T.sC + b.off(q, j, T.sH, T.sW)) * b.cx[q];
+                    if (b.in(q, j)) r += __ldg(base + I(k) * T.sC + b.off(q, j, T.sH, T.sW)) * b.cx[q];
                   s += r * b.cy[j];
                 }
                 acc[k] += s * alpha;
@@ -276,9 +284,9 @@ mipmap_fwd_kernel(TexList tex, PixelArgs a, float* __restrict__ out) {
   }
 }
 
-template <bool BICUBIC>
+template <bool BICUBIC, typename I>
 __global__ void __launch_bounds__(256)
-mipmap_bwd_kernel(TexList tex, PixelArgs a, const float* __restrict__ gout, Strides4 gos, float* __restrict__ grad_grid) {
+mipmap_bwd_kernel(TexList<I> tex, PixelArgs a, const float* __restrict__ gout, Strides4 gos, float* __restrict__ grad_grid) {
   const int64_t total = int64_t(a.N) * a.H * a.W, plane = int64_t(a.H) * a.W;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
     const int w = int(idx % a.W), h = int((idx / a.W) % a.H), n = int(idx / plane);
@@ -286,7 +294,7 @@ mipmap_bwd_kernel(TexList tex, PixelArgs a, const float* __restrict__ gout, Stri
     const float u = __ldg(pg), v = __ldg(pg + a.gs.s3);
     const float* pj = a.jac + n * a.js[0] + h * a.js[1] + w * a.js[2];
     const Footprint f = select_levels(__ldg(pj), __ldg(pj + a.js[4]), __ldg(pj + a.js[3]), __ldg(pj + a.js[3] + a.js[4]),
-                                      tex.t[0].W, tex.t[0].H, a.levels, a.max_aniso, a.force_max, a.clip_grad);
+                                      tex.t[0].W, tex.t[0].H, a.levels, a.lmax, a.max_aniso, a.force_max, a.clip_grad);
     const int nlev = a.levels > 1 ? 2 : 1;
     const float inv_n = 1.f / float(f.n);
     const float* pgo = gout + n * gos.s0 + h * gos.s2 + w * gos.s3;
@@ -294,12 +302,12 @@ mipmap_bwd_kernel(TexList tex, PixelArgs a, const float* __restrict__ gout, Stri
     for (int i = 0; i < f.n; ++i) {
       const float t = sample_pos(i, f.n), su = u + f.du * t, sv = v + f.dv * t;
       for (int lv = 0; lv < nlev; ++lv) {
-        const Tex& T = tex.t[f.d1 + lv];
+        const Tex<I>& T = tex.t[f.d1 + lv];
         const float alpha = (lv == 0 ? 1.f - f.a : f.a) * inv_n;
         if (alpha == 0.f) continue;  // contributes exact zeros to every gradient
-        const float* base = T.p + n * T.sN;
-        const int64_t tplane = int64_t(T.H) * T.W;
-        float* gbase = T.g ? T.g + int64_t(n) * a.C * tplane : nullptr;
+        const float* base = T.p + I(n) * T.sN;
+        const I tplane = I(T.H) * I(T.W);
+        float* gbase = T.g ? T.g + I(n) * I(a.C) * tplane : nullptr;
         float sx = 0.f, sy = 0.f;
         // the backward kernel honours align_corners (reference quirk: unlike its forward)
         if (!BICUBIC) {
@@ -309,8 +317,8 @@ mipmap_bwd_kernel(TexList tex, PixelArgs a, const float* __restrict__ gout, Stri
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (b.in(q)) {
-                if (gbase) red_add(gbase + c * tplane + b.off(q, T.W, 1), b.w[q] * go);
-                const float val = __ldg(base + c * T.sC + b.off(q, T.sH, T.sW));
+                if (gbase) red_add(gbase + I(c) * tplane + b.off(q, I(T.W), I(1)), b.w[q] * go);
+                const float val = __ldg(base + I(c) * T.sC + b.off(q, T.sH, T.sW));
                 sx += val * b.dx[q] * go;
                 sy += val * b.dy[q] * go;
               }
@@ -326,8 +334,8 @@ mipmap_bwd_kernel(TexList tex, PixelArgs a, const float* __restrict__ gout, Stri
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 if (b.in(q, j)) {
-                  if (gbase) red_add(gbase + c * tplane + b.off(q, j, T.W, 1), go * b.cx[q] * b.cy[j]);
-                  const float val = __ldg(base + c * T.sC + b.off(q, j, T.sH, T.sW));
+                  if (gbase) red_add(gbase + I(c) * tplane + b.off(q, j, I(T.W), I(1)), go * b.cx[q] * b.cy[j]);
+                  const float val = __ldg(base + I(c) * T.sC + b.off(q, j, T.sH, T.sW));
                   sx -= go * val * b.gx[q] * b.cy[j];
                   sy -= go * val * b.gy[j] * b.cx[q];
                 }
@@ -368,7 +376,7 @@ scatter_fwd_kernel(ScatterArgs a, float* __restrict__ out) {
         const float val = __ldg(pin + c * a.is.s1);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (b.in(q)) red_add(ob + c * oplane + b.off(q, a.Wo, 1), b.w[q] * val);
+          if (b.in(q)) red_add(ob + c * oplane + b.off(q, int64_t(a.Wo), int64_t(1)), b.w[q] * val);
       }
     } else {
       const Bicubic b(u, v, a.Ho, a.Wo, a.pad, a.align, true, false);
@@ -378,7 +386,7 @@ scatter_fwd_kernel(ScatterArgs a, float* __restrict__ out) {
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            if (b.in(q, j)) red_add(ob + c * oplane + b.off(q, j, a.Wo, 1), val * b.cx[q] * b.cy[j]);
+            if (b.in(q, j)) red_add(ob + c * oplane + b.off(q, j, int64_t(a.Wo), int64_t(1)), val * b.cx[q] * b.cy[j]);
       }
     }
   }
@@ -452,16 +460,32 @@ inline bool bad_enum(int pad, int interp) { return pad < 0 || pad > 2 || (interp
 
 using namespace drtk;
 
-static int fill_levels(TexList& tl, const float* const* levels, float* const* grad_levels, const int64_t* hw,
+// true when every element offset of every level (input strides and the dense gradient planes) fits 31 bits
+static bool levels_fit_int32(const int64_t* hw, const int64_t* strides, int L, int64_t N, int64_t C) {
+  for (int i = 0; i < L; ++i) {
+    const int64_t H = hw[2 * i], W = hw[2 * i + 1], *s = strides + 4 * i;
+    int64_t span = 0;
+    const int64_t ext[4] = {N, C, H, W};
+    for (int d = 0; d < 4; ++d) {
+      if (s[d] < 0) return false;
+      span += (ext[d] > 0 ? ext[d] - 1 : 0) * s[d];
+    }
+    if (span >= INT32_MAX || N * C * H * W >= INT32_MAX) return false;
+  }
+  return true;
+}
+
+template <typename I>
+static int fill_levels(TexList<I>& tl, const float* const* levels, float* const* grad_levels, const int64_t* hw,
                        const int64_t* strides, int L) {
   for (int i = 0; i < L; ++i) {
     if (hw[2 * i] <= 0 || hw[2 * i + 1] <= 0 || hw[2 * i] > INT32_MAX || hw[2 * i + 1] > INT32_MAX)
       return DRTK_B200_EINVAL;
-    Tex& t = tl.t[i];
+    Tex<I>& t = tl.t[i];
     t.p = levels[i];
     t.g = grad_levels ? grad_levels[i] : nullptr;
     t.H = int(hw[2 * i]); t.W = int(hw[2 * i + 1]);
-    t.sN = strides[4 * i]; t.sC = strides[4 * i + 1]; t.sH = strides[4 * i + 2]; t.sW = strides[4 * i + 3];
+    t.sN = I(strides[4 * i]); t.sC = I(strides[4 * i + 1]); t.sH = I(strides[4 * i + 2]); t.sW = I(strides[4 * i + 3]);
   }
   for (int i = L; i < kMaxLevels; ++i) tl.t[i] = tl.t[L - 1];
   return 0;
@@ -477,6 +501,7 @@ static int fill_pixel_args(PixelArgs& a, const float* grid, const int64_t* gs, c
   for (int i = 0; i < 5; ++i) a.js[i] = js[i];
   a.N = int(N); a.C = int(C); a.H = int(H); a.W = int(W);
   a.levels = L; a.max_aniso = max_aniso; a.pad = pad;
+  a.lmax = float(double(L - 1) - 1e-6);
   a.align = align != 0; a.force_max = force_max != 0; a.clip_grad = clip_grad != 0;
   return 0;
 }
@@ -489,12 +514,9 @@ extern "C" int drtk_b200_mipmap_grid_sample_forward(
   if (!levels || !level_hw || !level_strides || num_levels < 1 || num_levels > kMaxLevels ||
       bad_enum(padding_mode, interpolation_mode))
     return DRTK_B200_EINVAL;
-  TexList tl;
   PixelArgs a;
-  int rc = fill_levels(tl, levels, nullptr, level_hw, level_strides, num_levels);
-  if (rc) return rc;
-  rc = fill_pixel_args(a, grid, grid_strides, vt_dxdy_img, vt_strides, N, C, H, W, num_levels, max_aniso, padding_mode,
-                       align_corners, force_max_aniso, clip_grad);
+  int rc = fill_pixel_args(a, grid, grid_strides, vt_dxdy_img, vt_strides, N, C, H, W, num_levels, max_aniso, padding_mode,
+                           align_corners, force_max_aniso, clip_grad);
   if (rc) return rc;
   const int64_t total = N * H * W;
   if (total == 0 || C == 0) return 0;
@@ -502,8 +524,18 @@ extern "C" int drtk_b200_mipmap_grid_sample_forward(
     if (!levels[i]) return DRTK_B200_EINVAL;
   if (!out) return DRTK_B200_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (interpolation_mode == 0) mipmap_fwd_kernel<false><<<blocks_for(total), 256, 0, st>>>(tl, a, out);
-  else mipmap_fwd_kernel<true><<<blocks_for(total), 256, 0, st>>>(tl, a, out);
+  const bool bicubic = interpolation_mode != 0;
+  if (levels_fit_int32(level_hw, level_strides, num_levels, N, C)) {
+    TexList<int32_t> tl;
+    if ((rc = fill_levels(tl, levels, nullptr, level_hw, level_strides, num_levels))) return rc;
+    if (bicubic) mipmap_fwd_kernel<true, int32_t><<<blocks_for(total), 256, 0, st>>>(tl, a, out);
+    else mipmap_fwd_kernel<false, int32_t><<<blocks_for(total), 256, 0, st>>>(tl, a, out);
+  } else {
+    TexList<int64_t> tl;
+    if ((rc = fill_levels(tl, levels, nullptr, level_hw, level_strides, num_levels))) return rc;
+    if (bicubic) mipmap_fwd_kernel<true, int64_t><<<blocks_for(total), 256, 0, st>>>(tl, a, out);
+    else mipmap_fwd_kernel<false, int64_t><<<blocks_for(total), 256, 0, st>>>(tl, a, out);
+  }
   DRTK_CHECK_LAUNCH();
   return 0;
 }
@@ -517,13 +549,12 @@ extern "C" int drtk_b200_mipmap_grid_sample_backward(
   if (!grad_out_strides || !levels || !level_hw || !level_strides || num_levels < 1 ||
       num_levels > kMaxLevels || bad_enum(padding_mode, interpolation_mode))
     return DRTK_B200_EINVAL;
-  TexList tl;
   PixelArgs a;
-  int rc = fill_levels(tl, levels, grad_levels, level_hw, level_strides, num_levels);
+  int rc = fill_pixel_args(a, grid, grid_strides, vt_dxdy_img, vt_strides, N, C, H, W, num_levels, max_aniso, padding_mode,
+                           align_corners, force_max_aniso, clip_grad);
   if (rc) return rc;
-  rc = fill_pixel_args(a, grid, grid_strides, vt_dxdy_img, vt_strides, N, C, H, W, num_levels, max_aniso, padding_mode,
-                       align_corners, force_max_aniso, clip_grad);
-  if (rc) return rc;
+  for (int i = 0; i < num_levels; ++i)
+    if (level_hw[2 * i] <= 0 || level_hw[2 * i + 1] <= 0) return DRTK_B200_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (grad_levels)
     for (int i = 0; i < num_levels; ++i)
@@ -534,10 +565,19 @@ extern "C" int drtk_b200_mipmap_grid_sample_backward(
   if (!grad_out) return DRTK_B200_EINVAL;
   for (int i = 0; i < num_levels; ++i)
     if (!levels[i]) return DRTK_B200_EINVAL;
-  if (interpolation_mode == 0)
-    mipmap_bwd_kernel<false><<<blocks_for(total), 256, 0, st>>>(tl, a, grad_out, make4(grad_out_strides), grad_grid);
-  else
-    mipmap_bwd_kernel<true><<<blocks_for(total), 256, 0, st>>>(tl, a, grad_out, make4(grad_out_strides), grad_grid);
+  const bool bicubic = interpolation_mode != 0;
+  const Strides4 gos = make4(grad_out_strides);
+  if (levels_fit_int32(level_hw, level_strides, num_levels, N, C)) {
+    TexList<int32_t> tl;
+    if ((rc = fill_levels(tl, levels, grad_levels, level_hw, level_strides, num_levels))) return rc;
+    if (bicubic) mipmap_bwd_kernel<true, int32_t><<<blocks_for(total), 256, 0, st>>>(tl, a, grad_out, gos, grad_grid);
+    else mipmap_bwd_kernel<false, int32_t><<<blocks_for(total), 256, 0, st>>>(tl, a, grad_out, gos, grad_grid);
+  } else {
+    TexList<int64_t> tl;
+    if ((rc = fill_levels(tl, levels, grad_levels, level_hw, level_strides, num_levels))) return rc;
+    if (bicubic) mipmap_bwd_kernel<true, int64_t><<<blocks_for(total), 256, 0, st>>>(tl, a, grad_out, gos, grad_grid);
+    else mipmap_bwd_kernel<false, int64_t><<<blocks_for(total), 256, 0, st>>>(tl, a, grad_out, gos, grad_grid);
+  }
   DRTK_CHECK_LAUNCH();
   return 0;
 }
