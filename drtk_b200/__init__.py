@@ -25,13 +25,14 @@ from .rasterize import rasterize, rasterize_with_depth  # noqa: F401
 from .render import render, render_ref  # noqa: F401
 from .transform import transform, transform_with_v_cam  # noqa: F401
 from . import utils  # noqa: F401,E402
+from .screen_space_uv_derivative import screen_space_uv_derivative  # noqa: F401,E402
 
 __version__ = "0.1.0"
 
 __all__ = [
     "rasterize", "rasterize_with_depth", "render", "interpolate", "interpolation_matrix", "interpolation_normal_matrix",
     "edge_grad_estimator", "render_ref", "interpolate_ref", "grid_scatter", "grid_scatter_ref", "mipmap_grid_sample",
-    "mipmap_grid_sample_ref",
+    "mipmap_grid_sample_ref", "screen_space_uv_derivative",
     "transform", "transform_with_v_cam", "utils", "build", "install_as_drtk", "native_library_path",
 ]
 
@@ -48,5 +49,5 @@ def install_as_drtk() -> None:
         raise RuntimeError("a different `drtk` package is already imported")
     sys.modules["drtk"] = this
     for sub in ("rasterize", "render", "interpolate", "edge_grad_estimator", "transform", "utils", "grid_scatter",
-                "mipmap_grid_sample"):
+                "mipmap_grid_sample", "screen_space_uv_derivative"):
         sys.modules[f"drtk.{sub}"] = sys.modules[f"{__name__}.{sub}"]

@@ -78,6 +78,8 @@ PROTOTYPES = {
         _INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _P, _P]),
     "drtk_b200_edge_grad_backward_f64": (
         _INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _F64, _P, _P]),
+    "drtk_b200_screen_space_uv_derivative": (
+        _INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P]),
     "drtk_b200_transform_forward": (_INT, [_P, _P, _P, _P, _INT, _INT, _I64, _I64, _P, _P, _P]),
     "drtk_b200_transform_backward": (
         _INT, [_P, _P, _P, _P, _INT, _INT, _P, _P, _P, _P, _I64, _I64, _P, _P, _P]),

@@ -322,6 +322,23 @@ int drtk_b200_edge_grad_backward_f64(const double* v_pix, const int64_t* v_strid
                                      const int64_t* grad_output_strides, int64_t N, int64_t V, int64_t F, int64_t C,
                                      int64_t H, int64_t W, double max_dp_dr, double* grad_v_pix_img, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * screen_space_uv_derivative -- the producer of `vt_dxdy_img` for mipmap_grid_sample, one kernel instead of the
+ * reference's composition of face_dpdt + 2 x interpolate + project_points_grad + 2x2 inverse
+ * (drtk/screen_space_uv_derivative.py:16-80; pinhole camera, as in the reference).
+ *   v [N,V,3], vt [N,T,2] f32; vi, vti [F,3] i32 (shared topology; element strides *_strides[2])
+ *   index_img [N,H,W] i32; bary_img [N,3,H,W] f32; mask [N,H,W] bool (1 byte per pixel)
+ *   cam [N,16] f32 dense: campos 3, camrot 9 (row major), focal 4 (row major)
+ *   out [N,H,W,2,2] f32 dense = [[du/dx, dv/dx], [du/dy, dv/dy]]; zero where mask is false or the pixel is empty
+ * Forward only (no gradient); the Python host falls back to the differentiable composition when one is needed.
+ * ------------------------------------------------------------------------------------- */
+int drtk_b200_screen_space_uv_derivative(const float* v, const int64_t* v_strides, const float* vt,
+                                         const int64_t* vt_strides, const int32_t* vi, const int64_t* vi_strides,
+                                         const int32_t* vti, const int64_t* vti_strides, const int32_t* index_img,
+                                         const int64_t* index_strides, const float* bary_img,
+                                         const int64_t* bary_strides, const uint8_t* mask, const int64_t* mask_strides,
+                                         const float* cam, int64_t N, int64_t H, int64_t W, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

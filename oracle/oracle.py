@@ -319,3 +319,32 @@ def transform_vjp_fd(w_pix, w_cam, v, campos, camrot, focal, princpt, modes=None
                 gf[:, k] = (per_item_loss(hi)[0] - per_item_loss(lo)[0]) / (2 * h)
         out[name] = g
     return out
+
+
+# ---- screen_space_uv_derivative: numpy restatement of drtk/screen_space_uv_derivative.py:16-80 -------------
+def screen_space_uv_derivative(v, vt, vi, vti, index_img, bary_img, mask, campos, camrot, focal):
+    """float64.  v [N,V,3], vt [N,T,2], vi / vti [F,3], index_img [N,H,W], bary_img [N,3,H,W], mask [N,H,W] bool,
+    pinhole camera.  -> [N,H,W,2,2] = [[du/dx, dv/dx], [du/dy, dv/dy]], zero outside mask.  Pixels with index -1
+    are zero too (the reference evaluates interpolate's background sweep there; callers mask them)."""
+    v, vt, bary = (np.asarray(a, np.float64) for a in (v, vt, bary_img))
+    N, H, W = index_img.shape
+    out = np.zeros((N, H, W, 2, 2))
+    for n in range(N):
+        live = (index_img[n] >= 0) & np.asarray(mask[n], bool)
+        t = index_img[n][live]
+        corners, uv = v[n][vi[t]], vt[n][vti[t]]                                   # [P,3,3], [P,3,2]
+        dpdb = corners[:, 1:3] - corners[:, 0:1]                                   # geometry.py:73
+        dtdb = uv[:, 1:3] - uv[:, 0:1]
+        dpdt = np.linalg.solve(dtdb, dpdb)                                         # :77-81, [P,2,3]
+        b = bary[n][:, live].T                                                     # [P,3]
+        dpdt = dpdt * b.sum(1)[:, None, None]       # interpolating a per-face constant scales it by sum(b)
+        p = (corners * b[:, :, None]).sum(1)
+        R, c, Fm = (np.asarray(a[n], np.float64) for a in (camrot, campos, focal))
+        dcam = dpdt @ R.T                                                          # projection.py:683-684
+        pcam = (p - c) @ R.T
+        z = pcam[:, 2]
+        z = np.where(z < 0, np.minimum(z, -1e-8), np.maximum(z, 1e-8))
+        dproj = (dcam[:, :, :2] * z[:, None, None] - pcam[:, None, :2] * dcam[:, :, 2:3]) / (z * z)[:, None, None]
+        dpix = dproj @ Fm.T                                                        # [P, i, j] = d pix_j / d t_i
+        out[n][live] = np.linalg.inv(dpix)
+    return out

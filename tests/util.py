@@ -12,7 +12,7 @@ def golden_cases():
     # wire_*.npz (wireframe, reference CUDA outputs) and mat_*.npz (interpolation matrices, reference CPU outputs)
     # and transform_*.npz (projection, reference project_points outputs) are handled by their own tests
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not os.path.basename(p).startswith(("wire_", "mat_", "transform_", "samp_", "sampcuda_")))
+                  if not os.path.basename(p).startswith(("wire_", "mat_", "transform_", "samp_", "sampcuda_", "uvd_")))
 
 
 def load_golden(name):
