@@ -69,7 +69,8 @@ __global__ void raster_tri_kernel(const T* __restrict__ v, Strides3 vs, const in
   const T den = v01x * v02y - v01y * v02x;
   if (den == 0) return;
   const int bx0 = max(0, int(mnx)), by0 = max(0, int(mny));
-  const int bx1 = min(W - 1, int(mxx) + 1), by1 = min(H - 1, int(mxy) + 1);
+  // (the clamp before the conversion keeps `+ 1` from overflowing on huge coordinates)
+  const int bx1 = min(W - 1, int(fmin(mxx, T(W))) + 1), by1 = min(H - 1, int(fmin(mxy, T(H))) + 1);
   bool tl[3];
   top_left(den, v01x, v01y, v02x, v02y, v12x, v12y, tl);
   const T s = sign_d(den), aden = fabs(den);
