@@ -36,7 +36,7 @@ def levels_of(g):
 
 
 def test_fixture_sets():
-    assert len(SCATTER) == 12 and len(MIPMAP) == 24
+    assert len(SCATTER) == 12 and len(MIPMAP) == 24 and len(CUDA_MIP) == 5 and len(CUDA_SCATTER) == 4
 
 
 # ---- CPU: oracle vs the reference's statements -------------------------------------------------------
@@ -87,6 +87,41 @@ def test_torch_statement_mipmap(name):
     assert_close(grid.grad.numpy(), g["g_grid"], rtol=1e-10)
     for l, x in enumerate(lv):
         assert_close(x.grad.numpy(), g[f"g_level{l}"], rtol=1e-11)
+
+
+# ---- CPU: oracle vs outputs of the reference CUDA kernels (captured on a B200 by make_golden_samplers_cuda.py) -----
+CUDA_MIP = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "sampcuda_mipmap_*.npz")))
+CUDA_SCATTER = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "sampcuda_scatter_*.npz")))
+
+
+def _frac_bad(a, e, rtol):
+    a, e = np.asarray(a, np.float64), np.asarray(e, np.float64)
+    return float((np.abs(a - e) > rtol * np.abs(e) + rtol * np.abs(e).max()).mean())
+
+
+@pytest.mark.parametrize("name", CUDA_MIP)
+def test_oracle_mipmap_vs_reference_cuda_vectors(name):
+    """Per-pixel sample counts, clip_grad, the forward's align_corners override, non-square textures.  The fixtures are
+    fp32 GPU results; a pixel whose footprint sits on a level / sample-count boundary may fall on the other side of it."""
+    g = load(name)
+    aniso, interp, pad, nlev, align, force, clip = map(int, g["meta"])
+    lv = levels_of(g)
+    out = S.mipmap_grid_sample_fwd(lv, g["grid"], g["jac"], aniso, interp, pad, bool(align), bool(force), bool(clip))
+    assert _frac_bad(out, g["out"], 1e-5) < 5e-3, "out"
+    gl, gg = S.mipmap_grid_sample_bwd(g["w"], lv, g["grid"], g["jac"], aniso, interp, pad, bool(align), bool(force), bool(clip))
+    assert _frac_bad(gg, g["g_grid"], 3e-5) < 5e-3, "grad grid"
+    for l, x in enumerate(gl):
+        assert _frac_bad(x, g[f"g_level{l}"], 3e-5) < 2e-2, f"grad level {l}"
+
+
+@pytest.mark.parametrize("name", CUDA_SCATTER)
+def test_oracle_grid_scatter_vs_reference_cuda_vectors(name):
+    """Splat positions far outside the image: the bicubic kernel pads the sample position itself."""
+    g = load(name)
+    Ho, Wo, interp, pad, align = map(int, g["meta"])
+    assert _frac_bad(S.grid_scatter_fwd(g["input"], g["grid"], Ho, Wo, interp, pad, bool(align)), g["out"], 1e-5) < 2e-3
+    gi, gg = S.grid_scatter_bwd(g["w"], g["input"], g["grid"], interp, pad, bool(align))
+    assert _frac_bad(gi, g["g_input"], 1e-5) < 2e-3 and _frac_bad(gg, g["g_grid"], 3e-5) < 2e-3
 
 
 def test_argument_errors_cpu():
@@ -141,11 +176,6 @@ def _mip_inputs(seed, N=2, C=5, H=37, W=53, S=(64, 48), nlev=4, reach=1.2):
     jac = (th.rand((N, H, W, 2, 2), generator=g) - 0.5) * th.tensor([0.4, 0.04])[:, None] * th.rand((N, H, W, 1, 1), generator=g)
     w = th.rand((N, C, H, W), generator=g)
     return levels, grid, jac, w
-
-
-def _frac_bad(a, e, rtol):
-    a, e = np.asarray(a, np.float64), np.asarray(e, np.float64)
-    return float((np.abs(a - e) > rtol * np.abs(e) + rtol * np.abs(e).max()).mean())
 
 
 def _run_mip(fn, levels, grid, jac, w, *args, **kw):
