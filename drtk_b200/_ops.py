@@ -31,6 +31,16 @@ def _f32(t, who, name):
     return t
 
 
+def autocast_f32(*tensors):
+    """Under torch.autocast the reference's Autocast kernels cast every floating input to float32
+    (`cached_cast(kFloat32, ...)`, e.g. src/render/render_module.cpp:79-83).  The casts are autograd-tracked, so the
+    gradients return to the original (half / bfloat16) leaves in their own dtype."""
+    if not torch.is_autocast_enabled():
+        return tensors
+    return tuple(t.float() if (t is not None and t.is_floating_point() and t.dtype != torch.float32) else t
+                 for t in tensors)
+
+
 def _real(t, who, name):
     """float32 and float64 are served natively (fp32: the optimised kernels; fp64: the plain double-precision
     kernels of csrc/fp64.cu, like the reference's AT_DISPATCH_FLOATING_TYPES); half/bfloat16 only under autocast."""

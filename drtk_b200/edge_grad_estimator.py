@@ -119,6 +119,7 @@ def edge_grad_estimator(
     """
     if vi.ndim == 2:
         vi = vi[None, ...].expand(v_pix.shape[0], -1, -1)
+    v_pix, bary_img, img = _ops.autocast_f32(v_pix, bary_img, img)  # (src/edge_grad/edge_grad_module.cpp:172-196)
     if v_pix_img_hook is None:
         return _EdgeGradFusedFn.apply(v_pix, vi, bary_img.detach(), img, index_img, max_dp_dr)
     v_pix_img = _VPixImgConduit.apply(v_pix, vi, index_img, bary_img.detach())

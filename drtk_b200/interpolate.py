@@ -45,6 +45,7 @@ def interpolate(vert_attributes: th.Tensor, vi: th.Tensor, index_img: th.Tensor,
     """
     if vi.ndim == 2:
         vi = vi[None].expand(vert_attributes.shape[0], -1, -1)
+    vert_attributes, bary_img = _ops.autocast_f32(vert_attributes, bary_img)
     return _InterpolateFn.apply(vert_attributes, vi, index_img, bary_img)
 
 

@@ -23,7 +23,8 @@ def rasterize(v: th.Tensor, vi: th.Tensor, height: int, width: int, wireframe: b
     if vi.ndim == 2:
         vi = vi[None].expand(v.shape[0], -1, -1)
     with th.no_grad():
-        _, index_img = _ops.rasterize(v.detach(), vi, height, width, wireframe)
+        (v,) = _ops.autocast_f32(v.detach())
+        _, index_img = _ops.rasterize(v, vi, height, width, wireframe)
     return index_img
 
 
@@ -36,5 +37,6 @@ def rasterize_with_depth(
     if vi.ndim == 2:
         vi = vi[None].expand(v.shape[0], -1, -1)
     with th.no_grad():
-        depth_img, index_img = _ops.rasterize(v.detach(), vi, height, width, wireframe)
+        (v,) = _ops.autocast_f32(v.detach())
+        depth_img, index_img = _ops.rasterize(v, vi, height, width, wireframe)
     return depth_img, index_img

@@ -38,6 +38,7 @@ def render(v: th.Tensor, vi: th.Tensor, index_img: th.Tensor) -> Tuple[th.Tensor
     """
     if vi.ndim == 2:
         vi = vi[None].expand(v.shape[0], -1, -1)
+    (v,) = _ops.autocast_f32(v)
     return _RenderFn.apply(v, vi, index_img)
 
 

@@ -719,3 +719,36 @@ def test_pipeline_under_cuda_graph_capture():
         assert th.equal(outs[0], eager[0]) and th.equal(outs[1], eager[1])
         assert_close(npy(outs[2]), npy(eager[2]), rtol=5e-5, what="grad_v under graph replay")
         assert_close(npy(outs[3]), npy(eager[3]), rtol=5e-5, what="grad_attr under graph replay")
+
+
+@pytest.mark.parametrize("half", [th.float16, th.bfloat16])
+def test_autocast_casts_to_float32_like_the_reference(half):
+    """Under torch.autocast the reference's Autocast kernels cast floating inputs to float32 (src/*/..._module.cpp);
+    outputs are float32, gradients come back in the leaves' own dtype; outside autocast half inputs are refused."""
+    H, W, N, C = 64, 96, 2, 4
+    v, vi = scenes.grid_mesh(9, 8, H, W, N, seed=51)
+    vh = (v.to(DEV) * th.tensor([1.0, 1.0, 1.0], device=DEV)).to(half)
+    ah = scenes.vertex_attributes(N, v.shape[1], C, seed=52, device=DEV).to(half)
+    vid = vi.to(DEV)
+
+    def run(vv, aa):
+        index = drtk_b200.rasterize(vv, vid, H, W)
+        depth, bary = drtk_b200.render(vv, vid, index)
+        img = drtk_b200.interpolate(aa, vid, index, bary)
+        out = drtk_b200.edge_grad_estimator(vv, vid, bary, img, index)
+        (out.sum() + depth.sum()).backward()
+        return index, depth, bary, out
+
+    v1, a1 = vh.clone().requires_grad_(True), ah.clone().requires_grad_(True)
+    with th.autocast("cuda", dtype=half):
+        r1 = run(v1, a1)
+    v2, a2 = vh.float().requires_grad_(True), ah.float().requires_grad_(True)
+    r2 = run(v2, a2)
+    assert r1[1].dtype == r1[2].dtype == r1[3].dtype == th.float32
+    for x, y in zip(r1, r2):
+        assert th.equal(x, y)
+    assert v1.grad.dtype == half and a1.grad.dtype == half
+    assert_close(npy(v1.grad.float()), npy(v2.grad), rtol=2e-2, what="grad_v through the half cast")
+    assert_close(npy(a1.grad.float()), npy(a2.grad), rtol=2e-2, what="grad_attr through the half cast")
+    with pytest.raises(RuntimeError, match="float32 only|same dtype"):
+        drtk_b200.render(vh, vid, r2[0])
