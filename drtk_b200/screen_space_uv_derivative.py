@@ -31,6 +31,7 @@ def _composed(v, vt, vi, vti, index_img, bary_img, mask, campos, camrot, focal, 
     return th.where(mask[..., None, None], out, th.zeros_like(out))
 
 
+@th.compiler.disable
 def screen_space_uv_derivative(
     v: th.Tensor,
     vt: th.Tensor,

@@ -233,6 +233,7 @@ def _f32(t, name):
     raise RuntimeError(f"transform(): drtk_b200 computes in float32 only, but {name} has {t.dtype}; cast it to float32")
 
 
+@th.compiler.disable  # ctypes launch inside: keep torch.compile out, like the reference's native ops
 def project_points(v, campos, camrot, focal, princpt, distortion_mode=None, distortion_coeff=None, fov=None,
                    lut_vector_field=None, lut_spacing=None) -> Tuple[th.Tensor, th.Tensor]:
     """-> (v_pix, v_cam), both [N,V,3]; v_pix = (x_pixels, y_pixels, z_camera).  `drtk/utils/projection.py:486-646`."""
