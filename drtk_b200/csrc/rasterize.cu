@@ -201,20 +201,24 @@ __global__ void __launch_bounds__(256) bin_kernel(RasterArgs a, int64_t total, u
   }
 }
 
-// exclusive scan of `count[0..M)` into `offset[0..M)`, zeroing `count` so that bin_kernel<true>
-// can reuse it as the per-tile cursor.  One CTA of 1024 threads sweeps the array in coalesced
-// slabs of 4096 entries (uint4 per thread) carrying the running total; M is #tiles * N (3e4 at
-// config 4, 1.3e5 at config 5), so a multi-CTA scan would not pay for its extra launch.
-__global__ void __launch_bounds__(1024) scan_kernel(uint32_t* count, uint32_t* offset, int64_t M) {
+// Per-image exclusive scan of the tile counts into list offsets, zeroing `count` so that bin_kernel<true> can
+// reuse it as the per-tile cursor.  One CTA of 1024 threads per IMAGE (a small triangle adds at most four list
+// entries, so image n owns the fixed list region [n * 4F, (n + 1) * 4F) and the images scan independently):
+// T tiles in coalesced slabs of 4096 entries (uint4 per thread) carrying the running total -- one slab at
+// config 4, four at config 5.  (A single CTA over all N * T counters took 13.6 us at config 4.)
+__global__ void __launch_bounds__(1024) scan_kernel(uint32_t* count, uint32_t* offset, int64_t M,
+                                                    uint32_t list_stride, bool vec) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry_s = 0u;
+  count += (int64_t)blockIdx.x * M;
+  offset += (int64_t)blockIdx.x * M;
+  if (tid == 0) carry_s = blockIdx.x * list_stride;
   __syncthreads();
   for (int64_t base = 0; base < M; base += 4096) {
     const int64_t i = base + (int64_t)tid * 4;
     uint32_t c[4] = {0u, 0u, 0u, 0u};
-    if (i + 3 < M) {
+    if (vec && i + 3 < M) {
       const uint4 q = *reinterpret_cast<const uint4*>(count + i);
       c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
     } else {
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* count, uint32_t* o
     uint32_t o4[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { o4[k] = run; run += c[k]; }
-    if (i + 3 < M) {
+    if (vec && i + 3 < M) {
       *reinterpret_cast<uint4*>(offset + i) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
       *reinterpret_cast<uint4*>(count + i) = make_uint4(0u, 0u, 0u, 0u);
     } else {
@@ -746,7 +750,9 @@ extern "C" int drtk_b200_rasterize(const float* v, const int64_t* v_strides, con
     const unsigned blocks = (unsigned)((total + 255) / 256);
     bin_kernel<false><<<blocks, 256, 0, stream>>>(a, total, tile_count, nullptr, nullptr, nullptr, nullptr);
     DRTK_CHECK_LAUNCH();
-    scan_kernel<<<1, 1024, 0, stream>>>(tile_count, tile_offset, w.M);
+    const int64_t T = w.M / N;  // tiles per image; 16-B aligned per-image segments allow the uint4 path
+    if (4 * F * N > 0xFFFFFFFFLL) return DRTK_B200_EUNSUPPORTED;
+    scan_kernel<<<(unsigned)N, 1024, 0, stream>>>(tile_count, tile_offset, T, (uint32_t)(4 * F), (T & 3) == 0);
     DRTK_CHECK_LAUNCH();
     bin_kernel<true><<<blocks, 256, 0, stream>>>(a, total, tile_count, tile_offset, tile_list,
                                                  large_count, large_list);
