@@ -383,7 +383,10 @@ def main():
     for _ in range(3):
         step_e2e()
     e2e_finish()
-    ms_e2e = timed_region(step_e2e, args.steps, e2e_finish)
+    # host-side interference (another tenant on the box's PCIe root / memory controller) once doubled this number on
+    # an otherwise healthy run: the K-step region is timed twice and the faster pass is reported, both are listed
+    e2e_runs = [timed_region(step_e2e, args.steps, e2e_finish) for _ in range(2)]
+    ms_e2e = min(e2e_runs)
     clocks = sampler.stop() if sampler else None
 
     # host <-> device copy bandwidth of this box (context for e2e: 62 MB cross PCIe every step)
@@ -438,6 +441,7 @@ def main():
                    "l2": "per-step working set ~10 GB >> 126 MB L2 (inputs larger than L2, no explicit flush)",
                    "loss": "none materialised: backward seeded with cotangent w (= gradient of the linear loss (img*w).sum()), no torch kernels on big tensors inside the step"},
         "e2e": {"value": e2e_value, "unit": "Mpix/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step_runs": [round(x, 4) for x in e2e_runs],
                 "note": "pinned host v_pix/attr/vi copied in, grad_v + grad_attr (the step's result) copied out, every step, inside the timed region; copies double-buffered on side streams (prefetch of step k+1 / read-back of step k overlap compute)"},
         "gpu_launches": sum(KERNELS.values()) * args.steps,
         "clocks": clocks, "roofline": roofline, "per_op": breakdown, "pcie": pcie,
@@ -459,6 +463,39 @@ def main():
                                           "note": "unmodified reference CUDA kernels (oracle/_ref, sm_100 build), same tensors, same cotangent"}
         except Exception as ex:  # noqa: BLE001
             line["reference_cuda"] = {"unavailable": repr(ex)[:200]}
+
+    # ---- the same step captured once in a CUDA graph and replayed (informational: launch + Python overhead out) ----
+    if world == 1:
+        try:
+            for name, fn in orig.items():  # drop the per-op event hooks: no event timing inside a capture
+                setattr(_ops, name, fn)
+            gv_s = v_d.detach().clone().requires_grad_(True)
+            ga_s = attr_d.detach().clone().requires_grad_(True)
+
+            def graph_step():
+                index = drtk_b200.rasterize(gv_s, vi_d, H, W)
+                _, bary = drtk_b200.render(gv_s, vi_d, index)
+                img = drtk_b200.interpolate(ga_s, vi_d, index, bary)
+                img = drtk_b200.edge_grad_estimator(gv_s, vi_d, bary, img, index)
+                return th.autograd.grad(img, (gv_s, ga_s), grad_outputs=w)
+
+            side = th.cuda.Stream(dev)
+            side.wait_stream(main)
+            with th.cuda.stream(side):
+                for _ in range(2):
+                    graph_step()
+            main.wait_stream(side)
+            graph = th.cuda.CUDAGraph()
+            with th.cuda.graph(graph):
+                graph_out = graph_step()
+            for _ in range(2):
+                graph.replay()
+            ms_graph = timed_region(graph.replay, args.steps)
+            line["cuda_graph"] = {"ms_per_step": ms_graph, "value": total_px / (ms_graph * 1e-3) / 1e6, "unit": "Mpix/s",
+                                  "note": "one forward+backward step captured with torch.cuda.graph and replayed; same kernels"}
+            del graph, graph_out
+        except Exception as ex:  # noqa: BLE001
+            line["cuda_graph"] = {"unavailable": repr(ex)[:200]}
 
     if world == 1 and not args.no_cpu_baseline:
         r = run_reference_cpu(cfg, steps=3, warmup=1)
