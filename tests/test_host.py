@@ -1,4 +1,5 @@
 """CPU suite: host-side logic of the drop-in package (no GPU, no kernel launches)."""
+import os
 import sys
 
 import pytest
@@ -144,3 +145,26 @@ def test_pure_torch_refs_match_the_oracle():
     vv = v.double().requires_grad_(True)
     drtk_b200.render_ref(vv, vi, th.from_numpy(index))[1].sum().backward()
     assert vv.grad is not None and bool(th.isfinite(vv.grad).all())
+
+
+def test_product_never_touches_the_oracle_or_the_reference():
+    """The oracle / oracle/_ref are test infrastructure: no module of the product may import or open them, and every
+    op with a kernel in the reference refuses CPU tensors instead of falling back."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in glob.glob(os.path.join(root, "drtk_b200", "*.py")):
+        src = open(f).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+        assert "oracle/" not in src and "_ref/" not in src and "/root/reference" not in src, f
+    x = th.zeros(1, 3, 3)
+    vi = th.zeros(1, 3, dtype=th.int32)
+    idx = th.zeros(1, 4, 4, dtype=th.int32)
+    bary = th.zeros(1, 3, 4, 4)
+    for call in (lambda: drtk_b200.rasterize(x, vi, 4, 4), lambda: drtk_b200.render(x, vi, idx),
+                 lambda: drtk_b200.interpolate(x, vi, idx, bary),
+                 lambda: drtk_b200.edge_grad_estimator(x, vi, bary, bary, idx).sum().backward(),
+                 lambda: drtk_b200.grid_scatter(bary, th.zeros(1, 4, 4, 2), 4, 4),
+                 lambda: drtk_b200.mipmap_grid_sample([bary], th.zeros(1, 4, 4, 2), th.zeros(1, 4, 4, 2, 2), 1)):
+        with pytest.raises(RuntimeError):
+            call()
