@@ -318,9 +318,16 @@ __global__ void __launch_bounds__(kEThreads, 4) edge_grad_tile_kernel(EdgeArgs a
 //     pre-pass, instead of the index -> vi -> v two-level gather (3 + 6 scalar loads per triangle).
 constexpr int kStripPx = 256, kStripWarps = 8;
 
-__global__ void __launch_bounds__(256) xy_table_kernel(EdgeArgs a, float4* __restrict__ table) {
+// Also zero-fills grad_v_pix, which the strip kernel accumulates into (saves a memset launch per step).
+__global__ void __launch_bounds__(256) xy_table_kernel(EdgeArgs a, float4* __restrict__ table, float* __restrict__ zero,
+                                                       int64_t zero_count) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
+  {
+    const int64_t gid = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * gridDim.y * blockDim.x;
+    for (int64_t i = gid; i < zero_count; i += nthreads) zero[i] = 0.f;
+  }
   if (f >= a.F) return;
   const int32_t* vip = a.vi + (int64_t)n * a.vis.s0 + (int64_t)f * a.vis.s1;
   const float* vp = a.v + (int64_t)n * a.vs.s0;
@@ -442,9 +449,13 @@ static int edge_launch(const float* v_pix, const int64_t* v_strides, const float
   if (N < 0 || C < 0 || H < 0 || W < 0) return DRTK_B200_EINVAL;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool fused = grad_v_pix != nullptr;
-  if (fused && N * V > 0) DRTK_CUDA(cudaMemsetAsync(grad_v_pix, 0, sizeof(float) * (size_t)(N * V * 3), stream));
+  // grad_v_pix is zero-filled by xy_table_kernel on the strip path, by a memset everywhere else
+  auto zero_grad_v = [&]() -> int {
+    if (fused && N * V > 0) DRTK_CUDA(cudaMemsetAsync(grad_v_pix, 0, sizeof(float) * (size_t)(N * V * 3), stream));
+    return 0;
+  };
   const int64_t npix = N * H * W;
-  if (npix == 0) return 0;
+  if (npix == 0) return zero_grad_v();
   if (!v_pix || !img || !index_img || !vi || !grad_output || (!fused && !grad_v_pix_img) || (fused && !bary_img))
     return DRTK_B200_EINVAL;
   if (H > (1 << 30) || W > (1 << 30) || N > 65535) return DRTK_B200_EUNSUPPORTED;
@@ -464,7 +475,7 @@ static int edge_launch(const float* v_pix, const int64_t* v_strides, const float
     const size_t tb = (size_t)(N * F) * 32;
     if (!workspace || workspace_bytes < tb + 32) return DRTK_B200_EWORKSPACE;
     float4* table = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(workspace) + 31) & ~uintptr_t(31));
-    xy_table_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)N), 256, 0, stream>>>(a, table);
+    xy_table_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)N), 256, 0, stream>>>(a, table, grad_v_pix, N * V * 3);
     const int strips_per_row = (int)((W + kStripPx - 1) / kStripPx);
     const int64_t num_strips = N * (H - 1) * strips_per_row;
     const int64_t need = (num_strips + kStripWarps - 1) / kStripWarps;
@@ -474,6 +485,7 @@ static int edge_launch(const float* v_pix, const int64_t* v_strides, const float
     DRTK_CHECK_LAUNCH();
     return 0;
   }
+  if (const int rc = zero_grad_v()) return rc;
   if (fused) edge_grad_tile_kernel<true><<<grid, kEThreads, 0, stream>>>(a, nullptr, fz);
   else edge_grad_tile_kernel<false><<<grid, kEThreads, 0, stream>>>(a, grad_v_pix_img, fz);
   DRTK_CHECK_LAUNCH();

@@ -581,9 +581,12 @@ struct QSmem {
   unsigned long long empty[kBwdStages];
 };
 
+// Also zero-fills the vertex-gradient table the walkers reduce into (saves a memset launch per step).
 __global__ void __launch_bounds__(256) vi_table_kernel(const int32_t* __restrict__ vi, Strides3 vis, int F,
-                                                       int64_t total, int4* __restrict__ tab) {
+                                                       int64_t total, int4* __restrict__ tab,
+                                                       float4* __restrict__ zero, int64_t zero_count) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t j = i; j < zero_count; j += (int64_t)gridDim.x * blockDim.x) zero[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i >= total) return;
   const int64_t n = i / F, f = i - n * F;
   const int32_t* vip = vi + n * vis.s0 + f * vis.s1;
@@ -949,10 +952,14 @@ extern "C" int drtk_b200_interpolate_backward(
     float* bary_img_grad, void* stream_) {
   if (N < 0 || V < 0 || C < 0 || H < 0 || W < 0) return DRTK_B200_EINVAL;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (vert_attributes_grad && N * V * C > 0)
-    DRTK_CUDA(cudaMemsetAsync(vert_attributes_grad, 0, sizeof(float) * (size_t)(N * V * C), stream));  // (:661)
+  // (:661) the vertex-gradient table starts at zero: vi_table_kernel does it on the quad-walker path, a memset elsewhere
+  auto zero_vert_grad = [&]() -> int {
+    if (vert_attributes_grad && N * V * C > 0)
+      DRTK_CUDA(cudaMemsetAsync(vert_attributes_grad, 0, sizeof(float) * (size_t)(N * V * C), stream));
+    return 0;
+  };
   const int64_t npix = N * H * W;
-  if (npix == 0) return 0;
+  if (npix == 0) return zero_vert_grad();
   if (!vert_attributes_grad && !bary_img_grad) return 0;
   if (C == 0) {
     if (bary_img_grad) DRTK_CUDA(cudaMemsetAsync(bary_img_grad, 0, sizeof(float) * (size_t)(npix * 3), stream));
@@ -993,7 +1000,8 @@ extern "C" int drtk_b200_interpolate_backward(
       int4* tab = nullptr;
       DRTK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tab), sizeof(int4) * (size_t)(tab_imgs * F), stream));
       const int64_t total = tab_imgs * F;
-      vi_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(vi, b.f.vis, (int)F, total, tab);
+      vi_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+          vi, b.f.vis, (int)F, total, tab, reinterpret_cast<float4*>(vert_attributes_grad), nv ? N * V * C / 4 : 0);
       // 256-bit attribute-row loads need 32-B aligned rows
       const bool v8 = avec && (b.f.as.s1 % 8 == 0) && (b.f.as.s0 % 8 == 0) && (C % 8 == 0) &&
                       (reinterpret_cast<uintptr_t>(vert_attributes) % 32 == 0);
@@ -1025,6 +1033,7 @@ extern "C" int drtk_b200_interpolate_backward(
       if (e2 != cudaSuccess) return (int)e2;
       return 0;
     }
+    if (const int rcz = zero_vert_grad()) return rcz;
     auto launch = [&](auto kern, size_t smem, int TP) {
       const int tiles_per_img = (int)((H * W + TP - 1) / TP);
       const int64_t num_tiles = N * (int64_t)tiles_per_img;
@@ -1054,6 +1063,7 @@ extern "C" int drtk_b200_interpolate_backward(
 
   // generic path (arbitrary strides / odd widths): one thread per pixel, segmented shuffle reduction
   if (H * W >= (int64_t)0x7FFFFFF0 || N > 65535) return DRTK_B200_EUNSUPPORTED;
+  if (const int rcz = zero_vert_grad()) return rcz;
   const dim3 blocks((unsigned)((H * W + 255) / 256), (unsigned)N);
   const bool rv4 = (C % 4 == 0) && (reinterpret_cast<uintptr_t>(vert_attributes_grad) % 16 == 0);
   if (nv && nb) {

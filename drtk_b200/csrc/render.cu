@@ -324,9 +324,16 @@ struct RunSetup {  // per-triangle constants of the backward (:186-219 of the re
 };
 
 // table row: {p0x,p0y,v01x,v01y} {v02x,v02y,rden,d0} {d1,d2,rz1,rz2} {rz0 | sign bit = den_clamped, i0,i1,i2}
-__global__ void __launch_bounds__(256) tri_table_kernel(RenderArgs a, float4* __restrict__ table) {
+// Also zero-fills the padded gradient accumulator the walker reduces into (saves a memset launch per step).
+__global__ void __launch_bounds__(256) tri_table_kernel(RenderArgs a, float4* __restrict__ table,
+                                                        float4* __restrict__ zero, int64_t zero_count) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
+  {
+    const int64_t gid = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * gridDim.y * blockDim.x;
+    for (int64_t i = gid; i < zero_count; i += nthreads) zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   if (f >= a.F) return;
   TriVerts t;
   load_tri_dense(a.vi + (int64_t)n * a.vis.s0, a.v + (int64_t)n * a.V * 3, f, t);
@@ -545,8 +552,8 @@ extern "C" int drtk_b200_render_backward(const float* v, const int64_t* v_stride
     char* ws32 = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 31) & ~uintptr_t(31));
     float4* table = reinterpret_cast<float4*>(ws32);
     float* gpad = reinterpret_cast<float*>(ws32 + tb);
-    DRTK_CUDA(cudaMemsetAsync(gpad, 0, gb, stream));
-    tri_table_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)N), 256, 0, stream>>>(b.r, table);
+    tri_table_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)N), 256, 0, stream>>>(
+        b.r, table, reinterpret_cast<float4*>(gpad), (int64_t)(gb / sizeof(float4)));
     const dim3 wgrid((unsigned)((H * W / kWalkPx + 127) / 128), (unsigned)N);
     if (grad_bary && grad_depth) render_bwd_walk_kernel<true, true><<<wgrid, 128, 0, stream>>>(b, table, gpad);
     else if (grad_bary) render_bwd_walk_kernel<true, false><<<wgrid, 128, 0, stream>>>(b, table, gpad);
