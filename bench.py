@@ -196,7 +196,37 @@ def run_reference_cpu(cfg, steps, warmup, sample_items=1):
     px = sample_items * c["H"] * c["W"]
     return {"value": px / dt / 1e6, "unit": "Mpix/s", "cores": cores, "kind": kind,
             "sample": f"{sample_items} of {c['N']} batch items of config {cfg} per step ({px / 1e6:.2f} Mpix), {steps} steps, {warmup} warm-up",
-            "ms_per_step": dt * 1e3}
+            "ms_per_step": dt * 1e3, "transform_only": cpu_transform_only(cfg)}
+
+
+def cpu_transform_only(cfg, reps=5):
+    """BASELINE's 'transform-only CPU path': the reference's `drtk.transform` is a chain of stock torch ops on the
+    [N,V,3] vertex table (drtk/transform.py:68-119 -> drtk/utils/projection.py:33-53, :536); the same chain
+    (`drtk_b200.transform.project_points_ref`, a port -- /root/reference does not exist on the GPU box) forward +
+    backward on CPU tensors of the configuration's size, all host threads torch uses."""
+    try:
+        import drtk_b200  # noqa: F401  (the package attribute `transform` is the function; the module holds the statement)
+        T = sys.modules["drtk_b200.transform"]
+        c = scenes.CONFIGS[cfg]
+        v, _ = scenes.grid_mesh(c["nx"], c["ny"], c["H"], c["W"], c["N"], seed=1000 * cfg)
+        N = v.shape[0]
+        v = (v + th.tensor([0.0, 0.0, 1.0])).requires_grad_(True)
+        cam = (th.zeros(N, 3), th.eye(3)[None].expand(N, -1, -1).contiguous(),
+               (th.eye(2) * 1000.0)[None].expand(N, -1, -1).contiguous(), th.full((N, 2), c["W"] / 2.0))
+        g = th.ones_like(v)
+
+        def once():
+            v.grad = None
+            T.project_points_ref(v, *cam)[0].backward(g)
+        once()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            once()
+        dt = (time.perf_counter() - t0) / reps
+        return {"ms_fwd_bwd": round(dt * 1e3, 3), "Mvertices_per_s": round(v.shape[0] * v.shape[1] / dt / 1e6, 2),
+                "cores": th.get_num_threads(), "kind": "port", "vertices": v.shape[0] * v.shape[1]}
+    except Exception as ex:  # noqa: BLE001
+        return {"unavailable": repr(ex)[:160]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -237,7 +267,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
                 "config": {"workload": workload, "note": "reference CPU kernels on the host cores, bounded sample"},
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "transform_only")},
                 "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -499,7 +529,7 @@ def main():
 
     if world == 1 and not args.no_cpu_baseline:
         r = run_reference_cpu(cfg, steps=3, warmup=1)
-        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "transform_only")}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
