@@ -398,3 +398,33 @@ def edge_grad_backward_fused(v_pix, img, index_img, vi, grad_output, bary_img, m
             float(max_dp_dr), _lib.ptr(out), _lib.ptr(ws), ws.numel(), _stream(v_pix.device))
     _lib.check(rc, "edge_grad_estimator() backward")
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# optional tracing: DRTK_B200_NVTX=1 wraps every launcher in an NVTX range (nsys / ncu --nvtx timelines).
+# Nothing is wrapped, and nothing costs anything, when the variable is unset.
+def _install_nvtx_ranges():
+    import functools
+    import os
+    if not os.environ.get("DRTK_B200_NVTX"):
+        return
+    names = ("rasterize", "render_forward", "render_backward", "interpolate_forward", "interpolate_backward",
+             "interpolation_matrix_forward", "interpolation_matrix_backward", "interpolation_normal_matrix_values",
+             "interpolation_normal_matrix_values_backward", "edge_grad_backward", "edge_grad_backward_fused")
+
+    def ranged(name, fn):
+        @functools.wraps(fn)
+        def wrapper(*a, **k):
+            torch.cuda.nvtx.range_push("drtk_b200." + name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return wrapper
+
+    g = globals()
+    for n in names:
+        g[n] = ranged(n, g[n])
+
+
+_install_nvtx_ranges()
