@@ -59,13 +59,13 @@ def build(ref_root: str, only=None, verbose: bool = False) -> None:
 
     os.makedirs(OUT, exist_ok=True)
     inc = os.path.join(ref_root, "src", "include")
-    for name, files in EXTS.items():
-        if only and name not in only:
-            continue
+
+    def build_one(name):
+        files = EXTS[name]
         so_final = os.path.join(OUT, f"{name}_ext.so")
         if os.path.exists(so_final):
             print(f"[build_ref] {so_final} exists, skipping")
-            continue
+            return
         t0 = time.time()
         bdir = os.path.join(OUT, "build", name)
         os.makedirs(bdir, exist_ok=True)
@@ -82,6 +82,14 @@ def build(ref_root: str, only=None, verbose: bool = False) -> None:
         )
         shutil.copy2(os.path.join(bdir, f"{name}_ext.so"), so_final)
         print(f"[build_ref] built {so_final} in {time.time() - t0:.0f}s")
+
+    # every extension has only two or three translation units, so one ninja run cannot fill the cores: the
+    # extensions are compiled side by side (each in its own build directory)
+    todo = [n for n in EXTS if not only or n in only]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(todo), 4) or 1) as pool:
+        for f in [pool.submit(build_one, n) for n in todo]:
+            f.result()
     # the intermediate objects are large and not needed on the GPU box
     shutil.rmtree(os.path.join(OUT, "build"), ignore_errors=True)
 
