@@ -40,3 +40,63 @@ def allreduce_shared_grads(grads: Iterable[Optional[th.Tensor]], group=None, asy
         outs.append(flat[off:off + x.numel()].view_as(x))
         off += x.numel()
     return outs, work
+
+
+class OverlappedSharedGradReducer:
+    """All-reduce the batch-summed gradient of each SHARED parameter as soon as autograd has finished it, instead of
+    after the whole backward: `vert_attributes.grad` is complete when interpolate's backward returns, while render's
+    and edge_grad's backward kernels (the gradient of `v_pix`) are still to run, so its exchange hides behind them.
+
+        reducer = OverlappedSharedGradReducer([v_pix, attr])       # leaves of shape [N_local, ...]
+        loss.backward()                                            # hooks fire per parameter
+        grad_v, grad_attr = reducer.finish()                       # [...] tensors, summed over batch and ranks
+
+    On CUDA the reduction is issued on a side stream (the collective orders itself after the gradient's producer
+    through an event, the caller's stream only waits in `finish()`).  Works without an initialised process group
+    (plain batch sums).  The gloo world-size-2 test covers the logic; the NCCL path has not been timed yet, so
+    `bench.py` still uses the single bucketed call of `allreduce_shared_grads`."""
+
+    def __init__(self, params: Iterable[th.Tensor], group=None):
+        self.params = list(params)
+        self.group = group
+        self._pending = {}
+        self._side = {}
+        self._handles = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
+
+    def _distributed(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _make_hook(self, i):
+        def hook(p):
+            if p.is_cuda:
+                side = self._side.setdefault(p.device, th.cuda.Stream(p.device))
+                side.wait_stream(th.cuda.current_stream(p.device))
+                with th.cuda.stream(side):
+                    local = p.grad.sum(dim=0)
+                    work = dist.all_reduce(local, op=dist.ReduceOp.SUM, group=self.group, async_op=True) if self._distributed() else None
+                p.grad.record_stream(side)
+            else:
+                local = p.grad.sum(dim=0)
+                work = dist.all_reduce(local, op=dist.ReduceOp.SUM, group=self.group, async_op=True) if self._distributed() else None
+            self._pending[i] = (local, work)
+        return hook
+
+    def finish(self) -> List[Optional[th.Tensor]]:
+        """Wait for the exchanges of this backward pass; returns the reduced gradients in parameter order (None for a
+        parameter that received no gradient)."""
+        out: List[Optional[th.Tensor]] = []
+        for i, p in enumerate(self.params):
+            local, work = self._pending.pop(i, (None, None))
+            if work is not None:
+                work.wait()  # on CUDA: the current stream waits for the collective, the host does not block
+            if local is not None and local.is_cuda:
+                cur = th.cuda.current_stream(local.device)
+                cur.wait_stream(self._side[local.device])
+                local.record_stream(cur)
+            out.append(local)
+        return out
+
+    def close(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []

@@ -25,6 +25,16 @@ def _worker(rank, world, port, n_global, V, C, out_dir):
     (gv, ga), work = ddist.allreduce_shared_grads([gv_all[b:e], ga_all[b:e]], async_op=True)
     work.wait()
     th.save((gv, ga), os.path.join(out_dir, f"r{rank}.pt"))
+    # the overlapped reducer: hooks fire as autograd finishes each parameter's gradient
+    pv = th.zeros(e - b, V, 3, requires_grad=True)
+    pa = th.zeros(e - b, V, C, requires_grad=True)
+    red = ddist.OverlappedSharedGradReducer([pv, pa])
+    for _ in range(2):  # two backward passes: the reducer is reusable
+        pv.grad = None; pa.grad = None
+        ((pv * gv_all[b:e]).sum() + (pa * ga_all[b:e]).sum() + (pv * gv_all[b:e]).sum()).backward()  # v gets two contributions
+        ov, oa = red.finish()
+    red.close()
+    th.save((ov, oa), os.path.join(out_dir, f"o{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -40,3 +50,17 @@ def test_world_size_2_shared_gradient_allreduce(tmp_path):
         gv, ga = th.load(os.path.join(str(tmp_path), f"r{r}.pt"))
         assert th.allclose(gv, gv_all.sum(0), atol=1e-5)
         assert th.allclose(ga, ga_all.sum(0), atol=1e-5)
+        ov, oa = th.load(os.path.join(str(tmp_path), f"o{r}.pt"))
+        assert th.allclose(ov, 2 * gv_all.sum(0), atol=1e-5) and th.allclose(oa, ga_all.sum(0), atol=1e-5)
+
+
+def test_overlapped_reducer_without_process_group():
+    from drtk_b200 import dist as ddist
+    p = th.zeros(3, 5, 2, requires_grad=True)
+    w = th.arange(30.0).view(3, 5, 2)
+    red = ddist.OverlappedSharedGradReducer([p])
+    (p * w).sum().backward()
+    (g,) = red.finish()
+    red.close()
+    assert th.equal(g, w.sum(0))
+    assert red.finish() == [None]
