@@ -55,7 +55,7 @@ def screen_space_uv_derivative(
         return _composed(v, vt, vi, vti, index_img, bary_img, mask, campos, camrot, focal, dist_mode, dist_coeff)
     floats = (v, vt, bary_img, campos, camrot, focal)
     needs_grad = th.is_grad_enabled() and any(t.requires_grad for t in floats)
-    if needs_grad or not v.is_cuda or any(t.dtype != th.float32 for t in floats):
+    if needs_grad or not v.is_cuda or any(t.dtype != th.float32 for t in floats) or index_img.dtype != th.int32:
         return _composed(v, vt, vi, vti, index_img, bary_img, mask, campos, camrot, focal, None, None)
     N, H, W = index_img.shape
     lib = _lib.load()
