@@ -12,6 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdrtk_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
+ABI_VERSION = 2  # DRTK_B200_ABI_VERSION of include/drtk_b200.h
+
 _lib = None
 _lock = threading.Lock()
 
@@ -45,9 +47,10 @@ PROTOTYPES = {
         _INT,
         [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _P],
     ),
+    "drtk_b200_interpolate_backward_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "drtk_b200_interpolate_backward": (
         _INT,
-        [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _P, _P],
+        [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _SZ, _P],
     ),
     "drtk_b200_edge_grad_backward": (
         _INT,
@@ -119,7 +122,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.drtk_b200_abi_version() != 1:
+        if lib.drtk_b200_abi_version() != ABI_VERSION:
             raise RuntimeError("drtk_b200: ABI version mismatch between python host and native library")
         _lib = lib
     return _lib

@@ -37,8 +37,16 @@ def autocast_f32(*tensors):
     gradients return to the original (half / bfloat16) leaves in their own dtype."""
     if not torch.is_autocast_enabled():
         return tensors
-    return tuple(t.float() if (t is not None and t.is_floating_point() and t.dtype != torch.float32) else t
-                 for t in tensors)
+    return tuple(_autocast_one(t) for t in tensors)
+
+
+_HALF_TYPES = (torch.float16, torch.bfloat16)
+
+
+def _autocast_one(t):
+    """`cached_cast(kFloat32, t)` of ATen's autocast: only reduced-precision floats are cast; float64 is not
+    eligible (aten/src/ATen/autocast_mode.h `is_eligible`: scalar_type != kDouble) and keeps the double kernels."""
+    return t.float() if (t is not None and t.dtype in _HALF_TYPES) else t
 
 
 def _real(t, who, name):
@@ -193,8 +201,7 @@ def interpolate_forward(attr, vi, index_img, bary_img):
     """-> out [N,C,H,W]; checks of src/interpolate/interpolate_kernel.cu:459-526."""
     _chk(attr.is_floating_point(), f"interpolate(): expected vert_attributes to have floating point type, but v has {attr.dtype}")
     if torch.is_autocast_enabled():
-        attr = attr.float() if attr.dtype != torch.float32 else attr
-        bary_img = bary_img.float() if bary_img.dtype != torch.float32 else bary_img
+        attr, bary_img = _autocast_one(attr), _autocast_one(bary_img)
     _check_interp(attr, vi, index_img, bary_img)
     attr = _real(attr, "interpolate", "vert_attributes")
     lib = _lib.load()
@@ -223,10 +230,15 @@ def interpolate_backward(grad_out, attr, vi, index_img, bary_img, need_attr_grad
     with torch.cuda.device(attr.device):
         ga = torch.empty((N, V, C), dtype=attr.dtype, device=attr.device) if need_attr_grad else None
         gb = torch.empty((N, 3, H, W), dtype=attr.dtype, device=attr.device) if need_bary_grad else None
-        rc = getattr(lib, "drtk_b200_interpolate_backward" + _sfx(attr))(
-            _lib.ptr(grad_out), _lib.strides(grad_out), _lib.ptr(attr), _lib.strides(attr), _lib.ptr(vi),
-            _lib.strides(vi), _lib.ptr(index_img), _lib.strides(index_img), _lib.ptr(bary_img),
-            _lib.strides(bary_img), N, V, F, C, H, W, _lib.ptr(ga), _lib.ptr(gb), _stream(attr.device))
+        common = (_lib.ptr(grad_out), _lib.strides(grad_out), _lib.ptr(attr), _lib.strides(attr), _lib.ptr(vi),
+                  _lib.strides(vi), _lib.ptr(index_img), _lib.strides(index_img), _lib.ptr(bary_img),
+                  _lib.strides(bary_img), N, V, F, C, H, W, _lib.ptr(ga), _lib.ptr(gb))
+        if attr.dtype == torch.float64:
+            rc = lib.drtk_b200_interpolate_backward_f64(*common, _stream(attr.device))
+        else:
+            nbytes = lib.drtk_b200_interpolate_backward_workspace_bytes(N, F, vi.stride(0))
+            ws = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=attr.device)
+            rc = lib.drtk_b200_interpolate_backward(*common, _lib.ptr(ws), ws.numel(), _stream(attr.device))
     _lib.check(rc, "interpolate() backward")
     return ga, gb
 

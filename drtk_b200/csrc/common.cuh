@@ -11,7 +11,12 @@
 
 namespace drtk {
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+// SM count of the CURRENT device (148 on B200: 2 dies x 74 SMs), queried once per device and cached
+// (capi.cu); sizes every persistent / one-wave grid.
+int num_sms();
+// images per launch when the batch index rides on gridDim.y / gridDim.z (limit 65535): larger batches are
+// processed in consecutive slices by the entry points (batch items are independent in every kernel)
+constexpr int64_t kMaxBatchPerLaunch = 32768;
 
 struct Strides3 { int64_t s0, s1, s2; };
 struct Strides4 { int64_t s0, s1, s2, s3; };

@@ -458,7 +458,20 @@ static int edge_launch(const float* v_pix, const int64_t* v_strides, const float
   if (npix == 0) return zero_grad_v();
   if (!v_pix || !img || !index_img || !vi || !grad_output || (!fused && !grad_v_pix_img) || (fused && !bary_img))
     return DRTK_B200_EINVAL;
-  if (H > (1 << 30) || W > (1 << 30) || N > 65535) return DRTK_B200_EUNSUPPORTED;
+  if (H > (1 << 30) || W > (1 << 30)) return DRTK_B200_EUNSUPPORTED;
+  if (N > kMaxBatchPerLaunch) {  // batch index rides on gridDim.y/z: slices of the batch (the workspace is reused)
+    for (int64_t n0 = 0; n0 < N; n0 += kMaxBatchPerLaunch) {
+      const int64_t nn = (N - n0 < kMaxBatchPerLaunch) ? N - n0 : kMaxBatchPerLaunch;
+      const int rc = edge_launch(v_pix + n0 * v_strides[0], v_strides, img + n0 * img_strides[0], img_strides,
+                                 index_img + n0 * index_strides[0], index_strides, vi + n0 * vi_strides[0], vi_strides,
+                                 grad_output + n0 * grad_output_strides[0], grad_output_strides, nn, V, F, C, H, W,
+                                 max_dp_dr, grad_v_pix_img ? grad_v_pix_img + n0 * 3 * H * W : nullptr,
+                                 bary_img ? bary_img + n0 * bary_strides[0] : nullptr, bary_strides,
+                                 grad_v_pix ? grad_v_pix + n0 * V * 3 : nullptr, workspace, workspace_bytes, stream_);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   EdgeArgs a;
   a.v = v_pix; a.vs = make3(v_strides); a.img = img; a.ims = make4(img_strides);
   a.index_img = index_img; a.is = make3(index_strides); a.vi = vi; a.vis = make3(vi_strides);
@@ -479,7 +492,7 @@ static int edge_launch(const float* v_pix, const int64_t* v_strides, const float
     const int strips_per_row = (int)((W + kStripPx - 1) / kStripPx);
     const int64_t num_strips = N * (H - 1) * strips_per_row;
     const int64_t need = (num_strips + kStripWarps - 1) / kStripWarps;
-    const int64_t cap = (int64_t)kNumSMs * 8 * 4;  // a few strips per warp: short tail, ids loads of neighbours overlap
+    const int64_t cap = (int64_t)num_sms() * 8 * 4;  // a few strips per warp: short tail, ids loads of neighbours overlap
     edge_grad_strip_kernel<<<(unsigned)(need < cap ? need : cap), kStripWarps * 32, 0, stream>>>(a, fz, table, strips_per_row,
                                                                                           num_strips);
     DRTK_CHECK_LAUNCH();

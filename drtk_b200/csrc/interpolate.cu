@@ -1088,11 +1088,19 @@ interp_bwd_merged_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* 
   }
 }
 
-inline unsigned grid_for(int64_t work_items, int threads, int ctas_per_sm) {
-  const int64_t need = (work_items + threads - 1) / threads;
-  const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
-  return (unsigned)(need < cap ? (need > 0 ? need : 1) : cap);
+// Developer switches, read ONCE per process (never on the launch path):
+//   DRTK_B200_BWD_V4=1   take the round-1 v4 tile kernel instead of the quad-walker kernel (A/B runs)
+//   DRTK_B200_MERGED=1   take the merged-walker experiment (phase B folded into the run walkers)
+struct BwdSwitches {
+  bool v4, merged;
+  BwdSwitches() : v4(getenv("DRTK_B200_BWD_V4") != nullptr), merged(getenv("DRTK_B200_MERGED") != nullptr) {}
+};
+inline const BwdSwitches& bwd_switches() {
+  static const BwdSwitches s;
+  return s;
 }
+
+inline size_t bwd_table_bytes(int64_t tab_imgs, int64_t F) { return sizeof(int4) * (size_t)(tab_imgs * F) + 32; }
 
 }  // namespace
 }  // namespace drtk
@@ -1103,7 +1111,8 @@ static int fill_args(InterpArgs& a, const float* attr, const int64_t* attr_strid
                      const int64_t* vi_strides, const int32_t* index_img, const int64_t* index_strides,
                      const float* bary_img, const int64_t* bary_strides, int64_t N, int64_t V, int64_t F,
                      int64_t C, int64_t H, int64_t W) {
-  if (!attr || !vi || !index_img || !bary_img || !attr_strides || !vi_strides || !index_strides ||
+  // an empty face list (F == 0) may come with a null vi pointer: no pixel can reference a triangle then
+  if (!attr || (!vi && F > 0) || !index_img || !bary_img || !attr_strides || !vi_strides || !index_strides ||
       !bary_strides)
     return DRTK_B200_EINVAL;
   if (H > (1 << 30) || W > (1 << 30) || N > (1 << 30) || C > (1 << 20)) return DRTK_B200_EUNSUPPORTED;
@@ -1122,6 +1131,19 @@ extern "C" int drtk_b200_interpolate_forward(const float* vert_attributes, const
   if (N < 0 || C < 0 || H < 0 || W < 0) return DRTK_B200_EINVAL;
   if (N * C * H * W == 0) return 0;
   if (!out) return DRTK_B200_EINVAL;
+  if (N > kMaxBatchPerLaunch) {  // batch index rides on gridDim.y: slices of the batch
+    if (!vert_attributes || !index_img || !bary_img || !attr_strides || !vi_strides || !index_strides || !bary_strides)
+      return DRTK_B200_EINVAL;
+    for (int64_t n0 = 0; n0 < N; n0 += kMaxBatchPerLaunch) {
+      const int64_t nn = (N - n0 < kMaxBatchPerLaunch) ? N - n0 : kMaxBatchPerLaunch;
+      const int rc = drtk_b200_interpolate_forward(
+          vert_attributes + n0 * attr_strides[0], attr_strides, vi ? vi + n0 * vi_strides[0] : nullptr, vi_strides,
+          index_img + n0 * index_strides[0], index_strides, bary_img + n0 * bary_strides[0], bary_strides, nn, V, F, C,
+          H, W, out + n0 * C * H * W, stream_);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   InterpArgs a;
   const int rc = fill_args(a, vert_attributes, attr_strides, vi, vi_strides, index_img, index_strides,
                            bary_img, bary_strides, N, V, F, C, H, W);
@@ -1131,14 +1153,14 @@ extern "C" int drtk_b200_interpolate_forward(const float* vert_attributes, const
                    VecOk::image(bary_img, W, a.bs.s3, a.bs.s2, a.bs.s1, a.bs.s0);
   const bool avec = (C % 4 == 0) && a.as.s2 == 1 && (a.as.s1 % 4 == 0) && (a.as.s0 % 4 == 0) && a.as.s1 > 0 &&
                     (V * a.as.s1 + C < (int64_t)0x7FFFFFF0) && (reinterpret_cast<uintptr_t>(vert_attributes) % 16 == 0);
-  if (H * W >= (int64_t)0x7FFFFFF0 || N > 65535) return DRTK_B200_EUNSUPPORTED;
+  if (H * W >= (int64_t)0x7FFFFFF0) return DRTK_B200_EUNSUPPORTED;
   // Grid: one wave of co-resident CTAs (grid-stride loops inside).  The CTAs of all images together must not
   // exceed what is resident at once -- 148 SMs x occupancy -- or the last, partly filled wave costs up to a
   // third of the kernel (measured at config 4: 1184 CTAs on 444 slots = 2.67 waves).
   auto launch = [&](auto kern) {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0) != cudaSuccess || occ < 1) occ = 1;
-    const int64_t slots = (int64_t)kNumSMs * occ;
+    const int64_t slots = (int64_t)num_sms() * occ;
     const int64_t need = ((vec ? H * W / 4 : H * W) + 255) / 256;
     int64_t gx = slots / N;
     if (gx < 1) gx = 1;
@@ -1153,14 +1175,33 @@ extern "C" int drtk_b200_interpolate_forward(const float* vert_attributes, const
   return 0;
 }
 
+extern "C" size_t drtk_b200_interpolate_backward_workspace_bytes(int64_t N, int64_t F, int64_t vi_batch_stride) {
+  if (N <= 0 || F <= 0) return 0;
+  return bwd_table_bytes(vi_batch_stride == 0 ? 1 : N, F);  // the packed int4 triangle table of the quad-walker path
+}
+
 extern "C" int drtk_b200_interpolate_backward(
     const float* grad_out, const int64_t* grad_out_strides, const float* vert_attributes,
     const int64_t* attr_strides, const int32_t* vi, const int64_t* vi_strides, const int32_t* index_img,
     const int64_t* index_strides, const float* bary_img, const int64_t* bary_strides, int64_t N,
     int64_t V, int64_t F, int64_t C, int64_t H, int64_t W, float* vert_attributes_grad,
-    float* bary_img_grad, void* stream_) {
+    float* bary_img_grad, void* workspace, size_t workspace_bytes, void* stream_) {
   if (N < 0 || V < 0 || C < 0 || H < 0 || W < 0) return DRTK_B200_EINVAL;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N > kMaxBatchPerLaunch) {  // batch index rides on gridDim.y in the generic kernels: slices of the batch
+    for (int64_t n0 = 0; n0 < N; n0 += kMaxBatchPerLaunch) {
+      const int64_t nn = (N - n0 < kMaxBatchPerLaunch) ? N - n0 : kMaxBatchPerLaunch;
+      const int rc = drtk_b200_interpolate_backward(
+          grad_out ? grad_out + n0 * grad_out_strides[0] : nullptr, grad_out_strides,
+          vert_attributes ? vert_attributes + n0 * attr_strides[0] : nullptr, attr_strides,
+          vi ? vi + n0 * vi_strides[0] : nullptr, vi_strides, index_img ? index_img + n0 * index_strides[0] : nullptr,
+          index_strides, bary_img ? bary_img + n0 * bary_strides[0] : nullptr, bary_strides, nn, V, F, C, H, W,
+          vert_attributes_grad ? vert_attributes_grad + n0 * V * C : nullptr,
+          bary_img_grad ? bary_img_grad + n0 * 3 * H * W : nullptr, workspace, workspace_bytes, stream_);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   // (:661) the vertex-gradient table starts at zero: vi_table_kernel does it on the quad-walker path, a memset elsewhere
   auto zero_vert_grad = [&]() -> int {
     if (vert_attributes_grad && N * V * C > 0)
@@ -1177,7 +1218,7 @@ extern "C" int drtk_b200_interpolate_backward(
   if (!grad_out || !grad_out_strides) return DRTK_B200_EINVAL;
   if (V == 0 || F == 0) {  // nothing can be covered: all gradients are zero (index_img must be all -1)
     if (bary_img_grad) DRTK_CUDA(cudaMemsetAsync(bary_img_grad, 0, sizeof(float) * (size_t)(npix * 3), stream));
-    return 0;
+    return zero_vert_grad();
   }
   InterpBwdArgs b;
   const int rc = fill_args(b.f, vert_attributes, attr_strides, vi, vi_strides, index_img, index_strides,
@@ -1205,9 +1246,10 @@ extern "C" int drtk_b200_interpolate_backward(
     const int64_t tiles_q = N * ((H * W + QTP - 1) / QTP);
     const int64_t tab_imgs = (b.f.vis.s0 == 0) ? 1 : N;
     if ((C % 4 == 0) && tiles_q < (int64_t)0x7FFFFFF0 && tab_imgs * F < (int64_t)0x0FFFFFFF &&
-        (!nv || reinterpret_cast<uintptr_t>(vert_attributes_grad) % 16 == 0) && !getenv("DRTK_B200_BWD_V4")) {
-      int4* tab = nullptr;
-      DRTK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tab), sizeof(int4) * (size_t)(tab_imgs * F), stream));
+        (!nv || reinterpret_cast<uintptr_t>(vert_attributes_grad) % 16 == 0) && !bwd_switches().v4) {
+      // the packed triangle table lives in the caller's workspace: the library never allocates
+      if (!workspace || workspace_bytes < bwd_table_bytes(tab_imgs, F)) return DRTK_B200_EWORKSPACE;
+      int4* tab = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(workspace) + 15) & ~uintptr_t(15));
       const int64_t total = tab_imgs * F;
       vi_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
           vi, b.f.vis, (int)F, total, tab, reinterpret_cast<float4*>(vert_attributes_grad), nv ? N * V * C / 4 : 0);
@@ -1219,7 +1261,7 @@ extern "C" int drtk_b200_interpolate_backward(
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { rc2 = (int)e; return; }
         const int tiles_per_img = (int)((H * W + QTP - 1) / QTP);
-        const int64_t ctas = 2 * kNumSMs;  // two co-resident CTAs per SM
+        const int64_t ctas = 2 * num_sms();  // two co-resident CTAs per SM
         const int64_t chunks = (tiles_q + kQChunk - 1) / kQChunk;
         const unsigned grid = (unsigned)(chunks < ctas ? chunks : ctas);
         kern<<<grid, 32 * (QTP / kQUnit * 2 + kQProducers), smem, stream>>>(
@@ -1233,14 +1275,13 @@ extern "C" int drtk_b200_interpolate_backward(
         else { if (avec) launch5(interp_bwd_quad_kernel<QTP, false, true, true, MULTI>);                     \
                else launch5(interp_bwd_quad_kernel<QTP, false, true, false, MULTI>); }                       \
       } while (0)
-      static const bool merged_on = getenv("DRTK_B200_MERGED") != nullptr;  // EXPERIMENT switch
-      if (merged_on && C <= kQCh && nb && avec) {
+      if (bwd_switches().merged && C <= kQCh && nb && avec) {
         auto launchm = [&](auto kern) {
           const size_t smem = sizeof(QSmem<QTP>) + 128;
           cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           if (e != cudaSuccess) { rc2 = (int)e; return; }
           const int tiles_per_img = (int)((H * W + QTP - 1) / QTP);
-          const int64_t ctas = 2 * kNumSMs;
+          const int64_t ctas = 2 * num_sms();
           const int64_t chunks = (tiles_q + kQChunk - 1) / kQChunk;
           const unsigned grid = (unsigned)(chunks < ctas ? chunks : ctas);
           kern<<<grid, 32 * (QTP / kQUnit * 2 + kQProducers), smem, stream>>>(
@@ -1249,11 +1290,8 @@ extern "C" int drtk_b200_interpolate_backward(
         if (nv) launchm(interp_bwd_merged_kernel<QTP, true>); else launchm(interp_bwd_merged_kernel<QTP, false>);
       } else if (C > kQCh) DRTK_Q5(true); else DRTK_Q5(false);
 #undef DRTK_Q5
-      cudaError_t e1 = cudaGetLastError();
-      cudaError_t e2 = cudaFreeAsync(tab, stream);
       if (rc2) return rc2;
-      if (e1 != cudaSuccess) return (int)e1;
-      if (e2 != cudaSuccess) return (int)e2;
+      DRTK_CHECK_LAUNCH();
       return 0;
     }
     if (const int rcz = zero_vert_grad()) return rcz;
@@ -1262,7 +1300,7 @@ extern "C" int drtk_b200_interpolate_backward(
       const int64_t num_tiles = N * (int64_t)tiles_per_img;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { rc2 = (int)e; return; }
-      const unsigned grid = (unsigned)(num_tiles < kNumSMs ? num_tiles : kNumSMs);  // one persistent CTA per SM
+      const unsigned grid = (unsigned)(num_tiles < num_sms() ? num_tiles : (int64_t)num_sms());  // one persistent CTA per SM
       kern<<<grid, kBwdBlock, smem, stream>>>(b, vert_attributes_grad, bary_img_grad, tiles_per_img, num_tiles);
     };
 #define DRTK_BWD_TILE(LPW)                                                                                  \
@@ -1285,7 +1323,7 @@ extern "C" int drtk_b200_interpolate_backward(
   }
 
   // generic path (arbitrary strides / odd widths): one thread per pixel, segmented shuffle reduction
-  if (H * W >= (int64_t)0x7FFFFFF0 || N > 65535) return DRTK_B200_EUNSUPPORTED;
+  if (H * W >= (int64_t)0x7FFFFFF0) return DRTK_B200_EUNSUPPORTED;
   if (const int rcz = zero_vert_grad()) return rcz;
   const dim3 blocks((unsigned)((H * W + 255) / 256), (unsigned)N);
   const bool rv4 = (C % 4 == 0) && (reinterpret_cast<uintptr_t>(vert_attributes_grad) % 16 == 0);

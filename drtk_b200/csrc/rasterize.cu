@@ -2,32 +2,64 @@
 //
 // Contract (bit-exact with the reference CUDA build): src/rasterize/rasterize_kernel.cu:42-168
 // (+ unpack :402-415, memset :484-488) of facebookresearch/DRTK.  Per (triangle, pixel)
-// sample the arithmetic below reproduces the reference's compiled sm_100 SASS
-// (--use_fast_math: FTZ, MUFU.RCP, one specific FMA contraction per expression) with
-// explicit intrinsics, so that the packed (depth_bits << 32 | triangle_id) minimum -- an
+// sample the arithmetic reproduces the reference's compiled sm_100 SASS (--use_fast_math: FTZ,
+// MUFU.RCP, one specific FMA contraction per expression; raster_core.cuh) with explicit
+// intrinsics, so that the packed (depth_bits << 32 | triangle_id) minimum -- an
 // order-independent quantity -- comes out identical however the work is organised.
 //
-// Organisation (NOT the reference's thread-per-triangle + 64-bit global atomics + memset +
-// unpack): triangles are binned to 32x32-pixel screen tiles; one CTA per tile keeps the packed
-// z-buffer of its tile in shared memory, resolves it there and writes index_img / depth_img
-// once with coalesced 128-bit stores.  Global traffic: the 8 B/px outputs plus the bin lists.
+// Organisation (NOT the reference's thread-per-triangle walk + 64-bit global atomics + memset +
+// unpack):
 //
-//   bin_count  -> scan_offsets -> bin_fill -> raster_tiles
+//   bin_count -> scan -> bin_fill -> raster_tiles
 //
-// A triangle whose clamped bounding box spans at most 2x2 tiles ("small") is appended to
-// those tiles' lists (<= 4 entries, so the list storage is bounded by 4*N*F and the call needs
-// no device->host sync to size anything).  Everything else ("large") goes to one per-image
-// list that every tile of that image walks cooperatively (all threads of the CTA split the
-// pixels of the clipped bounding box).
+// * The triangle SETUP runs once per triangle, in bin_fill: vertex gathers, culling rules, canonical
+//   edges, 1/|den|, 1/z_k, bounding box.  The result is an 80-byte RECORD which bin_fill appends to the
+//   list of every 32x32-pixel tile the bounding box touches (at most 2x2 tiles = "small"; list storage is
+//   bounded by 4*N*F records, so nothing is sized by a device->host sync).  A tile's records are
+//   CONTIGUOUS, so the tile CTA stages them with ONE bulk-async copy (cp.async.bulk -> SASS UBLKCP)
+//   completing on an mbarrier.
+// * Triangles whose box spans more than 2x2 tiles ("large") go to one compact per-image list of
+//   bounding boxes; every tile CTA scans that list with all its threads (16 B per entry) and builds the
+//   records of the few entries that touch it.
+// * raster_tiles, one CTA per tile, two phases per pass of <= 248 records:
+//     phase 1  work item = one image row of one triangle (block-balanced).  The covered pixels of a
+//              (triangle, row) are ONE interval whose ends are solved exactly (raster_core.cuh:
+//              row_span_exact, ~one evaluation of the true edge function per edge instead of one test
+//              per sample).  Each covered pixel records the triangle's slot in a per-pixel owner word
+//              (four slot bytes, 32-bit shared-memory CAS): no depth is computed here.
+//     phase 2  work item = pixel.  Every pixel shades its <= 4 owners (depth as the reference computes
+//              it) and keeps the minimum key in a register: all lanes busy, no 64-bit atomics.
+//              A pixel covered by more than four triangles of one pass (rare) shades the surplus in
+//              phase 1 with a 64-bit shared-memory atomicMin, merged at the end.
+//   Finally each thread writes index_img / depth_img for four adjacent pixels with 128-bit stores.
+//   No global atomics, no memset of the images, no unpack pass.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "raster_core.cuh"
+#include "tma.cuh"
 
 namespace drtk {
+// round-1 tile rasteriser (rasterize_v1.cu), selectable with DRTK_B200_RASTER_V1=1 for A/B runs
+size_t rasterize_v1_workspace_bytes(int64_t N, int64_t F, int64_t H, int64_t W);
+int rasterize_v1(const float* v, const int64_t* v_strides, const int32_t* vi, const int64_t* vi_strides, int64_t N,
+                 int64_t V, int64_t F, int64_t H, int64_t W, float* depth_img, int32_t* index_img, void* workspace,
+                 cudaStream_t stream);
 namespace {
+
+inline bool use_v1() {
+  static const bool on = getenv("DRTK_B200_RASTER_V1") != nullptr;  // read once per process
+  return on;
+}
 
 constexpr int kTileLog = 5;
 constexpr int kTile = 1 << kTileLog;        // 32 x 32 pixels
 constexpr int kTilePix = kTile * kTile;     // 1024
-constexpr int kRasterThreads = 128;
+constexpr int kRasterThreads = 256;
+constexpr int kPassRecs = 248;              // records per pass: slot ids are bytes, 0xFF = "no owner"
+constexpr int kRecF4 = 5;                   // a record is 5 x 16 B
+constexpr uint32_t kOwnEmpty = 0xFFFFFFFFu;
+constexpr int kLargeBlock = 128;            // large-list entries examined per round of a tile CTA
 
 struct RasterArgs {
   const float* v;
@@ -38,35 +70,17 @@ struct RasterArgs {
   int tilesX, tilesY;
 };
 
-// Everything a sample test needs, derived once per triangle.
-struct TriSetup {
-  // canonical edges k = 0,1,2  <->  (v1,v2), (v2,v0), (v0,v1); origin o = endpoint with the lower
-  // vertex index (src/rasterize/rasterize_kernel.cu:29-40).  (ax, ay) is the edge direction times
-  // s = sign(den) * (swapped ? -1 : 1): b_k = s * fma(-ab.y, p.x-o.x, rn((p.y-o.y)*ab.x)) equals
-  // fma(-ay, p.x-o.x, rn((p.y-o.y)*ax)) bit for bit (round-to-nearest is sign symmetric), which
-  // saves the three multiplications by +-1 per sample.
-  float ox[3], oy[3], ax[3], ay[3];
+// Everything a sample needs, derived once per triangle.
+struct TriFull {
+  EdgeSetup e;
   float d0, d1, d2;  // MUFU.RCP(epsclamp(z_k))
   float rden;        // MUFU.RCP(|den|)
-  bool tl[3];
   int bx0, by0, bx1, by1;  // clamped pixel bounding box (inclusive); may be empty
 };
 
-__device__ __forceinline__ void canon_edge_setup(int ia, int ib, float pax, float pay, float pbx,
-                                                 float pby, float sgn, float& ox, float& oy,
-                                                 float& ax, float& ay) {
-  if (ia <= ib) {
-    ox = pax; oy = pay;
-    ax = mul_rn(sub_rn(pbx, pax), sgn); ay = mul_rn(sub_rn(pby, pay), sgn);
-  } else {
-    ox = pbx; oy = pby;
-    ax = mul_rn(sub_rn(pax, pbx), -sgn); ay = mul_rn(sub_rn(pay, pby), -sgn);
-  }
-}
-
 // Loads triangle f of image n, applies the reference's rejection rules (:81, :96-100, :107) and
 // fills the setup.  Returns false when the triangle produces no samples.
-__device__ __forceinline__ bool tri_setup(const RasterArgs& a, int n, int f, TriSetup& s) {
+__device__ __forceinline__ bool tri_full(const RasterArgs& a, int n, int f, TriFull& s) {
   const int32_t* vip = a.vi + (int64_t)n * a.vis.s0 + (int64_t)f * a.vis.s1;
   const int i0 = (int)(((uint32_t)vip[0]) & 0x0FFFFFFFu);  // top nibble reserved (:74)
   const int i1 = vip[a.vis.s2];
@@ -87,11 +101,8 @@ __device__ __forceinline__ bool tri_setup(const RasterArgs& a, int n, int f, Tri
   if (!(mnx <= (float)(a.W - 1) && mny <= (float)(a.H - 1) && mxx > 0.f && mxy > 0.f))
     return false;  // (:97-98)
 
-  const float v01x = sub_rn(p1x, p0x), v01y = sub_rn(p1y, p0y);
-  const float v02x = sub_rn(p2x, p0x), v02y = sub_rn(p2y, p0y);
-  const float v12x = sub_rn(p2x, p1x), v12y = sub_rn(p2y, p1y);
-  const float den = diff_of_products(v01x, v02y, v01y, v02x);  // (:105) FMUL + FFMA as compiled
-  if (den == 0.f) return false;                                   // (:107)
+  edge_setup(i0, i1, i2, p0x, p0y, p1x, p1y, p2x, p2y, s.e);
+  if (s.e.den == 0.f) return false;  // (:107)
 
   // bounding box with the reference's truncation and +1 border (:109-113)
   s.bx0 = max(0, __float2int_rz(mnx));
@@ -99,91 +110,73 @@ __device__ __forceinline__ bool tri_setup(const RasterArgs& a, int n, int f, Tri
   s.bx1 = min(a.W - 1, (int)((unsigned)__float2int_rz(mxx) + 1u));
   s.by1 = min(a.H - 1, (int)((unsigned)__float2int_rz(mxy) + 1u));
 
-  const float sgn = den > 0.f ? 1.f : -1.f;  // sign(den), den != 0 (:125)
-  canon_edge_setup(i1, i2, p1x, p1y, p2x, p2y, sgn, s.ox[0], s.oy[0], s.ax[0], s.ay[0]);
-  canon_edge_setup(i2, i0, p2x, p2y, p0x, p0y, sgn, s.ox[1], s.oy[1], s.ax[1], s.ay[1]);
-  canon_edge_setup(i0, i1, p0x, p0y, p1x, p1y, sgn, s.ox[2], s.oy[2], s.ax[2], s.ay[2]);
-
-  if (den > 0.f) {  // top-left classification (:133-141)
-    s.tl[0] = (v12y < 0.f) || (v12y == 0.f && v12x > 0.f);
-    s.tl[1] = (v02y > 0.f) || (v02y == 0.f && v02x < 0.f);
-    s.tl[2] = (v01y < 0.f) || (v01y == 0.f && v01x > 0.f);
-  } else {
-    s.tl[0] = (v12y > 0.f) || (v12y == 0.f && v12x < 0.f);
-    s.tl[1] = (v02y < 0.f) || (v02y == 0.f && v02x > 0.f);
-    s.tl[2] = (v01y > 0.f) || (v01y == 0.f && v01x < 0.f);
-  }
-  s.rden = rcp_approx(fabsf(den));  // (:148) under fast-math: bary * MUFU.RCP(|den|)
-  s.d0 = rcp_approx(epsclamp(z0));  // (:151)
+  s.rden = rcp_approx(fabsf(s.e.den));  // (:148) under fast-math: bary * MUFU.RCP(|den|)
+  s.d0 = rcp_approx(epsclamp(z0));      // (:151)
   s.d1 = rcp_approx(epsclamp(z1));
   s.d2 = rcp_approx(epsclamp(z2));
   return true;
 }
 
-// One (triangle, pixel) sample.  Returns true and the depth bits when the pixel centre (x, y)
-// is covered under the top-left rule (:118-153).  row[k] = rn((p.y - o_k.y) * ax_k) is per row (the
-// reference compiler hoists the same product; same value either way).
-__device__ __forceinline__ bool sample(const float (&ox)[3], const float (&ay)[3], const bool (&tl)[3],
-                                       float rden, float d0, float d1, float d2, float px,
-                                       const float (&row)[3], uint32_t& depth_bits) {
-  const float b0 = fma_rn(-ay[0], sub_rn(px, ox[0]), row[0]);
-  const float b1 = fma_rn(-ay[1], sub_rn(px, ox[1]), row[1]);
-  const float b2 = fma_rn(-ay[2], sub_rn(px, ox[2]), row[2]);
-  if (!(b0 >= 0.f && b1 >= 0.f && b2 >= 0.f)) return false;
-  // top-left rule: only reached by samples exactly on an edge (one min3 + compare guards the three
-  // equality tests; all b are >= 0 and not NaN here, so min == 0 <=> some b == 0)
-  if (fminf(fminf(b0, b1), b2) == 0.f) {
-    if ((b0 == 0.f && !tl[0]) || (b1 == 0.f && !tl[1]) || (b2 == 0.f && !tl[2])) return false;
-  }
+// depth bits of a COVERED sample (:148-153): c_k = b_k * RCP(|den|); inv = FFMA(c2,d2, FFMA(c0,d0, FMUL(c1,d1)));
+// depth = MUFU.RCP(epsclamp(inv))
+__device__ __forceinline__ uint32_t depth_bits_of(float b0, float b1, float b2, float rden, float d0, float d1,
+                                                  float d2) {
   const float c0 = mul_rn(b0, rden), c1 = mul_rn(b1, rden), c2 = mul_rn(b2, rden);
-  // dot(d_inv, bary) as compiled: FMUL(b1,d1) -> FFMA(b0,d0,.) -> FFMA(b2,d2,.)
   const float inv = fma_rn(c2, d2, fma_rn(c0, d0, mul_rn(c1, d1)));
-  depth_bits = __float_as_uint(rcp_approx(epsclamp(inv)));
+  return __float_as_uint(rcp_approx(epsclamp(inv)));
+}
+
+// One (triangle, pixel) sample of the validation / wide-coordinate paths: coverage test + depth.
+__device__ __forceinline__ bool sample(const TriFull& s, float px, const float (&row)[3], uint32_t& depth_bits) {
+  if (!sample_covered(s.e.ox, s.e.ay, row, s.e.tl_bits, px)) return false;
+  depth_bits = depth_bits_of(edge_value(s.e.ay[0], s.e.ox[0], row[0], px), edge_value(s.e.ay[1], s.e.ox[1], row[1], px),
+                             edge_value(s.e.ay[2], s.e.ox[2], row[2], px), s.rden, s.d0, s.d1, s.d2);
   return true;
 }
-__device__ __forceinline__ bool sample(const TriSetup& s, float px, const float (&row)[3],
-                                       uint32_t& depth_bits) {
-  return sample(s.ox, s.ay, s.tl, s.rden, s.d0, s.d1, s.d2, px, row, depth_bits);
-}
 
-__device__ __forceinline__ void row_terms(const TriSetup& s, float py, float (&row)[3]) {
-  row[0] = mul_rn(sub_rn(py, s.oy[0]), s.ax[0]);
-  row[1] = mul_rn(sub_rn(py, s.oy[1]), s.ax[1]);
-  row[2] = mul_rn(sub_rn(py, s.oy[2]), s.ax[2]);
-}
-
-// Conservative x-range of one image row: pixels outside [xs, xe] cannot pass the edge tests.
-// Edge k crosses zero at x* = o.x + row/ay; samples within one pixel of x* are always kept, which
-// covers the rounding of the exact test (<= 2^-23 (|dy| |ax/ay| + |dx|) px) as long as the edge is
-// not nearly horizontal and the coordinates are moderate; otherwise the edge does not prune.
-__device__ __forceinline__ void row_span(const float (&ox)[3], const float (&ax)[3], const float (&ay)[3],
-                                         const float (&row)[3], float dy_max, int& xs, int& xe) {
+__device__ __forceinline__ void row_terms(const TriFull& s, float py, float (&row)[3]) {
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const float aay = fabsf(ay[k]);
-    if (aay * 1048576.f >= fabsf(ax[k]) * dy_max && fabsf(ox[k]) < 1048576.f) {  // (false for ay == 0, NaN)
-      const float xstar = fma_rn(row[k], rcp_approx(ay[k]), ox[k]);
-      if (fabsf(xstar) < 1.0e9f) {
-        if (ay[k] < 0.f) xs = max(xs, __float2int_rd(xstar) - 1);  // b grows with x: x >= x*
-        else xe = min(xe, __float2int_ru(xstar) + 1);              // b falls with x: x <= x*
-      }
-    }
-  }
+  for (int k = 0; k < 3; ++k) row[k] = edge_row_term(py, s.e.oy[k], s.e.ax[k]);
+}
+
+// ------------------------------------------------------------------------------------------
+// records
+// ------------------------------------------------------------------------------------------
+// float4 0..2: (ox_k, oy_k, ax_k, ay_k)   3: (d0, d1, d2, rden)   4: (triangle id, meta, 0, 0) as ints
+// meta (raster_core.cuh): top/left bits, bounding box clipped to the tile and relative to it, WILD flag
+__device__ __forceinline__ int record_meta(const TriFull& s, int x_lo, int y_lo, int x_hi, int y_hi, int W) {
+  const int bx0 = max(s.bx0, x_lo) - x_lo, bx1 = min(s.bx1, x_hi) - x_lo;
+  const int by0 = max(s.by0, y_lo) - y_lo, by1 = min(s.by1, y_hi) - y_lo;
+  const bool tame = fabsf(s.e.ox[0]) < kSpanCoordMax && fabsf(s.e.ox[1]) < kSpanCoordMax &&
+                    fabsf(s.e.ox[2]) < kSpanCoordMax && W <= (int)kSpanCoordMax;  // false for NaN
+  return (int)s.e.tl_bits | (bx0 << RASTER_META_BX0) | (bx1 << RASTER_META_BX1) | (by0 << RASTER_META_BY0) |
+         (by1 << RASTER_META_BY1) | (tame ? 0 : RASTER_META_WILD);
+}
+
+template <class Store>  // Store(int q, float4 value)
+__device__ __forceinline__ void write_record(const TriFull& s, int f, int meta, Store&& st) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) st(k, make_float4(s.e.ox[k], s.e.oy[k], s.e.ax[k], s.e.ay[k]));
+  st(3, make_float4(s.d0, s.d1, s.d2, s.rden));
+  st(4, make_float4(__int_as_float(f), __int_as_float(meta), 0.f, 0.f));
 }
 
 // ------------------------------------------------------------------------------------------
 // binning
 // ------------------------------------------------------------------------------------------
+// FILL = false: count the list entries of every tile.  FILL = true: append the records (small triangles) and the
+// bounding boxes (large triangles).  Both passes take the same decisions from the same arithmetic.
 template <bool FILL>
 __global__ void __launch_bounds__(256) bin_kernel(RasterArgs a, int64_t total, uint32_t* tile_count,
-                                                  const uint32_t* tile_offset, uint32_t* tile_list,
-                                                  uint32_t* large_count, uint32_t* large_list) {
+                                                  const uint32_t* __restrict__ tile_offset, float4* __restrict__ recs,
+                                                  uint32_t* large_count, uint32_t* __restrict__ large_id,
+                                                  int4* __restrict__ large_bbox) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int n = (int)(idx / a.F);
   const int f = (int)(idx - (int64_t)n * a.F);
-  TriSetup s;
-  if (!tri_setup(a, n, f, s)) return;
+  TriFull s;
+  if (!tri_full(a, n, f, s)) return;
   if (s.bx0 > s.bx1 || s.by0 > s.by1) return;
   const int tx0 = s.bx0 >> kTileLog, tx1 = s.bx1 >> kTileLog;
   const int ty0 = s.by0 >> kTileLog, ty1 = s.by1 >> kTileLog;
@@ -193,11 +186,17 @@ __global__ void __launch_bounds__(256) bin_kernel(RasterArgs a, int64_t total, u
       for (int tx = tx0; tx <= tx1; ++tx) {
         const int64_t t = tbase + (int64_t)ty * a.tilesX + tx;
         const uint32_t k = atomicAdd(&tile_count[t], 1u);
-        if (FILL) tile_list[tile_offset[t] + k] = (uint32_t)f;
+        if (FILL) {
+          const int x_lo = tx << kTileLog, y_lo = ty << kTileLog;
+          const int meta = record_meta(s, x_lo, y_lo, min(x_lo + kTile - 1, a.W - 1), min(y_lo + kTile - 1, a.H - 1), a.W);
+          float4* dst = recs + (size_t)(tile_offset[t] + k) * kRecF4;
+          write_record(s, f, meta, [&](int q, float4 val) { dst[q] = val; });
+        }
       }
   } else if (FILL) {
     const uint32_t k = atomicAdd(&large_count[n], 1u);
-    large_list[(int64_t)n * a.F + k] = (uint32_t)f;
+    large_id[(int64_t)n * a.F + k] = (uint32_t)f;
+    large_bbox[(int64_t)n * a.F + k] = make_int4(s.bx0, s.by0, s.bx1, s.by1);
   }
 }
 
@@ -263,177 +262,228 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* count, uint32_t* o
 // ------------------------------------------------------------------------------------------
 // per-tile resolve
 // ------------------------------------------------------------------------------------------
-// Shared-memory records of the triangles of one pass (structure of arrays, one slot per thread).
-struct TileRecs {
-  float ox[3][kRasterThreads], oy[3][kRasterThreads], ax[3][kRasterThreads], ay[3][kRasterThreads];
-  float d[3][kRasterThreads], rden[kRasterThreads];
-  int meta[kRasterThreads];  // tl bits 0-2 | bx0 << 3 | bx1 << 8 | by0 << 13   (tile-local 0..31)
-  int tri[kRasterThreads];
-  int prefix[kRasterThreads + 1];  // exclusive scan of the per-triangle row counts
+struct __align__(16) TileSmem {
+  float4 rec[kPassRecs * kRecF4];          // 19 840 B: the records of this pass (bulk-async copy / built in place)
+  unsigned long long zbuf[kTilePix];       //  8 192 B: packed minimum of the deep-overlap path (5th+ owner of a pixel)
+  uint32_t own[kTilePix];                  //  4 096 B: four owner slots per pixel, 0xFF = free
+  uint8_t rowmap[kPassRecs * kTile];       //  7 936 B: row item -> record slot
+  int prefix[kPassRecs + 1];               // exclusive scan of the per-record row counts
+  int warp_tot[kRasterThreads / 32];
+  uint32_t mlist[kPassRecs];               // large triangles that touch this tile (ids), current round
+  int nmatch;
+  unsigned long long bar;                  // mbarrier of the record copy
 };
 
-__global__ void __launch_bounds__(kRasterThreads) raster_tiles_kernel(
-    RasterArgs a, const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_offset,
-    const uint32_t* __restrict__ tile_list, const uint32_t* __restrict__ large_count,
-    const uint32_t* __restrict__ large_list, float* __restrict__ depth_img,
-    int32_t* __restrict__ index_img) {
-  __shared__ unsigned long long zbuf[kTilePix];
-  __shared__ TileRecs R;
-  __shared__ __align__(16) int warp_tot[kRasterThreads / 32];  // aligned: its vector load must not straddle R.prefix
+// key of one owner at pixel (px, py): depth exactly as the reference computes it for a covered sample
+__device__ __forceinline__ unsigned long long shade_key(const float4* __restrict__ rec, float px, float py) {
+  const float4 e0 = rec[0], e1 = rec[1], e2 = rec[2], z = rec[3];
+  const uint32_t id = __float_as_uint(rec[4].x);
+  const float b0 = edge_value(e0.w, e0.x, edge_row_term(py, e0.y, e0.z), px);
+  const float b1 = edge_value(e1.w, e1.x, edge_row_term(py, e1.y, e1.z), px);
+  const float b2 = edge_value(e2.w, e2.x, edge_row_term(py, e2.y, e2.z), px);
+  return ((unsigned long long)depth_bits_of(b0, b1, b2, z.w, z.x, z.y, z.z) << 32) | id;
+}
+
+// Register `slot` as an owner of pixel p.  First owner: one CAS against "all free".  Bytes fill from the low end.
+__device__ __forceinline__ void claim_pixel(TileSmem& S, int p, uint32_t slot, float px, float py) {
+  uint32_t old = atomicCAS(&S.own[p], kOwnEmpty, 0xFFFFFF00u | slot);
+  while (old != kOwnEmpty) {
+    if ((old >> 24) != 0xFFu) {  // four owners already: shade here, 64-bit minimum (rare)
+      atomicMin(&S.zbuf[p], shade_key(S.rec + slot * kRecF4, px, py));
+      return;
+    }
+    const int sh = ((old >> 8) & 0xFFu) == 0xFFu ? 8 : (((old >> 16) & 0xFFu) == 0xFFu ? 16 : 24);
+    const uint32_t want = (old & ~(0xFFu << sh)) | (slot << sh);
+    const uint32_t prev = atomicCAS(&S.own[p], old, want);
+    if (prev == old) return;
+    old = prev;
+  }
+}
+
+// One pass over the m records in S.rec (m <= kPassRecs).  Entered and left by all threads of the CTA.
+__device__ __forceinline__ void tile_pass(TileSmem& S, int m, int x_lo, int y_lo, unsigned long long (&best)[4]) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // ---- A. row items: exclusive block scan of the row counts, row item -> slot map ----
+  int rows = 0, my_by0 = 0;
+  if (tid < m) {
+    const int meta = __float_as_int(S.rec[tid * kRecF4 + 4].y);
+    my_by0 = (meta >> RASTER_META_BY0) & 31;
+    rows = max(0, ((meta >> RASTER_META_BY1) & 31) - my_by0 + 1);
+  }
+  int inc = rows;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) S.warp_tot[wid] = inc;
+  __syncthreads();
+  int woff = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kRasterThreads / 32; ++w) {
+    const int t = S.warp_tot[w];
+    woff += (w < wid) ? t : 0;
+    total += t;
+  }
+  const int excl = woff + inc - rows;
+  if (tid < m) {
+    S.prefix[tid] = excl;
+    for (int r = 0; r < rows; ++r) S.rowmap[excl + r] = (uint8_t)tid;
+  }
+  __syncthreads();
+
+  // ---- B. phase 1: one (triangle, row) per thread: exact span, owners ----
+  for (int item = tid; item < total; item += kRasterThreads) {
+    const int slot = S.rowmap[item];
+    const float4* rec = S.rec + slot * kRecF4;
+    const float4 e0 = rec[0], e1 = rec[1], e2 = rec[2];
+    const int meta = __float_as_int(rec[4].y);
+    const int ly = ((meta >> RASTER_META_BY0) & 31) + (item - S.prefix[slot]);
+    const float py = (float)(y_lo + ly);
+    const float ox[3] = {e0.x, e1.x, e2.x}, ay[3] = {e0.w, e1.w, e2.w};
+    const float row[3] = {edge_row_term(py, e0.y, e0.z), edge_row_term(py, e1.y, e1.z), edge_row_term(py, e2.y, e2.z)};
+    const unsigned tl = (unsigned)meta & RASTER_META_TL_MASK;
+    const int xs0 = x_lo + ((meta >> RASTER_META_BX0) & 31), xe0 = x_lo + ((meta >> RASTER_META_BX1) & 31);
+    int xs = xs0, xe = xe0;
+    const bool wild = (meta & RASTER_META_WILD) != 0;
+    if (!wild) row_span_exact(ox, ay, row, tl, xs0, xe0, xs, xe);
+    const int pbase = (ly << kTileLog) - x_lo;
+    for (int x = xs; x <= xe; ++x) {
+      if (wild && !sample_covered(ox, ay, row, tl, (float)x)) continue;
+      claim_pixel(S, pbase + x, (uint32_t)slot, (float)x, py);
+    }
+  }
+  __syncthreads();
+
+  // ---- C. phase 2: one pixel quad per thread: shade the owners, keep the minimum ----
+  {
+    const int p4 = tid * 4;
+    const int ly = p4 >> kTileLog, lx = p4 & (kTile - 1);
+    const uint4 w4 = *reinterpret_cast<const uint4*>(&S.own[p4]);
+    if ((w4.x & w4.y & w4.z & w4.w) != kOwnEmpty) {
+      *reinterpret_cast<uint4*>(&S.own[p4]) = make_uint4(kOwnEmpty, kOwnEmpty, kOwnEmpty, kOwnEmpty);  // for the next pass
+      const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+      const float py = (float)(y_lo + ly);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t w = ws[j];
+        const float px = (float)(x_lo + lx + j);
+        while ((w & 0xFFu) != 0xFFu) {
+          const unsigned long long key = shade_key(S.rec + (w & 0xFFu) * kRecF4, px, py);
+          best[j] = key < best[j] ? key : best[j];
+          w = (w >> 8) | 0xFF000000u;
+        }
+      }
+    }
+  }
+  __syncthreads();  // S.rec may be overwritten now
+}
+
+__global__ void __launch_bounds__(kRasterThreads, 4) raster_tiles_kernel(
+    RasterArgs a, const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_offset,
+    const float4* __restrict__ recs, const uint32_t* __restrict__ large_count, const uint32_t* __restrict__ large_id,
+    const int4* __restrict__ large_bbox, float* __restrict__ depth_img, int32_t* __restrict__ index_img) {
+  __shared__ TileSmem S;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = blockIdx.z;
   const int64_t t = ((int64_t)n * a.tilesY + tile_y) * a.tilesX + tile_x;
   const int x_lo = tile_x << kTileLog, y_lo = tile_y << kTileLog;
   const int x_hi = min(x_lo + kTile - 1, a.W - 1), y_hi = min(y_lo + kTile - 1, a.H - 1);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(&S.bar);
 
-  for (int i = tid; i < kTilePix; i += kRasterThreads) zbuf[i] = ~0ull;  // (:484-488)
-
-  // (1) small triangles.  Work item = one image row of one triangle's clipped bounding box, so the
-  // threads of a warp do equally sized pieces of work whatever the triangle sizes are.
-  const uint32_t cnt = tile_count[t];
-  const uint32_t* list = tile_list + tile_offset[t];
-  for (uint32_t base = 0; base < cnt; base += kRasterThreads) {
-    __syncthreads();  // zbuf initialised / previous pass done with the records
-    int rows = 0;
-    if (base + tid < cnt) {
-      const int f = (int)list[base + tid];
-      TriSetup s;
-      if (tri_setup(a, n, f, s)) {
-        const int bx0 = max(s.bx0, x_lo), bx1 = min(s.bx1, x_hi);
-        const int by0 = max(s.by0, y_lo), by1 = min(s.by1, y_hi);
-        if (bx0 <= bx1 && by0 <= by1) {
-          rows = by1 - by0 + 1;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            R.ox[k][tid] = s.ox[k]; R.oy[k][tid] = s.oy[k]; R.ax[k][tid] = s.ax[k]; R.ay[k][tid] = s.ay[k];
-          }
-          R.d[0][tid] = s.d0; R.d[1][tid] = s.d1; R.d[2][tid] = s.d2; R.rden[tid] = s.rden;
-          R.meta[tid] = (s.tl[0] ? 1 : 0) | (s.tl[1] ? 2 : 0) | (s.tl[2] ? 4 : 0) | ((bx0 - x_lo) << 3) |
-                        ((bx1 - x_lo) << 8) | ((by0 - y_lo) << 13);
-          R.tri[tid] = f;
-        }
-      }
-    }
-    // block-wide exclusive scan of `rows`
-    int inc = rows;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += v;
-    }
-    if (lane == 31) warp_tot[wid] = inc;
-    __syncthreads();
-    int woff = 0;
-#pragma unroll
-    for (int w = 0; w < kRasterThreads / 32; ++w) woff += (w < wid) ? warp_tot[w] : 0;
-    R.prefix[tid] = woff + inc - rows;
-    if (tid == kRasterThreads - 1) R.prefix[kRasterThreads] = woff + inc;
-    __syncthreads();
-    const int total = R.prefix[kRasterThreads];
-
-    for (int item = tid; item < total; item += kRasterThreads) {
-      // owner = largest slot with prefix[slot] <= item (slots with zero rows are skipped naturally)
-      int lo = 0, hi = kRasterThreads;
-#pragma unroll
-      for (int it = 0; it < 7; ++it) {  // log2(128)
-        const int mid = (lo + hi) >> 1;
-        if (R.prefix[mid] <= item) lo = mid; else hi = mid;
-      }
-      const int sl = lo;
-      const int meta = R.meta[sl];
-      const int ly = ((meta >> 13) & 31) + (item - R.prefix[sl]);
-      int xs = (meta >> 3) & 31, xe = (meta >> 8) & 31;
-      const float ox[3] = {R.ox[0][sl], R.ox[1][sl], R.ox[2][sl]};
-      const float ax[3] = {R.ax[0][sl], R.ax[1][sl], R.ax[2][sl]};
-      const float ay[3] = {R.ay[0][sl], R.ay[1][sl], R.ay[2][sl]};
-      const bool tl[3] = {(meta & 1) != 0, (meta & 2) != 0, (meta & 4) != 0};
-      const float py = (float)(y_lo + ly);
-      float row[3], dy_max = 1.f;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float dy = sub_rn(py, R.oy[k][sl]);
-        row[k] = mul_rn(dy, ax[k]);
-        dy_max = fmaxf(dy_max, fabsf(dy));
-      }
-      int gxs = x_lo + xs, gxe = x_lo + xe;
-      row_span(ox, ax, ay, row, dy_max, gxs, gxe);
-      if (gxs > gxe) continue;
-      const float rden = R.rden[sl], d0 = R.d[0][sl], d1 = R.d[1][sl], d2 = R.d[2][sl];
-      const unsigned long long f = (unsigned long long)(uint32_t)R.tri[sl];
-      unsigned long long* zrow = zbuf + (ly << kTileLog) - x_lo;
-      for (int x = gxs; x <= gxe; ++x) {
-        uint32_t db;
-        if (sample(ox, ay, tl, rden, d0, d1, d2, (float)x, row, db)) {
-          // (:155-161) packed minimum.  The first write to a pixel is by far the common case: one native
-          // compare-and-swap against "empty" settles it without the load + compare + CAS loop that a 64-bit
-          // shared-memory atomicMin compiles to; only a pixel that is already taken pays for the loop.
-          const unsigned long long key = ((unsigned long long)db << 32) | f;
-          const unsigned long long old = atomicCAS(zrow + x, ~0ull, key);
-          if (old != ~0ull && key < old) atomicMin(zrow + x, key);
-        }
-      }
+  const uint32_t cnt = a.F > 0 ? tile_count[t] : 0u;  // after bin_kernel<true>: entries of this tile
+  const uint32_t off = a.F > 0 ? tile_offset[t] : 0u;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    S.nmatch = 0;
+    if (cnt) {  // first pass in flight while the CTA initialises its pixel state
+      const uint32_t bytes = min(cnt, (uint32_t)kPassRecs) * (uint32_t)(kRecF4 * 16);
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_g2s(S.rec, recs + (size_t)off * kRecF4, bytes, bar);
     }
   }
-  __syncthreads();
+  *reinterpret_cast<uint4*>(&S.own[tid * 4]) = make_uint4(kOwnEmpty, kOwnEmpty, kOwnEmpty, kOwnEmpty);
+  *reinterpret_cast<ulonglong2*>(&S.zbuf[tid * 4]) = make_ulonglong2(~0ull, ~0ull);
+  *reinterpret_cast<ulonglong2*>(&S.zbuf[tid * 4 + 2]) = make_ulonglong2(~0ull, ~0ull);
+  unsigned long long best[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+  __syncthreads();  // barrier initialised, pixel state initialised
 
-  // (2) large triangles of this image: whole CTA cooperates on each one
-  const uint32_t nlarge = large_count[n];
-  const uint32_t* llist = large_list + (int64_t)n * a.F;
-  for (uint32_t j = 0; j < nlarge; ++j) {
-    const int f = (int)llist[j];
-    TriSetup s;
-    if (!tri_setup(a, n, f, s)) continue;  // uniform across the CTA
-    const int bx0 = max(s.bx0, x_lo), bx1 = min(s.bx1, x_hi);
-    const int by0 = max(s.by0, y_lo), by1 = min(s.by1, y_hi);
-    if (bx0 > bx1 || by0 > by1) continue;
-    const int bw = bx1 - bx0 + 1, npx = bw * (by1 - by0 + 1);
-    for (int p = tid; p < npx; p += kRasterThreads) {
-      const int yy = p / bw, xx = p - yy * bw;
-      const int x = bx0 + xx, y = by0 + yy;
-      float row[3];
-      row_terms(s, (float)y, row);
-      uint32_t db;
-      if (sample(s, (float)x, row, db)) {
-        const unsigned long long packed = ((unsigned long long)db << 32) | (uint32_t)f;
-        atomicMin(&zbuf[((y - y_lo) << kTileLog) + (x - x_lo)], packed);
+  // (1) small triangles: the tile's own record list, kPassRecs at a time
+  uint32_t parity = 0;
+  for (uint32_t base = 0; base < cnt; base += kPassRecs) {
+    const int m = (int)min(cnt - base, (uint32_t)kPassRecs);
+    if (base && tid == 0) {  // later passes (tiles with more than kPassRecs triangles)
+      fence_proxy_async_smem();
+      mbar_arrive_expect_tx(bar, (uint32_t)m * (kRecF4 * 16));
+      bulk_g2s(S.rec, recs + (size_t)(off + base) * kRecF4, (uint32_t)m * (kRecF4 * 16), bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    tile_pass(S, m, x_lo, y_lo, best);
+  }
+
+  // (2) large triangles of this image: scan the bounding boxes, build the records of those touching the tile
+  const uint32_t nlarge = a.F > 0 ? large_count[n] : 0u;
+  const uint32_t* lid = large_id + (int64_t)n * a.F;
+  const int4* lbb = large_bbox + (int64_t)n * a.F;
+  for (uint32_t base = 0; base < nlarge; base += kLargeBlock) {
+    bool hit = false;
+    uint32_t f = 0;
+    if (tid < kLargeBlock && base + tid < nlarge) {
+      const int4 bb = lbb[base + tid];
+      hit = bb.x <= x_hi && bb.z >= x_lo && bb.y <= y_hi && bb.w >= y_lo;
+      f = lid[base + tid];
+    }
+    const unsigned bm = __ballot_sync(0xffffffffu, hit);
+    if (bm) {
+      int wbase = 0;
+      if (lane == 0) wbase = atomicAdd(&S.nmatch, __popc(bm));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (hit) S.mlist[wbase + __popc(bm & ((1u << lane) - 1u))] = f;
+    }
+    __syncthreads();
+    const int m = S.nmatch;
+    if (m > kPassRecs - kLargeBlock || (base + kLargeBlock >= nlarge && m > 0)) {  // uniform over the CTA
+      if (tid < m) {
+        TriFull s;
+        float4* dst = S.rec + tid * kRecF4;
+        if (tri_full(a, n, (int)S.mlist[tid], s) && max(s.bx0, x_lo) <= min(s.bx1, x_hi) && max(s.by0, y_lo) <= min(s.by1, y_hi)) {
+          write_record(s, (int)S.mlist[tid], record_meta(s, x_lo, y_lo, x_hi, y_hi, a.W), [&](int q, float4 val) { dst[q] = val; });
+        } else {  // cannot happen for a listed triangle; an empty record keeps the pass well defined
+          dst[4] = make_float4(0.f, __int_as_float((1 << RASTER_META_BY0) | (0 << RASTER_META_BY1)), 0.f, 0.f);
+        }
       }
+      __syncthreads();
+      tile_pass(S, m, x_lo, y_lo, best);
+      if (tid == 0) S.nmatch = 0;
+      __syncthreads();
     }
   }
-  __syncthreads();
 
   // (3) resolve + store (:402-415): empty -> index -1 (low word all ones), depth 0
-  const int64_t img_base = (int64_t)n * a.H * a.W;
-  if ((a.W & 3) == 0) {
-    for (int q = tid; q < kTilePix / 4; q += kRasterThreads) {
-      const int ly = q >> 3, lx = (q & 7) << 2;
-      const int x = x_lo + lx, y = y_lo + ly;
-      if (x > x_hi || y > y_hi) continue;  // W % 4 == 0 -> the whole quad is inside or outside
-      int4 id;
-      float4 dp;
-      const unsigned long long z0 = zbuf[(ly << kTileLog) + lx], z1 = zbuf[(ly << kTileLog) + lx + 1],
-                               z2 = zbuf[(ly << kTileLog) + lx + 2], z3 = zbuf[(ly << kTileLog) + lx + 3];
-      id.x = (int)(uint32_t)z0; id.y = (int)(uint32_t)z1; id.z = (int)(uint32_t)z2; id.w = (int)(uint32_t)z3;
-      const uint32_t d0 = (uint32_t)(z0 >> 32), d1 = (uint32_t)(z1 >> 32), d2 = (uint32_t)(z2 >> 32),
-                     d3 = (uint32_t)(z3 >> 32);
-      dp.x = d0 == 0xFFFFFFFFu ? 0.f : __uint_as_float(d0);
-      dp.y = d1 == 0xFFFFFFFFu ? 0.f : __uint_as_float(d1);
-      dp.z = d2 == 0xFFFFFFFFu ? 0.f : __uint_as_float(d2);
-      dp.w = d3 == 0xFFFFFFFFu ? 0.f : __uint_as_float(d3);
-      const int64_t o = img_base + (int64_t)y * a.W + x;
-      stg_stream_i4(index_img + o, id);
-      stg_stream_f4(depth_img + o, dp);
-    }
+  const int p4 = tid * 4;
+  const int ly = p4 >> kTileLog, lx = p4 & (kTile - 1);
+  const int x = x_lo + lx, y = y_lo + ly;
+  if (y > y_hi || x > x_hi) return;
+  int ids[4];
+  float dps[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned long long zb = S.zbuf[p4 + j];
+    const unsigned long long k = zb < best[j] ? zb : best[j];
+    const uint32_t d = (uint32_t)(k >> 32);
+    ids[j] = (int)(uint32_t)k;
+    dps[j] = d == 0xFFFFFFFFu ? 0.f : __uint_as_float(d);
+  }
+  const int64_t o = (int64_t)n * a.H * a.W + (int64_t)y * a.W + x;
+  if ((a.W & 3) == 0) {  // the quad is entirely inside the image and 16-B aligned
+    stg_stream_i4(index_img + o, make_int4(ids[0], ids[1], ids[2], ids[3]));
+    stg_stream_f4(depth_img + o, make_float4(dps[0], dps[1], dps[2], dps[3]));
   } else {
-    for (int q = tid; q < kTilePix; q += kRasterThreads) {
-      const int ly = q >> kTileLog, lx = q & (kTile - 1);
-      const int x = x_lo + lx, y = y_lo + ly;
-      if (x > x_hi || y > y_hi) continue;
-      const unsigned long long z = zbuf[q];
-      const uint32_t d = (uint32_t)(z >> 32);
-      const int64_t o = img_base + (int64_t)y * a.W + x;
-      index_img[o] = (int)(uint32_t)z;
-      depth_img[o] = d == 0xFFFFFFFFu ? 0.f : __uint_as_float(d);
-    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (x + j <= x_hi) { index_img[o + j] = ids[j]; depth_img[o + j] = dps[j]; }
   }
 }
 
@@ -448,8 +498,8 @@ __global__ void __launch_bounds__(256) raster_atomic_kernel(RasterArgs a, int64_
   if (idx >= total) return;
   const int n = (int)(idx / a.F);
   const int f = (int)(idx - (int64_t)n * a.F);
-  TriSetup s;
-  if (!tri_setup(a, n, f, s)) return;
+  TriFull s;
+  if (!tri_full(a, n, f, s)) return;
   unsigned long long* img = packed_img + (int64_t)n * a.H * a.W;
   for (int y = s.by0; y <= s.by1; ++y) {
     float row[3];
@@ -652,7 +702,7 @@ __global__ void __launch_bounds__(256) raster_lines_kernel(RasterArgs a, int64_t
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct TiledWorkspace {
-  size_t off_count, off_offset, off_large_count, off_large_list, off_tile_list, total;
+  size_t off_count, off_large_count, zero_bytes, off_offset, off_large_id, off_large_bbox, off_recs, total;
   int64_t M;
 };
 
@@ -663,11 +713,11 @@ inline TiledWorkspace tiled_layout(int64_t N, int64_t F, int64_t H, int64_t W) {
   size_t o = 0;
   w.off_count = o;       o = align_up(o + sizeof(uint32_t) * (size_t)w.M, 256);
   w.off_large_count = o; o = align_up(o + sizeof(uint32_t) * (size_t)N, 256);
-  const size_t zero_end = o;  // [0, zero_end) is memset to 0 per call
-  (void)zero_end;
+  w.zero_bytes = o;      // [0, zero_bytes) is memset to 0 per call
   w.off_offset = o;      o = align_up(o + sizeof(uint32_t) * (size_t)w.M, 256);
-  w.off_large_list = o;  o = align_up(o + sizeof(uint32_t) * (size_t)(N * F), 256);
-  w.off_tile_list = o;   o = align_up(o + sizeof(uint32_t) * (size_t)(4 * N * F), 256);
+  w.off_large_id = o;    o = align_up(o + sizeof(uint32_t) * (size_t)(N * F), 256);
+  w.off_large_bbox = o;  o = align_up(o + sizeof(int4) * (size_t)(N * F), 256);
+  w.off_recs = o;        o = align_up(o + (size_t)(kRecF4 * 16) * (size_t)(4 * N * F), 256);
   w.total = o;
   return w;
 }
@@ -680,9 +730,11 @@ using namespace drtk;
 extern "C" size_t drtk_b200_rasterize_workspace_bytes(int64_t N, int64_t F, int64_t H, int64_t W,
                                                        int algo) {
   if (N <= 0 || H <= 0 || W <= 0 || F < 0) return 0;
+  if (N > kMaxBatchPerLaunch) N = kMaxBatchPerLaunch;  // larger batches are processed in slices that reuse the workspace
   if (algo == 1) return sizeof(unsigned long long) * (size_t)(N * H * W) + 256;
   const size_t lines = sizeof(unsigned long long) * (size_t)(N * H * W) + 256;  // wireframe mode uses the packed image
-  const size_t tiled = tiled_layout(N, F, H, W).total + 256;
+  size_t tiled = tiled_layout(N, F, H, W).total + 256;
+  if (use_v1()) tiled = rasterize_v1_workspace_bytes(N, F, H, W);
   return tiled > lines ? tiled : lines;
 }
 
@@ -695,6 +747,16 @@ extern "C" int drtk_b200_rasterize(const float* v, const int64_t* v_strides, con
   if (N == 0) return 0;
   if (!depth_img || !index_img || !v_strides || !vi_strides) return DRTK_B200_EINVAL;
   if ((F > 0 && (!v || !vi))) return DRTK_B200_EINVAL;
+  if (N > kMaxBatchPerLaunch) {  // batch index rides on gridDim.z: slices of the batch (the workspace is reused)
+    for (int64_t n0 = 0; n0 < N; n0 += kMaxBatchPerLaunch) {
+      const int64_t nn = (N - n0 < kMaxBatchPerLaunch) ? N - n0 : kMaxBatchPerLaunch;
+      const int rc = drtk_b200_rasterize(v ? v + n0 * v_strides[0] : nullptr, v_strides, vi ? vi + n0 * vi_strides[0] : nullptr,
+                                         vi_strides, nn, V, F, H, W, wireframe, algo, depth_img + n0 * H * W,
+                                         index_img + n0 * H * W, workspace, workspace_bytes, stream_);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   if (H > (1 << 30) || W > (1 << 30) || N * F > (int64_t)0x1FFFFFFF || V >= 0x10000000LL)
     return DRTK_B200_EUNSUPPORTED;
   if (workspace_bytes < drtk_b200_rasterize_workspace_bytes(N, F, H, W, algo) || !workspace)
@@ -715,7 +777,7 @@ extern "C" int drtk_b200_rasterize(const float* v, const int64_t* v_strides, con
     DRTK_CUDA(cudaMemsetAsync(packed, 0xFF, sizeof(unsigned long long) * (size_t)npx, stream));
     if (total > 0) {
       const int64_t want = (total * 32 + 255) / 256;
-      const int64_t cap = (int64_t)kNumSMs * 32;
+      const int64_t cap = (int64_t)num_sms() * 32;
       raster_lines_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(a, total, packed);
       DRTK_CHECK_LAUNCH();
     }
@@ -737,30 +799,30 @@ extern "C" int drtk_b200_rasterize(const float* v, const int64_t* v_strides, con
     return 0;
   }
 
+  if (use_v1()) return rasterize_v1(v, v_strides, vi, vi_strides, N, V, F, H, W, depth_img, index_img, workspace, stream);
   const TiledWorkspace w = tiled_layout(N, F, H, W);
-  if (w.M > 0x7FFFFFFFLL) return DRTK_B200_EUNSUPPORTED;
+  if (w.M > 0x7FFFFFFFLL || a.tilesY > 65535) return DRTK_B200_EUNSUPPORTED;
   uint32_t* tile_count = reinterpret_cast<uint32_t*>(ws + w.off_count);
   uint32_t* large_count = reinterpret_cast<uint32_t*>(ws + w.off_large_count);
   uint32_t* tile_offset = reinterpret_cast<uint32_t*>(ws + w.off_offset);
-  uint32_t* large_list = reinterpret_cast<uint32_t*>(ws + w.off_large_list);
-  uint32_t* tile_list = reinterpret_cast<uint32_t*>(ws + w.off_tile_list);
+  uint32_t* large_id = reinterpret_cast<uint32_t*>(ws + w.off_large_id);
+  int4* large_bbox = reinterpret_cast<int4*>(ws + w.off_large_bbox);
+  float4* recs = reinterpret_cast<float4*>(ws + w.off_recs);
 
-  DRTK_CUDA(cudaMemsetAsync(ws, 0, w.off_offset, stream));  // tile_count + large_count
+  DRTK_CUDA(cudaMemsetAsync(ws, 0, w.zero_bytes, stream));  // tile_count + large_count
   if (total > 0) {
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    bin_kernel<false><<<blocks, 256, 0, stream>>>(a, total, tile_count, nullptr, nullptr, nullptr, nullptr);
+    bin_kernel<false><<<blocks, 256, 0, stream>>>(a, total, tile_count, nullptr, nullptr, nullptr, nullptr, nullptr);
     DRTK_CHECK_LAUNCH();
     const int64_t T = w.M / N;  // tiles per image; 16-B aligned per-image segments allow the uint4 path
     if (4 * F * N > 0xFFFFFFFFLL) return DRTK_B200_EUNSUPPORTED;
     scan_kernel<<<(unsigned)N, 1024, 0, stream>>>(tile_count, tile_offset, T, (uint32_t)(4 * F), (T & 3) == 0);
     DRTK_CHECK_LAUNCH();
-    bin_kernel<true><<<blocks, 256, 0, stream>>>(a, total, tile_count, tile_offset, tile_list,
-                                                 large_count, large_list);
+    bin_kernel<true><<<blocks, 256, 0, stream>>>(a, total, tile_count, tile_offset, recs, large_count, large_id, large_bbox);
     DRTK_CHECK_LAUNCH();
   }
-  if (N > 65535 || a.tilesY > 65535) return DRTK_B200_EUNSUPPORTED;
   raster_tiles_kernel<<<dim3((unsigned)a.tilesX, (unsigned)a.tilesY, (unsigned)N), kRasterThreads, 0, stream>>>(
-      a, tile_count, tile_offset, tile_list, large_count, large_list, depth_img, index_img);
+      a, tile_count, tile_offset, recs, large_count, large_id, large_bbox, depth_img, index_img);
   DRTK_CHECK_LAUNCH();
   return 0;
 }

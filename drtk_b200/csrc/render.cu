@@ -463,7 +463,7 @@ inline size_t walk_gpad_bytes(int64_t N, int64_t V) { return (size_t)(N * V) * 1
 
 inline unsigned grid_for(int64_t work_items, int threads, int ctas_per_sm) {
   const int64_t need = (work_items + threads - 1) / threads;
-  const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+  const int64_t cap = (int64_t)num_sms() * ctas_per_sm;
   return (unsigned)(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
@@ -481,20 +481,30 @@ extern "C" int drtk_b200_render_forward(const float* v, const int64_t* v_strides
   if (N * H * W == 0) return 0;
   if (!v || !vi || !index_img || !depth_img || !bary_img) return DRTK_B200_EINVAL;
   if (H > (1 << 30) || W > (1 << 30) || N > (1 << 30)) return DRTK_B200_EUNSUPPORTED;
+  if (N > kMaxBatchPerLaunch) {  // batch index rides on gridDim.y: slices of the batch
+    for (int64_t n0 = 0; n0 < N; n0 += kMaxBatchPerLaunch) {
+      const int64_t nn = (N - n0 < kMaxBatchPerLaunch) ? N - n0 : kMaxBatchPerLaunch;
+      const int rc = drtk_b200_render_forward(v + n0 * v_strides[0], v_strides, vi + n0 * vi_strides[0], vi_strides,
+                                              index_img + n0 * index_strides[0], index_strides, nn, V, F, H, W,
+                                              depth_img + n0 * H * W, bary_img + n0 * 3 * H * W, stream_);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RenderArgs a;
   a.v = v; a.vs = make3(v_strides); a.vi = vi; a.vis = make3(vi_strides);
   a.index_img = index_img; a.is = make3(index_strides);
   a.N = (int)N; a.V = (int)V; a.F = (int)F; a.H = (int)H; a.W = (int)W;
   const bool vec = VecOk::image(index_img, W, a.is.s2, a.is.s1, a.is.s0);
-  if (H * W >= (int64_t)0x7FFFFFF0 || N > 65535) return DRTK_B200_EUNSUPPORTED;
+  if (H * W >= (int64_t)0x7FFFFFF0) return DRTK_B200_EUNSUPPORTED;
   // grid.y = image; grid.x sized so that all CTAs of all images are co-resident (one wave, grid-stride loops
   // inside): a partly filled last wave cost 8 % in interp_fwd_kernel
   const int64_t items = vec ? H * W / 4 : H * W;
   auto launch = [&](auto kern) {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0) != cudaSuccess || occ < 1) occ = 1;
-    int64_t gx = (int64_t)kNumSMs * occ / N;
+    int64_t gx = (int64_t)num_sms() * occ / N;
     const int64_t need = (items + 255) / 256;
     if (gx < 1) gx = 1;
     if (gx > need) gx = need;
@@ -533,13 +543,25 @@ extern "C" int drtk_b200_render_backward(const float* v, const int64_t* v_stride
   }
   if (!v || !vi || !index_img) return DRTK_B200_EINVAL;
   if (H > (1 << 30) || W > (1 << 30) || N > (1 << 30)) return DRTK_B200_EUNSUPPORTED;
+  if (N > kMaxBatchPerLaunch) {  // batch index rides on gridDim.y: slices of the batch (the workspace is reused)
+    for (int64_t n0 = 0; n0 < N; n0 += kMaxBatchPerLaunch) {
+      const int64_t nn = (N - n0 < kMaxBatchPerLaunch) ? N - n0 : kMaxBatchPerLaunch;
+      const int rc = drtk_b200_render_backward(
+          v + n0 * v_strides[0], v_strides, vi + n0 * vi_strides[0], vi_strides, index_img + n0 * index_strides[0],
+          index_strides, grad_depth ? grad_depth + n0 * grad_depth_strides[0] : nullptr, grad_depth_strides,
+          grad_bary ? grad_bary + n0 * grad_bary_strides[0] : nullptr, grad_bary_strides, nn, V, F, H, W,
+          grad_v + n0 * V * 3, workspace, workspace_bytes, stream_);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   RenderBwdArgs b;
   b.r.v = v; b.r.vs = make3(v_strides); b.r.vi = vi; b.r.vis = make3(vi_strides);
   b.r.index_img = index_img; b.r.is = make3(index_strides);
   b.r.N = (int)N; b.r.V = (int)V; b.r.F = (int)F; b.r.H = (int)H; b.r.W = (int)W;
   b.grad_depth = grad_depth; b.gds = grad_depth ? make3(grad_depth_strides) : Strides3{0, 0, 0};
   b.grad_bary = grad_bary; b.gbs = grad_bary ? make4(grad_bary_strides) : Strides4{0, 0, 0, 0};
-  if (H * W >= (int64_t)0x7FFFFFF0 || N > 65535) return DRTK_B200_EUNSUPPORTED;
+  if (H * W >= (int64_t)0x7FFFFFF0) return DRTK_B200_EUNSUPPORTED;
   auto dense3 = [&](const Strides3& s, int64_t d1, int64_t d2) { return s.s2 == 1 && s.s1 == d2 && (N == 1 || s.s0 == d1 * d2); };
   const bool dense = dense3(b.r.is, H, W) && b.r.vs.s2 == 1 && b.r.vs.s1 == 3 && (N == 1 || b.r.vs.s0 == V * 3) &&
                      b.r.vis.s2 == 1 && b.r.vis.s1 == 3 && V * 3 < (int64_t)0x7FFFFFF0 && F * 3 < (int64_t)0x7FFFFFF0 &&

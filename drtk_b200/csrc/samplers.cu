@@ -450,7 +450,7 @@ scatter_bwd_kernel(ScatterArgs a, const float* __restrict__ gout, Strides4 gos, 
 }
 
 inline unsigned blocks_for(int64_t total) {
-  const int64_t need = (total + 255) / 256, cap = int64_t(kNumSMs) * 16;
+  const int64_t need = (total + 255) / 256, cap = int64_t(num_sms()) * 16;
   return unsigned(need < 1 ? 1 : (need > cap ? cap : need));
 }
 inline bool bad_enum(int pad, int interp) { return pad < 0 || pad > 2 || (interp != 0 && interp != 2); }

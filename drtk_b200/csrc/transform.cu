@@ -290,7 +290,7 @@ transform_bwd_kernel(const float* __restrict__ v, Strides3 vs, const float* __re
 inline dim3 grid_for(int64_t N, int64_t V) {
   // a handful of CTAs per SM over the whole batch; every thread loops over its vertices
   int64_t bx = (V + 255) / 256;
-  const int64_t cap = (int64_t(kNumSMs) * 8 + N - 1) / N;
+  const int64_t cap = (int64_t(num_sms()) * 8 + N - 1) / N;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   return dim3(unsigned(bx), unsigned(N));

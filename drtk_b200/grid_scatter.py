@@ -10,6 +10,7 @@ import torch as th
 import torch.nn.functional as thf
 
 from . import _lib
+from . import _ops
 from ._ops import _chk
 
 _MODES = {"bilinear": 0, "bicubic": 2}
@@ -73,7 +74,7 @@ def grid_scatter(
         raise ValueError("grid_scatter(): expected padding_mode to be 'zeros', 'border', or 'reflection', "
                          f"but got: '{padding_mode}'")
     if th.is_autocast_enabled():
-        input, grid = input.float(), grid.float()
+        input, grid = _ops._autocast_one(input), _ops._autocast_one(grid)
     who = "grid_scatter_2d()"
     _chk(input.device == grid.device and input.is_cuda,
          f"{who}: expected input and grid to be on same device, but input is on {input.device} and grid is on {grid.device}")

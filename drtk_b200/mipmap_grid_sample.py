@@ -11,6 +11,7 @@ import torch as th
 import torch.nn.functional as thf
 
 from . import _lib
+from . import _ops
 from ._ops import _chk
 
 _MODES = {"bilinear": 0, "bicubic": 2}
@@ -124,8 +125,8 @@ def mipmap_grid_sample(
                          f"but got: '{padding_mode}'")
     input = list(input)
     if th.is_autocast_enabled():  # the reference's Autocast kernel casts everything to float32
-        input = [t.float() for t in input]
-        grid, vt_dxdy_img = grid.float(), vt_dxdy_img.float()
+        input = [_ops._autocast_one(t) for t in input]
+        grid, vt_dxdy_img = _ops._autocast_one(grid), _ops._autocast_one(vt_dxdy_img)
     _check(input, grid, vt_dxdy_img)
     opts = (int(max_aniso), _PADS[padding_mode], _MODES[mode], bool(align_corners), bool(force_max_aniso), bool(clip_grad))
     _chk(opts[0] >= 1, "mipmap_grid_sample(): max_aniso must be at least 1")

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DRTK_B200_ABI_VERSION 1
+#define DRTK_B200_ABI_VERSION 2
 
 #define DRTK_B200_EINVAL (-1)     /* bad argument (null pointer, non-positive size, ...) */
 #define DRTK_B200_EWORKSPACE (-2) /* workspace too small */
@@ -110,7 +110,12 @@ int drtk_b200_interpolate_forward(const float* vert_attributes, const int64_t* a
  * (src/interpolate/interpolate_kernel.cu:642-697).
  *   grad_out [N,C,H,W] (strides grad_out_strides[4])
  *   vert_attributes_grad [N,V,C] out or NULL (zero-filled by the callee, then accumulated)
- *   bary_img_grad        [N,3,H,W] out or NULL (every pixel written)                      */
+ *   bary_img_grad        [N,3,H,W] out or NULL (every pixel written)
+ *   workspace            device scratch of at least drtk_b200_interpolate_backward_workspace_bytes(N, F,
+ *                        vi_strides[0]) bytes (the packed per-triangle vertex-id table of the tiled fast path;
+ *                        the library itself never allocates device memory)                              */
+size_t drtk_b200_interpolate_backward_workspace_bytes(int64_t N, int64_t F, int64_t vi_batch_stride);
+
 int drtk_b200_interpolate_backward(const float* grad_out, const int64_t* grad_out_strides,
                                    const float* vert_attributes, const int64_t* attr_strides,
                                    const int32_t* vi, const int64_t* vi_strides,
@@ -118,7 +123,7 @@ int drtk_b200_interpolate_backward(const float* grad_out, const int64_t* grad_ou
                                    const float* bary_img, const int64_t* bary_strides, int64_t N,
                                    int64_t V, int64_t F, int64_t C, int64_t H, int64_t W,
                                    float* vert_attributes_grad, float* bary_img_grad,
-                                   void* stream);
+                                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Sparse interpolation matrices of a fixed rasterisation (dense, contiguous inputs, like the reference

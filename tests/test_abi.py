@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_version_and_error_strings():
     from drtk_b200 import _lib
     lib = _lib.load()
-    assert lib.drtk_b200_abi_version() == 1
+    assert lib.drtk_b200_abi_version() == _lib.ABI_VERSION
     assert b"workspace" in lib.drtk_b200_error_string(-2)
     assert lib.drtk_b200_error_string(0) == b"success"
     assert lib.drtk_b200_rasterize_workspace_bytes(8, 100352, 2048, 2048, 0) > 4 * 8 * 100352 * 4

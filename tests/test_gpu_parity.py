@@ -40,6 +40,36 @@ def npy(t):
     return t.detach().cpu().numpy()
 
 
+def assert_close_device(actual, expected, rtol, what):
+    """assert_close on the device (tensors too large to ship to numpy): |a-e| <= rtol*|e| + rtol*max|e|, written
+    as NOT(within tolerance) so that a NaN / Inf in `actual` fails instead of slipping through a `>` test."""
+    assert actual.shape == expected.shape, f"{what}: shape {tuple(actual.shape)} vs {tuple(expected.shape)}"
+    assert bool(th.isfinite(expected).all()), f"{what}: the expectation itself is not finite"
+    scale = float(expected.abs().max()) if expected.numel() else 0.0
+    bad = ~((actual - expected).abs() <= rtol * expected.abs() + rtol * scale)
+    assert not bool(bad.any()), f"{what}: {int(bad.sum())}/{bad.numel()} elements out of tolerance (or not finite)"
+
+
+def test_comparison_helpers_reject_nan_and_inf():
+    """Self-test of the parity tooling: a kernel that emits NaN / Inf must FAIL every fp32 comparison."""
+    e = np.array([1.0, 1.0, 2.0, 0.0], np.float32)
+    for bad_val in (np.nan, np.inf, -np.inf):
+        a = e.copy(); a[2] = bad_val
+        with pytest.raises(AssertionError):
+            assert_close(a, e, what="nan-injection")
+        with pytest.raises(AssertionError):
+            assert_close_device(cu(a), cu(e), 1e-5, "nan-injection (device)")
+    assert_close(e, e)
+    assert_close_device(cu(e), cu(e), 1e-5, "identity")
+    # a NaN injected into a real kernel output is caught too
+    v, vi = scenes.grid_mesh(9, 9, 64, 64, 1, seed=3)
+    index = drtk_b200.rasterize(cu(v), cu(vi), 64, 64)
+    _, bary = drtk_b200.render(cu(v), cu(vi), index)
+    poisoned = bary.clone(); poisoned[0, 1, 30, 30] = float("nan")
+    with pytest.raises(AssertionError):
+        assert_close(npy(poisoned), npy(bary), what="poisoned bary")
+
+
 def small_scenes():
     yield "grid_256", *scenes.grid_mesh(21, 21, 256, 256, 2, seed=7), 256, 256
     yield "overdraw_192x160", *scenes.grid_mesh(15, 15, 192, 160, 2, seed=11, overdraw=True), 192, 160
@@ -532,6 +562,68 @@ def test_pipeline_vs_reference_cuda(cfg, N, overdraw):
     assert_close(npy(n["gv"]), npy(r["gv"]), rtol=5e-5, what="grad v")
 
 
+@needs_ref
+@pytest.mark.parametrize("overdraw,hook", [(False, False), (False, True), (True, False), (True, True)])
+def test_pipeline_config4_batch8_vs_reference_cuda(overdraw, hook):
+    """The MEASURED configuration (BASELINE config 4: 100 352 triangles, 2048^2, batch 8, C = 16, bench.py's seeds:
+    mesh 4000 + b, attributes 4001, cotangent 4002) and its overdraw-2 variant (occlusion + intersections: the
+    horiz_int / vert_int branches of src/edge_grad/edge_grad_kernel.cu:320-341 at size), with and without a
+    v_pix_img hook (the hook selects the two-kernel edge_grad plan, no hook the fused one), against the reference's
+    CUDA kernels.  Compared on the device: index_img equal, fp32 outputs 1e-5, vertex gradients 5e-5 of scale."""
+    cfg, N, C = 4, 8, 16
+    c = scenes.CONFIGS[cfg]
+    H, W = c["H"], c["W"]
+    v, vi = scenes.grid_mesh(c["nx"], c["ny"], H, W, N, seed=1000 * cfg, overdraw=overdraw, device=DEV)
+    attr = scenes.vertex_attributes(N, v.shape[1], C, seed=1000 * cfg + 1, device=DEV)
+    w = th.rand((N, C, H, W), device=DEV, generator=th.Generator(device=DEV).manual_seed(1000 * cfg + 2))
+    res = {}
+    for tag, api in (("ref", R), ("new", drtk_b200)):
+        vv, aa = v.clone().requires_grad_(True), attr.clone().requires_grad_(True)
+        cap = {}
+        index = api.rasterize(vv, vi, H, W)
+        depth, bary = api.render(vv, vi, index)
+        img = api.interpolate(aa, vi, index, bary)
+        out = api.edge_grad_estimator(vv, vi, bary, img, index,
+                                      v_pix_img_hook=(lambda g: cap.__setitem__("g", g.clone())) if hook else None)
+        out.backward(gradient=w)
+        res[tag] = dict(index=index, depth=depth.detach(), bary=bary.detach(), img=img.detach(), gv=vv.grad, ga=aa.grad,
+                        gpix=cap.get("g"))
+        del out, img, bary, depth
+    r, n = res["ref"], res["new"]
+    assert th.equal(r["index"], n["index"]), f"index_img: {int((r['index'] != n['index']).sum())} pixels differ"
+    if overdraw:  # the scene really has occlusion: both sheets visible somewhere
+        F1 = vi.shape[0] // 2
+        assert bool((n["index"] >= F1).any()) and bool(((n["index"] >= 0) & (n["index"] < F1)).any())
+    assert_close_device(n["depth"], r["depth"], 1e-5, "depth_img")
+    assert_close_device(n["bary"], r["bary"], 1e-5, "bary_img")
+    assert_close_device(n["img"], r["img"], 1e-5, "interpolated img")
+    if hook:
+        assert_close_device(n["gpix"], r["gpix"], 1e-5, "grad_v_pix_img")
+    assert_close_device(n["ga"], r["ga"], 5e-5, "grad attr")
+    assert_close_device(n["gv"], r["gv"], 5e-5, "grad v")
+
+
+def test_empty_face_list():
+    """F == 0 (the reference handles it: background sweep forward, zero gradients backward)."""
+    N, V, C, H, W = 2, 5, 4, 16, 24
+    g = th.Generator().manual_seed(1)
+    v = cu(th.rand((N, V, 3), generator=g) * 10 + 1)
+    vi = th.zeros((0, 3), dtype=th.int32, device=DEV)
+    attr = cu(th.rand((N, V, C), generator=g)).requires_grad_(True)
+    index = drtk_b200.rasterize(v, vi, H, W)
+    assert bool((index == -1).all())
+    _, bary = drtk_b200.render(v, vi, index)
+    bary = bary.requires_grad_(True)
+    img = drtk_b200.interpolate(attr, vi, index, bary)
+    xs = (2 * th.arange(W, device=DEV) + 1) / W - 1
+    ys = (2 * th.arange(H, device=DEV) + 1) / H - 1
+    assert th.allclose(img[:, 0], xs[None, None, :].expand(N, H, W)) and th.allclose(img[:, 1], ys[None, :, None].expand(N, H, W))
+    img.sum().backward()
+    assert bool((attr.grad == 0).all()) and bool((bary.grad == 0).all())  # not uninitialised memory
+    ga, gb = _ops.interpolate_backward(th.ones_like(img), attr.detach(), vi[None].expand(N, -1, -1), index, bary.detach(), True, True)
+    assert bool((ga == 0).all()) and bool((gb == 0).all())
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_pipeline_autograd_golden(name):
     """The drop-in API end to end: same autograd surface as the reference (hook, identity forward,
@@ -594,9 +686,7 @@ def test_config5_slice_vs_reference_cuda():
     r, n = res["ref"], res["new"]
     assert th.equal(r[0], n[0]), "index_img"
     for k, name, tol in ((1, "depth", 1e-5), (2, "bary", 1e-5), (3, "img", 1e-5), (4, "grad_v", 5e-5), (5, "grad_attr", 5e-5)):
-        scale = float(r[k].abs().max())
-        bad = ((n[k] - r[k]).abs() > tol * r[k].abs() + tol * scale)
-        assert not bool(bad.any()), f"{name}: {int(bad.sum())} elements out of tolerance"
+        assert_close_device(n[k], r[k], tol, name)
 
 
 @pytest.mark.parametrize("cfg,N,overdraw,expand_vi", [(3, 2, False, True), (3, 1, True, False), (4, 1, False, True)])

@@ -73,7 +73,9 @@ def test_edge_grad_backward(name):
     out = O.edge_grad_bwd(g["v"], g["interp"], g["index_img"], g["vi"], g["w_img"], 1e4)
     assert_close(out, g["grad_v_pix_img"], what="grad_v_pix_img")
     # structural property (reference :270): the last row/column only receive neighbour terms
-    assert (out[:, 0, -1, :] == 0).all() or True
+    # -> no horizontal pair ends in the last row, no vertical pair in the last column
+    assert (out[:, 0, -1, :] == 0).all() and (out[:, 1, :, -1] == 0).all()
+    assert (g["grad_v_pix_img"][:, 0, -1, :] == 0).all() and (g["grad_v_pix_img"][:, 1, :, -1] == 0).all()
 
 
 @pytest.mark.parametrize("name", CASES)

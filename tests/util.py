@@ -37,9 +37,15 @@ def assert_close(actual, expected, rtol=1e-5, scale_rtol=None, what=""):
     assert a.shape == e.shape, f"{what}: shape {a.shape} vs {e.shape}"
     scale = float(np.abs(e).max()) if e.size else 0.0
     atol = (rtol if scale_rtol is None else scale_rtol) * scale
-    bad = np.abs(a - e) > rtol * np.abs(e) + atol
+    # NaN / Inf safe: "not within tolerance" (a NaN never satisfies <=), and a non-finite value must sit exactly
+    # where the expectation has the same non-finite value
+    with np.errstate(invalid="ignore"):
+        err = np.abs(a - e)
+        bad = ~(err <= rtol * np.abs(e) + atol)
+    bad &= ~((a == e) & ~np.isnan(a))  # identical infinities are fine
     if bad.any():
-        i = np.unravel_index(np.argmax(np.abs(a - e) - rtol * np.abs(e) - atol), a.shape)
+        excess = np.where(np.isfinite(err), err - rtol * np.abs(e) - atol, np.inf)
+        i = np.unravel_index(np.argmax(np.where(bad, excess, -np.inf)), a.shape)
         raise AssertionError(
             f"{what}: {int(bad.sum())}/{a.size} elements out of tolerance; worst at {i}: "
             f"actual {a[i]!r} expected {e[i]!r} (|d|={abs(a[i]-e[i]):.3e}, scale {scale:.3e})")

@@ -1,6 +1,8 @@
 """A/B timing of single ops on config-4 tensors (CUDA events, L2-cold by construction: each op streams >1 GB).
 usage: python tools/opbench.py [--ops interp_bwd,...] [--iters 20]
-Environment switches read by the library per call are toggled in-process (DRTK_B200_*)."""
+The library reads its DRTK_B200_* developer switches ONCE per process, so an A/B is two invocations:
+    python tools/opbench.py --ops interp_bwd --dump /tmp/a.pt
+    DRTK_B200_MERGED=1 python tools/opbench.py --ops interp_bwd --cmp /tmp/a.pt"""
 import argparse, os, sys
 import torch as th
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,10 +14,12 @@ ap.add_argument("--config", type=int, default=4)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--C", type=int, default=16)
 ap.add_argument("--ops", default="interp_bwd")
-ap.add_argument("--env", default="", help="comma list of VAR=VAL variants to compare, e.g. DRTK_B200_BWD_V4=1")
+ap.add_argument("--dump", default="", help="save each op's outputs to this file")
+ap.add_argument("--cmp", default="", help="compare each op's outputs with a file written by --dump")
+ap.add_argument("--overdraw", action="store_true")
 a = ap.parse_args()
 dev = "cuda:0"
-v, vi, H, W = scenes.config_mesh(a.config, device=dev)
+v, vi, H, W = scenes.config_mesh(a.config, overdraw=a.overdraw, device=dev)
 N = v.shape[0]
 vi3 = vi[None].expand(N, -1, -1)
 attr = scenes.vertex_attributes(N, v.shape[1], a.C, seed=1, device=dev)
@@ -62,21 +66,19 @@ if any(o.startswith("nm_") or o.startswith("imat") for o in a.ops.split(",")):
         OPS["imat_ref"] = lambda: th.ops.interpolate_ext.interpolation_matrix(vic, index, bary)[2]
     except Exception as ex:  # noqa: BLE001
         print("reference ops unavailable:", ex)
-variants = [""] + [e for e in a.env.split(",") if e]
+tag = ",".join(f"{k}={v_}" for k, v_ in sorted(os.environ.items()) if k.startswith("DRTK_B200_")) or "default"
+saved = th.load(a.cmp) if a.cmp else {}
+dump = {}
 for op in a.ops.split(","):
-    base = None
-    for var in variants:
-        if var:
-            k, val = var.split("="); os.environ[k] = val
-        med, mn, out = timeit(OPS[op])
-        if var:
-            del os.environ[var.split("=")[0]]
-        outs = [o for o in (out if isinstance(out, tuple) else (out,)) if o is not None]
-        msg = ""
-        if base is None:
-            base = outs
-        else:
-            for i, (x, y) in enumerate(zip(outs, base)):
-                d = (x.float() - y.float()).abs().max().item(); sc = y.float().abs().max().item()
-                msg += f" out{i}: maxdiff {d:.3e} (scale {sc:.3e})"
-        print(f"{op:14s} {var or 'default':28s} median {med:.4f} ms  min {mn:.4f} ms{msg}", flush=True)
+    med, mn, out = timeit(OPS[op])
+    outs = [o for o in (out if isinstance(out, tuple) else (out,)) if o is not None]
+    msg = ""
+    for i, (x, y) in enumerate(zip(outs, saved.get(op, []))):
+        y = y.to(dev)
+        d = (x.float() - y.float()).abs().max().item(); sc = y.float().abs().max().item()
+        msg += f" out{i}: maxdiff {d:.3e} (scale {sc:.3e}, finite {bool(th.isfinite(x.float()).all())})"
+    if a.dump:
+        dump[op] = [o.cpu() for o in outs]
+    print(f"{op:14s} {tag:28s} median {med:.4f} ms  min {mn:.4f} ms{msg}", flush=True)
+if a.dump:
+    th.save(dump, a.dump)
