@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- the DRTK rasterisation hot path on B200: Mpixels/s, forward + backward.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl new|reference] [--config 4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl new|reference] [--config 2|3|4|5] [--overdraw]
+                    [--regions R] [--transport auto|nccl|multimem]
 
 One step = one pass of the hot path over one batch of synthetic input (BASELINE.json):
 
@@ -21,9 +22,14 @@ attributes (the configuration the metric is quoted on).  Prints ONE JSON line (r
                  sources) on a bounded sample of the same workload, on the host cores of the box
   --impl reference   times that CPU implementation as its own arm (rank 0 only under torchrun)
 
-N > 1 (torchrun, one process per GPU, NCCL): the batch is sharded -- every rank runs the same
-per-GPU workload on its own items (weak scaling, no data-path collective) and the gradients of the
-shared mesh / attribute table are summed over the local batch and all-reduced once per step.
+The mesh and the attribute table are parameters SHARED by the batch items, so the result of a step is the gradient
+summed over the batch: [V,3] + [V,C].  N > 1 (torchrun, one process per GPU): the batch is sharded -- every rank runs
+the same per-GPU workload on its own items (weak scaling, no data-path collective) -- and those sums are all-reduced,
+each parameter as soon as autograd has finished it (drtk_b200.dist.SharedGradReducer: one fused batch-sum +
+multimem all-reduce kernel over NVSwitch multicast memory, or batch-sum kernel + NCCL).
+
+The K-step region is timed R times (--regions, default 3); `ms_per_step` / `value` are the MEDIAN region, all regions
+are listed.  `parity_check` compares the tensors of one step with the reference CUDA kernels run on the same inputs.
 """
 import argparse
 import json
@@ -42,6 +48,7 @@ sys.path.insert(0, ROOT)
 from drtk_b200 import scenes  # noqa: E402
 
 METRIC = "Mpixels/s fwd+bwd (rasterize+render+interpolate+edge_grad), 100k-tri@2048^2 b8"
+METRIC_OTHER = "Mpixels/s fwd+bwd (rasterize+render+interpolate+edge_grad), BASELINE config {cfg}{od}"
 C_ATTR = 16
 
 # algorithmic (compulsory) HBM bytes per pixel of each of OUR ops at fp32, C = attribute channels;
@@ -61,6 +68,7 @@ ALGO_BYTES_PER_PX = {
 # CUDA kernels launched by libdrtk_b200.so per op call (memsets are driver operations, not counted)
 KERNELS = {"rasterize": 4, "render_fwd": 1, "interpolate_fwd": 1, "edge_grad_bwd_fused": 2,
            "interpolate_bwd": 2, "render_bwd": 3}
+REDUCE_KERNELS = 2  # batch sum (+ in-kernel all-reduce) of grad_v and grad_attr
 
 
 def load_peaks():
@@ -139,11 +147,26 @@ class ClockSampler:
                 "reasons": reasons}
 
 
-def make_inputs(cfg, device, seed_offset=0):
-    c = scenes.CONFIGS[cfg]
-    v, vi = scenes.grid_mesh(c["nx"], c["ny"], c["H"], c["W"], c["N"], seed=1000 * cfg + seed_offset)
-    attr = scenes.vertex_attributes(c["N"], v.shape[1], C_ATTR, seed=1000 * cfg + 1 + seed_offset)
-    return v, vi, attr, c
+def config_of(cfg):
+    """(geometry dict, attribute channels).  Config 2 = the reference demo's two literal triangles (test/two_triangles.py:
+    21-32), 512x512, batch 1, 3 colour channels; configs 3-5 = the jittered grid meshes of scenes.CONFIGS, 16 channels."""
+    if cfg == 2:
+        return dict(H=512, W=512, N=1, F=2), 3
+    c = dict(scenes.CONFIGS[cfg])
+    c["F"] = 2 * (c["nx"] - 1) * (c["ny"] - 1)
+    return c, C_ATTR
+
+
+def make_inputs(cfg, seed_offset=0, overdraw=False, N=None):
+    c, C = config_of(cfg)
+    n = c["N"] if N is None else N
+    if cfg == 2:
+        v, vi, _, _ = scenes.two_triangles()
+        v = v.expand(n, -1, -1).contiguous()
+    else:
+        v, vi = scenes.grid_mesh(c["nx"], c["ny"], c["H"], c["W"], n, seed=1000 * cfg + seed_offset, overdraw=overdraw)
+    attr = scenes.vertex_attributes(n, v.shape[1], C, seed=1000 * cfg + 1 + seed_offset)
+    return v, vi, attr, c, C
 
 
 def pipeline(api, v_pix, vi, attr, w, H, W):
@@ -160,13 +183,11 @@ def pipeline(api, v_pix, vi, attr, w, H, W):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_reference_cpu(cfg, steps, warmup, sample_items=1):
+def run_reference_cpu(cfg, steps, warmup, sample_items=1, overdraw=False):
     """The reference's CPU implementation of the path (oracle/_ref when present, else the oracle
     port) on a bounded sample: `sample_items` batch items of the workload per step."""
-    c = scenes.CONFIGS[cfg]
-    v, vi = scenes.grid_mesh(c["nx"], c["ny"], c["H"], c["W"], sample_items, seed=1000 * cfg)
-    attr = scenes.vertex_attributes(sample_items, v.shape[1], C_ATTR, seed=1000 * cfg + 1)
-    w = th.rand((sample_items, C_ATTR, c["H"], c["W"]), generator=th.Generator().manual_seed(1000 * cfg + 2))
+    v, vi, attr, c, C = make_inputs(cfg, overdraw=overdraw, N=sample_items)
+    w = th.rand((sample_items, C, c["H"], c["W"]), generator=th.Generator().manual_seed(1000 * cfg + 2))
     from oracle import ref as R
     kind = "reference" if R.available() else "port"
     cores = th.get_num_threads()
@@ -196,19 +217,30 @@ def run_reference_cpu(cfg, steps, warmup, sample_items=1):
     px = sample_items * c["H"] * c["W"]
     return {"value": px / dt / 1e6, "unit": "Mpix/s", "cores": cores, "kind": kind,
             "sample": f"{sample_items} of {c['N']} batch items of config {cfg} per step ({px / 1e6:.2f} Mpix), {steps} steps, {warmup} warm-up",
-            "ms_per_step": dt * 1e3, "transform_only": cpu_transform_only(cfg)}
+            "ms_per_step": dt * 1e3, "transform_only": cpu_transform_only(cfg),
+            "same_rate_metric": "Mpix/s is a rate: the sample is a fraction of the batch of the same workload, not the whole step"}
 
 
 def cpu_transform_only(cfg, reps=5):
     """BASELINE's 'transform-only CPU path': the reference's `drtk.transform` is a chain of stock torch ops on the
-    [N,V,3] vertex table (drtk/transform.py:68-119 -> drtk/utils/projection.py:33-53, :536); the same chain
-    (`drtk_b200.transform.project_points_ref`, a port -- /root/reference does not exist on the GPU box) forward +
-    backward on CPU tensors of the configuration's size, all host threads torch uses."""
+    [N,V,3] vertex table (drtk/transform.py:68-119 -> drtk/utils/projection.py:33-53, :536), forward + backward on CPU
+    tensors of the configuration's size, all host threads torch uses.  Where /root/reference exists (the build
+    container) the reference's own file is imported and timed (`kind: reference`); on the GPU box, where it does not,
+    the same chain as stated in `drtk_b200.transform.project_points_ref` (`kind: port`)."""
     try:
         import drtk_b200  # noqa: F401  (the package attribute `transform` is the function; the module holds the statement)
-        T = sys.modules["drtk_b200.transform"]
-        c = scenes.CONFIGS[cfg]
-        v, _ = scenes.grid_mesh(c["nx"], c["ny"], c["H"], c["W"], c["N"], seed=1000 * cfg)
+        kind, project = "port", sys.modules["drtk_b200.transform"].project_points_ref
+        ref_file = "/root/reference/drtk/utils/projection.py"
+        if os.path.exists(ref_file):
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("_ref_projection", ref_file)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                kind, project = "reference", mod.project_points
+            except Exception:  # noqa: BLE001
+                pass
+        v, _, _, c, _ = make_inputs(cfg)
         N = v.shape[0]
         v = (v + th.tensor([0.0, 0.0, 1.0])).requires_grad_(True)
         cam = (th.zeros(N, 3), th.eye(3)[None].expand(N, -1, -1).contiguous(),
@@ -217,16 +249,46 @@ def cpu_transform_only(cfg, reps=5):
 
         def once():
             v.grad = None
-            T.project_points_ref(v, *cam)[0].backward(g)
+            project(v, *cam)[0].backward(g)
         once()
         t0 = time.perf_counter()
         for _ in range(reps):
             once()
         dt = (time.perf_counter() - t0) / reps
         return {"ms_fwd_bwd": round(dt * 1e3, 3), "Mvertices_per_s": round(v.shape[0] * v.shape[1] / dt / 1e6, 2),
-                "cores": th.get_num_threads(), "kind": "port", "vertices": v.shape[0] * v.shape[1]}
+                "cores": th.get_num_threads(), "kind": kind, "vertices": v.shape[0] * v.shape[1]}
     except Exception as ex:  # noqa: BLE001
         return {"unavailable": repr(ex)[:160]}
+
+
+def compare_with_reference(api_new, api_ref, v, vi, attr, w, H, W):
+    """One step of both arms on the same tensors, compared on the device: index_img equal; depth / bary / img within
+    1e-5 (relative + the same fraction of the tensor's scale); vertex / attribute gradients within 5e-5 of scale (both
+    sides are long atomically ordered fp32 sums).  NaN / Inf anywhere fails.  Returns the `parity_check` object."""
+    res = {}
+    for tag, api in (("ref", api_ref), ("new", api_new)):
+        vv, aa = v.detach().clone().requires_grad_(True), attr.detach().clone().requires_grad_(True)
+        index = api.rasterize(vv, vi, H, W)
+        depth, bary = api.render(vv, vi, index)
+        img = api.interpolate(aa, vi, index, bary)
+        out = api.edge_grad_estimator(vv, vi, bary, img, index)
+        out.backward(gradient=w)
+        res[tag] = dict(index=index, depth=depth.detach(), bary=bary.detach(), img=img.detach(), grad_v=vv.grad, grad_attr=aa.grad)
+        del out, img, bary, depth
+    r, n = res["ref"], res["new"]
+    rep = {"against": "reference CUDA kernels (oracle/_ref), same tensors", "index_equal": bool(th.equal(r["index"], n["index"])),
+           "index_mismatches": int((r["index"] != n["index"]).sum()), "err_over_scale": {}, "tolerance": {}}
+    ok = rep["index_equal"]
+    for k, tol in (("depth", 1e-5), ("bary", 1e-5), ("img", 1e-5), ("grad_v", 5e-5), ("grad_attr", 5e-5)):
+        a, e = n[k], r[k]
+        scale = float(e.abs().max())
+        within = (a - e).abs() <= tol * e.abs() + tol * scale  # False for NaN / Inf
+        finite = bool(th.isfinite(a).all())
+        rep["err_over_scale"][k] = float(((a - e).abs().max() / max(scale, 1e-30))) if finite else float("nan")
+        rep["tolerance"][k] = tol
+        ok = ok and finite and bool(within.all())
+    rep["ok"] = bool(ok)
+    return rep
 
 
 # ------------------------------------------------------------------------------------------------
@@ -236,9 +298,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="new", choices=["new", "reference"])
-    ap.add_argument("--config", type=int, default=4)
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5])
+    ap.add_argument("--overdraw", action="store_true", help="two sheets, the second rotated 7 degrees (occlusion + intersections)")
+    ap.add_argument("--regions", type=int, default=3, help="how many times the K-step region is timed (median reported)")
+    ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "multimem"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational legs (cuda graph, with_loss, host paths)")
     args = ap.parse_args()
 
     # stdout carries exactly ONE line (the JSON): everything else that libraries print there (e.g. NCCL's
@@ -254,19 +320,23 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cfg = args.config
-    c = scenes.CONFIGS[cfg]
-    workload = (f"BASELINE config {cfg}: {2 * (c['nx'] - 1) * (c['ny'] - 1)} triangles, {c['W']}x{c['H']}, "
-                f"batch {c['N']} per GPU, {C_ATTR} vertex attributes + edge_grad, synthetic jittered grid mesh")
+    cfg, overdraw = args.config, args.overdraw
+    c, C = config_of(cfg)
+    F_total = c["F"] * (2 if overdraw else 1)
+    workload = (f"BASELINE config {cfg}{' overdraw-2' if overdraw else ''}: {F_total} triangles, {c['W']}x{c['H']}, "
+                f"batch {c['N']} per GPU, {C} vertex attributes + edge_grad, synthetic "
+                f"{'two-triangle demo scene' if cfg == 2 else 'jittered grid mesh'}")
+    metric = METRIC if (cfg == 4 and not overdraw) else METRIC_OTHER.format(cfg=cfg, od=" overdraw-2" if overdraw else "")
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r = run_reference_cpu(cfg, max(args.steps, 1), args.warmup)
-        line = {"metric": METRIC, "value": r["value"], "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
+        r = run_reference_cpu(cfg, max(args.steps, 1), args.warmup, overdraw=overdraw)
+        line = {"metric": metric, "value": r["value"], "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-                "config": {"workload": workload, "note": "reference CPU kernels on the host cores, bounded sample"},
+                "config": {"workload": workload, "note": "reference CPU kernels on the host cores, bounded sample: "
+                           + r["sample"] + " (Mpix/s is a rate, so the sample compares with the whole-step arm)"},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "transform_only")},
                 "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -280,29 +350,29 @@ def main():
     from drtk_b200 import _ops
     from drtk_b200 import dist as ddist
     import torch.distributed as dist
+    numa_cpus = ddist.bind_to_gpu_numa_node(local_rank)  # before the pinned buffers are allocated
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- inputs: pinned host copies (e2e) and device-resident copies (value) ----
-    v_h, vi_h, attr_h, _ = make_inputs(cfg, dev, seed_offset=100 * rank)
-    v_h, vi_h, attr_h = v_h.pin_memory(), vi_h.pin_memory(), attr_h.pin_memory()
+    v_h, vi_h, attr_h, _, _ = make_inputs(cfg, seed_offset=100 * rank, overdraw=overdraw)
+    v_h, attr_h = v_h.pin_memory(), attr_h.pin_memory()
     H, W, N = c["H"], c["W"], c["N"]
     npx_rank = N * H * W
     v_d = v_h.to(dev).requires_grad_(True)
     attr_d = attr_h.to(dev).requires_grad_(True)
-    vi_d = vi_h.to(dev)
-    w = th.rand((N, C_ATTR, H, W), device=dev, generator=th.Generator(device=dev).manual_seed(1000 * cfg + 2))
+    vi_d = vi_h.to(dev)  # topology: resident on the device, not part of a step's input
+    w = th.rand((N, C, H, W), device=dev, generator=th.Generator(device=dev).manual_seed(1000 * cfg + 2))
 
     # per-op CUDA-event timing hooks (events on the launching stream, inside the timed region)
     op_events = {k: [] for k in KERNELS}
     orig = {}
 
-    def wrap(name, key_fn):
+    def wrap(name, key):
         fn = getattr(_ops, name)
         orig[name] = fn
 
         def timed(*a, **kw):
-            key = key_fn(*a, **kw)
             e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
             e0.record()
             out = fn(*a, **kw)
@@ -313,72 +383,73 @@ def main():
         setattr(_ops, name, timed)
 
     timing_on = [False]
-    wrap("rasterize", lambda *a, **k: "rasterize")
-    wrap("render_forward", lambda *a, **k: "render_fwd")
-    wrap("render_backward", lambda *a, **k: "render_bwd")
-    wrap("interpolate_forward", lambda *a, **k: "interpolate_fwd")
-    wrap("interpolate_backward", lambda *a, **k: "interpolate_bwd")
-    wrap("edge_grad_backward_fused", lambda *a, **k: "edge_grad_bwd_fused")
+    for name, key in (("rasterize", "rasterize"), ("render_forward", "render_fwd"), ("render_backward", "render_bwd"),
+                      ("interpolate_forward", "interpolate_fwd"), ("interpolate_backward", "interpolate_bwd"),
+                      ("edge_grad_backward_fused", "edge_grad_bwd_fused")):
+        wrap(name, key)
+
+    # shared-parameter gradients: batch-summed (and all-reduced over ranks) per parameter, from post-accumulate-grad hooks
+    reducer = ddist.SharedGradReducer([v_d, attr_d], transport=args.transport)
+    exchange = {"on": True}
 
     def step_device():
         v_d.grad = None
         attr_d.grad = None
         pipeline(drtk_b200, v_d, vi_d, attr_d, w, H, W)
-        if world > 1:  # shared-parameter gradient exchange: one bucketed NCCL all-reduce
-            ddist.allreduce_shared_grads([v_d.grad, attr_d.grad])
+        return reducer.finish()
 
-    gv_h = th.empty_like(v_h).pin_memory()
-    ga_h = th.empty_like(attr_h).pin_memory()
-    h2d = v_h.numel() * 4 + attr_h.numel() * 4 + vi_h.numel() * 4
-    d2h = gv_h.numel() * 4 + ga_h.numel() * 4
+    main_s = th.cuda.current_stream(dev)
+    bucket_h = th.empty((reducer.total,), dtype=th.float32).pin_memory()
+    h2d = v_h.numel() * 4 + attr_h.numel() * 4
+    d2h = bucket_h.numel() * 4
 
     # End-to-end step through the public API with HOST buffers.  The copies are part of every step and inside
-    # the timed region, but pipelined the way a training loop's prefetcher does it: step k+1's inputs are
-    # copied (pinned host -> device, copy stream) while step k computes, and step k's results (grad_v,
-    # grad_attr) are read back on a second copy stream while step k+1 runs.  Double-buffered device inputs.
-    main = th.cuda.current_stream(dev)
+    # the timed region, pipelined the way a training loop's prefetcher does it: step k+1's inputs (v_pix, attr)
+    # are copied pinned host -> device on a copy stream while step k computes, and step k's result (the reduced
+    # [V,3] + [V,C] gradients) is read back on a second copy stream while step k+1 runs.  The device inputs are
+    # double-buffered; each buffer is a leaf with its own reducer hooks.
     s_in, s_out = th.cuda.Stream(dev), th.cuda.Stream(dev)
-    ebuf = [dict(v=th.empty_like(v_h, device=dev), a=th.empty_like(attr_h, device=dev),
-                 vi=th.empty_like(vi_h, device=dev), ready=th.cuda.Event(), free=th.cuda.Event()) for _ in range(2)]
+    ebuf = []
+    for _ in range(2):
+        bv = th.empty_like(v_h, device=dev).requires_grad_(True)
+        ba = th.empty_like(attr_h, device=dev).requires_grad_(True)
+        ebuf.append(dict(v=bv, a=ba, ready=th.cuda.Event(), free=th.cuda.Event(), out_done=th.cuda.Event(),
+                         red=ddist.SharedGradReducer([bv, ba], transport=args.transport)))
     estate = {"k": 0, "primed": False}
 
     def e2e_prefetch(k):
         b = ebuf[k % 2]
-        with th.cuda.stream(s_in):
+        with th.cuda.stream(s_in), th.no_grad():
             s_in.wait_event(b["free"])
             b["v"].copy_(v_h, non_blocking=True)
             b["a"].copy_(attr_h, non_blocking=True)
-            b["vi"].copy_(vi_h, non_blocking=True)
             b["ready"].record(s_in)
 
     def step_e2e():
         k = estate["k"]
         if not estate["primed"]:
             for b in ebuf:
-                b["free"].record(main)
+                b["free"].record(main_s)
             e2e_prefetch(k)
             estate["primed"] = True
         b = ebuf[k % 2]
-        main.wait_event(b["ready"])
+        main_s.wait_event(b["ready"])
+        main_s.wait_event(b["out_done"])  # this buffer's bucket was read out two steps ago
         e2e_prefetch(k + 1)
-        v = b["v"].detach().requires_grad_(True)
-        a = b["a"].detach().requires_grad_(True)
-        pipeline(drtk_b200, v, b["vi"], a, w, H, W)
-        gv, ga = v.grad, a.grad
-        if world > 1:
-            ddist.allreduce_shared_grads([gv, ga])
-        b["free"].record(main)
-        s_out.wait_stream(main)
+        b["v"].grad = None
+        b["a"].grad = None
+        pipeline(drtk_b200, b["v"], vi_d, b["a"], w, H, W)
+        b["red"].finish()
+        b["free"].record(main_s)
+        s_out.wait_stream(main_s)
         with th.cuda.stream(s_out):
-            gv_h.copy_(gv, non_blocking=True)
-            ga_h.copy_(ga, non_blocking=True)
-        for t in (gv, ga):
-            t.record_stream(s_out)
+            bucket_h.copy_(b["red"].bucket, non_blocking=True)
+            b["out_done"].record(s_out)
         estate["k"] = k + 1
 
     def e2e_finish():  # the last step's read-back (and the one prefetch in flight) end inside the timed region
-        main.wait_stream(s_out)
-        main.wait_stream(s_in)
+        main_s.wait_stream(s_out)
+        main_s.wait_stream(s_in)
 
     def barrier():
         if world > 1:
@@ -403,23 +474,34 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
+    R = max(args.regions, 1)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_device()
     timing_on[0] = True
-    ms_step = timed_region(step_device, args.steps)
+    dev_runs = [timed_region(step_device, args.steps) for _ in range(R)]
     timing_on[0] = False
+    ms_step = statistics.median(dev_runs)
 
     for _ in range(3):
         step_e2e()
     e2e_finish()
-    # host-side interference (another tenant on the box's PCIe root / memory controller) once doubled this number on
-    # an otherwise healthy run: the K-step region is timed twice and the faster pass is reported, both are listed
-    e2e_runs = [timed_region(step_e2e, args.steps, e2e_finish) for _ in range(2)]
-    ms_e2e = min(e2e_runs)
+    e2e_runs = [timed_region(step_e2e, args.steps, e2e_finish) for _ in range(R)]
+    ms_e2e = statistics.median(e2e_runs)
     clocks = sampler.stop() if sampler else None
 
-    # host <-> device copy bandwidth of this box (context for e2e: 62 MB cross PCIe every step)
+    # the exchange alone (batch sums + all-reduce of both parameters on gradients already in place)
+    def exchange_only():
+        reducer._make_hook(0)(v_d)
+        reducer._make_hook(1)(attr_d)
+        reducer.finish()
+    for _ in range(3):
+        exchange_only()
+    ms_exchange = timed_region(exchange_only, 20)
+    for b in ebuf:
+        b["red"].close()
+
+    # host <-> device copy bandwidth of this box (context for e2e)
     pcie = None
     if rank == 0:
         big_h = th.empty(64 << 20, dtype=th.uint8).pin_memory()
@@ -445,18 +527,18 @@ def main():
     roofline, breakdown = None, {}
     if per_op:
         for k, ms in per_op.items():
-            gb = ALGO_BYTES_PER_PX[k](C_ATTR) * npx_rank / 1e9
+            gb = ALGO_BYTES_PER_PX[k](C) * npx_rank / 1e9
             breakdown[k] = {"ms": round(ms, 4), "algo_GB": round(gb, 4), "GBps": round(gb / (ms * 1e-3), 1),
                             "frac_of_peak": round(gb / (ms * 1e-3) / peak, 4)}
         dom = max(per_op, key=per_op.get)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and cfg == 4 and not overdraw:
             with open(tp) as f:
-                traffic = json.load(f).get(dom)  # ncu dram bytes per launch of the dominant kernel
+                traffic = json.load(f).get(dom)  # ncu dram bytes per launch of the dominant kernel (config 4 capture)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": breakdown[dom]["GBps"], "peak": peak, "unit": "GB/s",
                     "frac": breakdown[dom]["frac_of_peak"], "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX[dom](C_ATTR) * npx_rank}
+                    "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX[dom](C) * npx_rank}
 
     if rank != 0:
         if world > 1:
@@ -464,41 +546,59 @@ def main():
         return 0
 
     line = {
-        "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+        "metric": metric, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "new",
-        "config": {"workload": workload, "global_batch": N * world, "parallelism": f"dp{world} (batch sharded, shared-grad allreduce)",
-                   "l2": "per-step working set ~10 GB >> 126 MB L2 (inputs larger than L2, no explicit flush)",
-                   "loss": "none materialised: backward seeded with cotangent w (= gradient of the linear loss (img*w).sum()), no torch kernels on big tensors inside the step"},
+        "ms_per_step_regions": [round(x, 4) for x in dev_runs], "ms_per_step_min": min(dev_runs),
+        "config": {"workload": workload, "global_batch": N * world,
+                   "parallelism": f"dp{world} (batch sharded; shared-parameter gradients batch-summed"
+                                  + (f" and all-reduced, transport {reducer.transport})" if world > 1 else ")"),
+                   "l2": "per-step working set >> 126 MB L2 at configs 3-5 (inputs larger than L2, no explicit flush)",
+                   "loss": "none materialised: backward seeded with cotangent w (= gradient of the linear loss (img*w).sum()); see with_loss",
+                   "regions": f"{R} timed regions of {args.steps} steps; ms_per_step / value = median region"},
         "e2e": {"value": e2e_value, "unit": "Mpix/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step_runs": [round(x, 4) for x in e2e_runs],
-                "note": "pinned host v_pix/attr/vi copied in, grad_v + grad_attr (the step's result) copied out, every step, inside the timed region; copies double-buffered on side streams (prefetch of step k+1 / read-back of step k overlap compute)"},
-        "gpu_launches": sum(KERNELS.values()) * args.steps,
+                "ms_per_step_regions": [round(x, 4) for x in e2e_runs],
+                "note": "pinned host v_pix + attr copied in, the step's result (gradients summed over the batch"
+                        + (" and ranks" if world > 1 else "") + ": [V,3] + [V,C]) copied out, every step, inside the timed "
+                        "region; copies double-buffered on side streams; topology (vi) stays resident; median of the regions"},
+        "gpu_launches": (sum(KERNELS.values()) + REDUCE_KERNELS) * args.steps,
         "clocks": clocks, "roofline": roofline, "per_op": breakdown, "pcie": pcie,
-        "pipeline_algorithmic_GB_per_step": round(sum(ALGO_BYTES_PER_PX[k](C_ATTR) for k in KERNELS) * npx_rank / 1e9, 3),
+        "shared_grad_exchange": {"transport": reducer.transport, "ms_isolated": round(ms_exchange, 4),
+                                 "bytes": reducer.total * 4, "fallback_reason": getattr(reducer, "fallback_reason", None)},
+        "numa_cpus": (f"{numa_cpus[0]}-{numa_cpus[-1]} ({len(numa_cpus)})" if numa_cpus else None),
+        "pipeline_algorithmic_GB_per_step": round(sum(ALGO_BYTES_PER_PX[k](C) for k in KERNELS) * npx_rank / 1e9, 3),
     }
 
-    # ---- reference CUDA kernels on the same tensors (context for the >=4x target; not the arm) ----
+    # ---- reference CUDA kernels on the same tensors (context for the >=4x target; not the arm) + parity of the timed tensors ----
+    R_api = None
     if world == 1 and not args.no_ref_cuda:
         try:
-            from oracle import ref as R
-            if R.available():
+            from oracle import ref as R_api_mod
+            if R_api_mod.available():
+                R_api = R_api_mod
+
                 def step_ref():
                     v_d.grad = None; attr_d.grad = None
-                    pipeline(R, v_d, vi_d, attr_d, w, H, W)
+                    pipeline(R_api, v_d, vi_d, attr_d, w, H, W)
                 for _ in range(3):
                     step_ref()
-                ms_ref = timed_region(step_ref, args.steps)
+                ref_runs = [timed_region(step_ref, args.steps) for _ in range(R)]
+                ms_ref = statistics.median(ref_runs)
                 line["reference_cuda"] = {"value": total_px / (ms_ref * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": ms_ref,
-                                          "note": "unmodified reference CUDA kernels (oracle/_ref, sm_100 build), same tensors, same cotangent"}
+                                          "ms_per_step_regions": [round(x, 4) for x in ref_runs],
+                                          "note": "unmodified reference CUDA kernels (oracle/_ref, sm_100 build), same tensors, same cotangent, no batch sum"}
+                line["parity_check"] = compare_with_reference(drtk_b200, R_api, v_d, vi_d, attr_d, w, H, W)
         except Exception as ex:  # noqa: BLE001
             line["reference_cuda"] = {"unavailable": repr(ex)[:200]}
+    v_d.grad = None
+    attr_d.grad = None
+    reducer.close()
 
-    # ---- the same step captured once in a CUDA graph and replayed (informational: launch + Python overhead out) ----
-    if world == 1:
+    if world == 1 and not args.no_extras:
+        for name, fn in orig.items():  # drop the per-op event hooks
+            setattr(_ops, name, fn)
+        # ---- the same step captured once in a CUDA graph and replayed (informational: launch + Python overhead out) ----
         try:
-            for name, fn in orig.items():  # drop the per-op event hooks: no event timing inside a capture
-                setattr(_ops, name, fn)
             gv_s = v_d.detach().clone().requires_grad_(True)
             ga_s = attr_d.detach().clone().requires_grad_(True)
 
@@ -507,14 +607,15 @@ def main():
                 _, bary = drtk_b200.render(gv_s, vi_d, index)
                 img = drtk_b200.interpolate(ga_s, vi_d, index, bary)
                 img = drtk_b200.edge_grad_estimator(gv_s, vi_d, bary, img, index)
-                return th.autograd.grad(img, (gv_s, ga_s), grad_outputs=w)
+                gvv, gaa = th.autograd.grad(img, (gv_s, ga_s), grad_outputs=w)
+                return ddist.batch_sum(gvv), ddist.batch_sum(gaa)
 
             side = th.cuda.Stream(dev)
-            side.wait_stream(main)
+            side.wait_stream(main_s)
             with th.cuda.stream(side):
                 for _ in range(2):
                     graph_step()
-            main.wait_stream(side)
+            main_s.wait_stream(side)
             graph = th.cuda.CUDAGraph()
             with th.cuda.graph(graph):
                 graph_out = graph_step()
@@ -527,8 +628,78 @@ def main():
         except Exception as ex:  # noqa: BLE001
             line["cuda_graph"] = {"unavailable": repr(ex)[:200]}
 
+        # ---- SURVEY 8(d)'s literal pipeline: loss = (img * w).sum(); loss.backward()  (torch's own kernels on the big tensors) ----
+        try:
+            def loss_step(api):
+                v_d.grad = None; attr_d.grad = None
+                index = api.rasterize(v_d, vi_d, H, W)
+                _, bary = api.render(v_d, vi_d, index)
+                img = api.interpolate(attr_d, vi_d, index, bary)
+                img = api.edge_grad_estimator(v_d, vi_d, bary, img, index)
+                (img * w).sum().backward()
+            for _ in range(2):
+                loss_step(drtk_b200)
+            ms_l = timed_region(lambda: loss_step(drtk_b200), args.steps)
+            wl = {"ms_per_step": ms_l, "value": total_px / (ms_l * 1e-3) / 1e6, "unit": "Mpix/s",
+                  "note": "informational: the loss materialised with torch ops ((img*w).sum().backward()) inside the step, both arms"}
+            if R_api is not None:
+                for _ in range(2):
+                    loss_step(R_api)
+                ms_lr = timed_region(lambda: loss_step(R_api), args.steps)
+                wl["reference_cuda_ms_per_step"] = ms_lr
+            line["with_loss"] = wl
+        except Exception as ex:  # noqa: BLE001
+            line["with_loss"] = {"unavailable": repr(ex)[:200]}
+
+        # ---- host paths: wall-clock per step of the Python host (ctypes) vs the dispatcher ops (torch_shim) vs the reference ----
+        try:
+            from drtk_b200 import torch_ops
+
+            class _Shim:  # the public functions, forced through torch.ops.drtk_b200_*_ext
+                @staticmethod
+                def rasterize(v, vi_, h, w_):
+                    return torch_ops.rasterize(v, vi_[None].expand(v.shape[0], -1, -1) if vi_.ndim == 2 else vi_, h, w_)[1]
+
+                @staticmethod
+                def render(v, vi_, index):
+                    d, b = torch_ops.render(v, vi_[None].expand(v.shape[0], -1, -1) if vi_.ndim == 2 else vi_, index)
+                    return d, b
+
+                @staticmethod
+                def interpolate(a, vi_, index, bary):
+                    return torch_ops.interpolate(a, vi_[None].expand(a.shape[0], -1, -1) if vi_.ndim == 2 else vi_, index, bary)
+
+                @staticmethod
+                def edge_grad_estimator(v, vi_, bary, img, index):
+                    return torch_ops.edge_grad_estimator_fused(v, vi_[None].expand(v.shape[0], -1, -1) if vi_.ndim == 2 else vi_,
+                                                               bary.detach(), img, index)
+
+            def wall(api, iters):
+                def one():
+                    v_d.grad = None; attr_d.grad = None
+                    pipeline(api, v_d, vi_d, attr_d, w, H, W)
+                for _ in range(3):
+                    one()
+                th.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(iters):
+                    one()
+                t_issue = time.perf_counter() - t0
+                th.cuda.synchronize()
+                return {"issue_us_per_step": round(t_issue / iters * 1e6, 1), "wall_us_per_step": round((time.perf_counter() - t0) / iters * 1e6, 1)}
+            iters = 50 if cfg <= 3 else 10
+            hp = {"ctypes_python_autograd": wall(drtk_b200, iters)}
+            if torch_ops.available():
+                hp["dispatcher_ops_cpp_autograd"] = wall(_Shim, iters)
+            if R_api is not None:
+                hp["reference_cuda"] = wall(R_api, iters)
+            hp["note"] = "issue = host time to enqueue one forward+backward step; wall = including the device work"
+            line["host_paths"] = hp
+        except Exception as ex:  # noqa: BLE001
+            line["host_paths"] = {"unavailable": repr(ex)[:200]}
+
     if world == 1 and not args.no_cpu_baseline:
-        r = run_reference_cpu(cfg, steps=3, warmup=1)
+        r = run_reference_cpu(cfg, steps=3, warmup=1, overdraw=overdraw)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "transform_only")}
     emit(line)
     if world > 1:

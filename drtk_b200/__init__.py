@@ -16,6 +16,7 @@ without the native library every op raises.
 import sys
 
 from . import _lib
+from . import torch_ops  # noqa: F401
 from ._lib import build  # noqa: F401
 from .edge_grad_estimator import edge_grad_estimator  # noqa: F401
 from .grid_scatter import grid_scatter, grid_scatter_ref  # noqa: F401
@@ -33,7 +34,7 @@ __all__ = [
     "rasterize", "rasterize_with_depth", "render", "interpolate", "interpolation_matrix", "interpolation_normal_matrix",
     "edge_grad_estimator", "render_ref", "interpolate_ref", "grid_scatter", "grid_scatter_ref", "mipmap_grid_sample",
     "mipmap_grid_sample_ref", "screen_space_uv_derivative",
-    "transform", "transform_with_v_cam", "utils", "build", "install_as_drtk", "native_library_path",
+    "transform", "transform_with_v_cam", "utils", "build", "torch_ops", "install_as_drtk", "native_library_path",
 ]
 
 

@@ -30,7 +30,7 @@ from typing import Callable, Optional
 
 import torch as th
 
-from . import _ops
+from . import _ops, torch_ops
 
 
 class _VPixImgConduit(th.autograd.Function):
@@ -119,6 +119,15 @@ def edge_grad_estimator(
     """
     if vi.ndim == 2:
         vi = vi[None, ...].expand(v_pix.shape[0], -1, -1)
+    if torch_ops.enabled():  # dispatcher ops (C++ autograd functions); the zero-cost conduit stays a Python node
+        if v_pix_img_hook is None:
+            return torch_ops.edge_grad_estimator_fused(v_pix, vi, bary_img.detach(), img, index_img, max_dp_dr)
+        v_pix_c, bary_c = _ops.autocast_f32(v_pix, bary_img)
+        v_pix_img = _VPixImgConduit.apply(v_pix_c, vi, index_img, bary_c.detach())
+        out = torch_ops.edge_grad_estimator(v_pix, v_pix_img, vi, img, index_img, max_dp_dr)
+        if v_pix_img.requires_grad:
+            v_pix_img.register_hook(v_pix_img_hook)
+        return out
     v_pix, bary_img, img = _ops.autocast_f32(v_pix, bary_img, img)  # (src/edge_grad/edge_grad_module.cpp:172-196)
     if v_pix_img_hook is None:
         return _EdgeGradFusedFn.apply(v_pix, vi, bary_img.detach(), img, index_img, max_dp_dr)

@@ -6,7 +6,7 @@ Autograd contract of the reference's InterpolateFunction
 """
 import torch as th
 
-from . import _ops
+from . import _ops, torch_ops
 
 
 class _InterpolateFn(th.autograd.Function):
@@ -45,6 +45,8 @@ def interpolate(vert_attributes: th.Tensor, vi: th.Tensor, index_img: th.Tensor,
     """
     if vi.ndim == 2:
         vi = vi[None].expand(vert_attributes.shape[0], -1, -1)
+    if torch_ops.enabled():
+        return torch_ops.interpolate(vert_attributes, vi, index_img, bary_img)
     vert_attributes, bary_img = _ops.autocast_f32(vert_attributes, bary_img)
     return _InterpolateFn.apply(vert_attributes, vi, index_img, bary_img)
 

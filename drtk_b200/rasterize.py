@@ -9,7 +9,7 @@ from typing import Tuple
 
 import torch as th
 
-from . import _ops
+from . import _ops, torch_ops
 
 
 @th.compiler.disable
@@ -22,6 +22,8 @@ def rasterize(v: th.Tensor, vi: th.Tensor, height: int, width: int, wireframe: b
     """
     if vi.ndim == 2:
         vi = vi[None].expand(v.shape[0], -1, -1)
+    if torch_ops.enabled():
+        return torch_ops.rasterize(v, vi, height, width, wireframe)[1]
     with th.no_grad():
         (v,) = _ops.autocast_f32(v.detach())
         _, index_img = _ops.rasterize(v, vi, height, width, wireframe)
@@ -36,6 +38,9 @@ def rasterize_with_depth(
     empty and is not differentiable (use :func:`drtk_b200.render` for differentiable depth)."""
     if vi.ndim == 2:
         vi = vi[None].expand(v.shape[0], -1, -1)
+    if torch_ops.enabled():
+        depth_img, index_img = torch_ops.rasterize(v, vi, height, width, wireframe)
+        return depth_img, index_img
     with th.no_grad():
         (v,) = _ops.autocast_f32(v.detach())
         depth_img, index_img = _ops.rasterize(v, vi, height, width, wireframe)

@@ -7,7 +7,7 @@ from typing import Tuple
 
 import torch as th
 
-from . import _ops
+from . import _ops, torch_ops
 
 
 class _RenderFn(th.autograd.Function):
@@ -38,6 +38,9 @@ def render(v: th.Tensor, vi: th.Tensor, index_img: th.Tensor) -> Tuple[th.Tensor
     """
     if vi.ndim == 2:
         vi = vi[None].expand(v.shape[0], -1, -1)
+    if torch_ops.enabled():
+        depth_img, bary_img = torch_ops.render(v, vi, index_img)
+        return depth_img, bary_img
     (v,) = _ops.autocast_f32(v)
     return _RenderFn.apply(v, vi, index_img)
 

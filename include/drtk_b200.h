@@ -286,6 +286,30 @@ int drtk_b200_grid_scatter_backward(const float* grad_out, const int64_t* grad_o
                                     float* grad_grid, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Multi-GPU support: the batch shards over ranks with no data-path collective; the only
+ * exchange is the gradient of parameters SHARED by all batch items.  The reference has no counterpart (its
+ * users get the per-rank batch sum from autograd's expand-backward and the cross-rank sum from DDP / NCCL).
+ *
+ * batch_sum: out[m] = sum_n x[n * batch_stride + m], m < M  -- the local batch reduction, written straight into the
+ *   communication bucket.
+ * batch_sum_allreduce: the same followed, IN THE SAME KERNEL, by the sum over all ranks through NVSwitch multicast
+ *   memory (multimem.red.add.f32 into every rank's copy of the bucket, flag barriers over peer memory); no NCCL
+ *   call.  bucket_local / bucket_multicast: this rank's copy and the multicast address of a symmetric buffer of M
+ *   floats; peer_flags[r]: rank r's flag array (world * drtk_b200_batch_sum_allreduce_grid() zero-initialised
+ *   uint32) as mapped into this process; epoch: 3 * (number of earlier calls on these flags).  Every rank must
+ *   make the same sequence of calls.  On return (stream order) bucket_local holds the sum over ranks.
+ *   timeout_flag (device int, may be NULL) is set to 1 when a peer did not arrive within ~2 s (the wait then gives
+ *   up instead of hanging the GPU; the bucket is invalid).
+ * ------------------------------------------------------------------------------------- */
+int drtk_b200_batch_sum(const float* x, int64_t N, int64_t M, int64_t batch_stride, float* out, void* stream);
+
+int drtk_b200_batch_sum_allreduce_grid(void);
+
+int drtk_b200_batch_sum_allreduce(const float* x, int64_t N, int64_t M, int64_t batch_stride, float* bucket_local,
+                                  float* bucket_multicast, void* const* peer_flags, int rank, int world,
+                                  uint32_t epoch, int* timeout_flag, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * float64 dispatch of the six hot-path launchers (the reference instantiates every kernel for float and double,
  * src/include/kernel_utils.h:47-57).  Same arguments and contracts as the float entry points above, with double
  * data; no workspace except the packed 64-bit z-buffer of the rasteriser; `rasterize_f64` still writes a float

@@ -56,3 +56,30 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.drtk_b200_rasterize(None, s3, None, s3, 1, 1, 1, -8, 8, 0, 0, None, None, None, 0, None) == -1
     # empty problems are a successful no-op
     assert lib.drtk_b200_render_forward(None, s3, None, s3, None, s3, 0, 0, 0, 0, 0, None, None, None) == 0
+
+
+def test_dispatcher_boundary_registers_the_reference_schemas():
+    """csrc/torch_shim.cpp: the reference's op schemas under drtk_b200_*_ext, with Autograd / Autocast / CUDA kernels
+    and (by design) no CPU kernel."""
+    import torch
+    from drtk_b200 import torch_ops
+    torch_ops.build()
+    torch_ops.load()
+    want = {
+        "drtk_b200_rasterize_ext::rasterize": "(Tensor v, Tensor vi, int height, int width, bool wireframe) -> Tensor[]",
+        "drtk_b200_render_ext::render": "(Tensor v, Tensor vi, Tensor index_img) -> Tensor[]",
+        "drtk_b200_interpolate_ext::interpolate": "(Tensor vert_attributes, Tensor vi, Tensor index_img, Tensor bary_img) -> Tensor",
+        "drtk_b200_edge_grad_ext::edge_grad_estimator":
+            "(Tensor v_pix, Tensor v_pix_img, Tensor vi, Tensor img, Tensor index_img, float max_dp_dr=10000.) -> Tensor",
+    }
+    for name, sig in want.items():
+        ns, op = name.split("::")
+        schema = str(getattr(getattr(torch.ops, ns), op).default._schema)
+        assert schema == name + sig, schema
+        for key in ("CUDA", "Autograd", "AutocastCUDA"):
+            assert torch._C._dispatch_has_kernel_for_dispatch_key(name, key), (name, key)
+        assert not torch._C._dispatch_has_kernel_for_dispatch_key(name, "CPU")
+    # a CPU tensor fails loudly (no CPU fallback)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.drtk_b200_render_ext.render(torch.zeros(1, 3, 3), torch.zeros(1, 1, 3, dtype=torch.int32),
+                                              torch.zeros(1, 4, 4, dtype=torch.int32))

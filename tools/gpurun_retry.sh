@@ -7,7 +7,8 @@ T=$1; shift
 for i in $(seq 1 40); do
   /usr/local/graft/bin/gpurun $GP --timeout $T -- "$@"
   rc=$?
-  if [ $rc -ne 3 ]; then exit $rc; fi
-  sleep 120
+  # 3 = busy (nothing charged); 2 = refused, e.g. an abandoned earlier request still holds the one-call slot
+  if [ $rc -ne 3 ] && [ $rc -ne 2 ]; then exit $rc; fi
+  sleep 90
 done
 exit 3

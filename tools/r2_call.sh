@@ -7,6 +7,8 @@ if [ $rc -ne 0 ]; then export DRTK_B200_RASTER_V1=1; echo "SANITY rc=$rc -> fall
 tail -25 gpurun_out/${T}_sanity.txt
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/${T}_pytest.txt
 tail -5 gpurun_out/${T}_pytest.txt
+DRTK_B200_DISPATCH=torch timeout 600 python -m pytest tests/test_gpu_parity.py -q -k "pipeline or autograd or autocast or drop_in or graph or corner or empty_face" 2>&1 | tail -15 > gpurun_out/${T}_pytest_torchops.txt
+tail -5 gpurun_out/${T}_pytest_torchops.txt
 timeout 200 python tools/opbench.py --ops rasterize,interp_bwd,interp_bwd_b,interp_bwd_v,edge_fused,render_bwd --dump /tmp/a.pt > gpurun_out/${T}_opbench.txt 2>&1
 DRTK_B200_MERGED=1 timeout 200 python tools/opbench.py --ops interp_bwd,interp_bwd_b --cmp /tmp/a.pt >> gpurun_out/${T}_opbench.txt 2>&1
 DRTK_B200_RASTER_V1=1 timeout 200 python tools/opbench.py --ops rasterize --cmp /tmp/a.pt >> gpurun_out/${T}_opbench.txt 2>&1
