@@ -9,7 +9,8 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdrtk_b200.so")
+# DRTK_B200_LIB: developer override for A/B runs of kernel variants (tools/build_variants.sh)
+LIB_PATH = os.environ.get("DRTK_B200_LIB") or os.path.join(_HERE, "libdrtk_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 ABI_VERSION = 2  # DRTK_B200_ABI_VERSION of include/drtk_b200.h

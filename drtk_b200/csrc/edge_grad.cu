@@ -72,7 +72,9 @@ struct TableFetch {
   }
 };
 
-// pix_in_tri (:30-70): top-left rule with plain (non-canonical) edge functions
+// pix_in_tri (:30-70): top-left rule with plain (non-canonical) edge functions.  The top/left classification of the
+// edges is only evaluated for a sample that lies exactly ON an edge (some b == 0); strictly inside / outside -- all
+// but a handful of samples -- is decided by the three signs.
 __device__ __forceinline__ bool pix_in_tri(const Tri2& t, int x, int y) {
   if (t.den == 0.f) return false;
   const float px = (float)x, py = (float)y;
@@ -83,6 +85,7 @@ __device__ __forceinline__ bool pix_in_tri(const Tri2& t, int x, int y) {
   const float b1 = mul_rn(diff_of_products(q0x, t.v02y, q0y, t.v02x), s);
   const float b2 = mul_rn(diff_of_products(q0y, t.v01x, q0x, t.v01y), s);
   if (!(b0 >= 0.f && b1 >= 0.f && b2 >= 0.f)) return false;
+  if (fminf(fminf(b0, b1), b2) > 0.f) return true;
   bool tl0, tl1, tl2;
   if (t.den > 0.f) {
     tl0 = (t.v12y < 0.f) || (t.v12y == 0.f && t.v12x > 0.f);
@@ -456,7 +459,7 @@ static int edge_launch(const float* v_pix, const int64_t* v_strides, const float
   };
   const int64_t npix = N * H * W;
   if (npix == 0) return zero_grad_v();
-  if (!v_pix || !img || !index_img || !vi || !grad_output || (!fused && !grad_v_pix_img) || (fused && !bary_img))
+  if (!v_pix || !img || !index_img || (!vi && F > 0) || !grad_output || (!fused && !grad_v_pix_img) || (fused && !bary_img))
     return DRTK_B200_EINVAL;
   if (H > (1 << 30) || W > (1 << 30)) return DRTK_B200_EUNSUPPORTED;
   if (N > kMaxBatchPerLaunch) {  // batch index rides on gridDim.y/z: slices of the batch (the workspace is reused)

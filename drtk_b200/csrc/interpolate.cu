@@ -879,221 +879,11 @@ interp_bwd_quad_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
   }
 }
 
-// ==========================================================================================================
-// EXPERIMENT (branch exp/merged-walker, switched on with DRTK_B200_MERGED=1; untested on hardware when written):
-// phase B merged into the run walkers.  A walker quad (4 lanes x 4 channels, 16 pixels) that crosses a run boundary
-// already fetches the run's packed vertex ids; here each lane also loads ITS 16-byte quarter of the three attribute
-// rows (one coalesced 64-B row per (run, vertex) instead of phase B's per-pixel-pair gathers), every pixel's bary
-// gradient is 12 FMAs per lane + a 4-lane butterfly, and the tile is read from shared memory once.  The results go
-// back into the stage's own bary planes (each walker overwrites only the four pixels it has just consumed) and
-// the team writes them out as coalesced rows.  The two teams take alternate tiles (one pipeline stage each).
-// Needs: C <= 16 (one channel pass), C % 4 == 0, dense attribute rows (AVEC), bary gradient requested.
-// ==========================================================================================================
-template <int TP, bool NEED_VERT>
-__device__ __forceinline__ void walk_runs_merged(const float* __restrict__ gp, const int* __restrict__ ip, float* bp,
-                                                 float* vg, const int4* __restrict__ tab, unsigned Cs,
-                                                 const float* __restrict__ arow, unsigned rs, int off_mask, int q) {
-  int cur = -1;
-  int4 t = make_int4(0, 0, 0, 0);
-  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
-  float4 R0 = make_float4(0.f, 0.f, 0.f, 0.f), R1 = R0, R2 = R0;  // this lane's four channels of the run's three rows
-  const float on = off_mask ? 0.f : 1.f;                          // idle lanes (4q >= C) add nothing to the dot products
-#pragma unroll 1
-  for (int x = 0; x < kQSeg; x += 4) {
-    const float4 G0 = *reinterpret_cast<const float4*>(gp + x);
-    const float4 G1 = *reinterpret_cast<const float4*>(gp + TP + x);
-    const float4 G2 = *reinterpret_cast<const float4*>(gp + 2 * TP + x);
-    const float4 G3 = *reinterpret_cast<const float4*>(gp + 3 * TP + x);
-    const int4 iq = *reinterpret_cast<const int4*>(ip + x);
-    float4 p0q = make_float4(0.f, 0.f, 0.f, 0.f), p1q = p0q, p2q = p0q;
-    if (NEED_VERT) {
-      p0q = *reinterpret_cast<const float4*>(bp + x);
-      p1q = *reinterpret_cast<const float4*>(bp + TP + x);
-      p2q = *reinterpret_cast<const float4*>(bp + 2 * TP + x);
-    }
-    const int ids[4] = {iq.x, iq.y, iq.z, iq.w};
-    const float g[4][4] = {{G0.x, G0.y, G0.z, G0.w}, {G1.x, G1.y, G1.z, G1.w},
-                           {G2.x, G2.y, G2.z, G2.w}, {G3.x, G3.y, G3.z, G3.w}};  // [channel][pixel]
-    const float q0[4] = {p0q.x, p0q.y, p0q.z, p0q.w};
-    const float q1[4] = {p1q.x, p1q.y, p1q.z, p1q.w};
-    const float q2[4] = {p2q.x, p2q.y, p2q.z, p2q.w};
-    // the packed vertex ids of the runs that START inside this group are requested up front (predicated: ~1 in 4)
-    int4 tn[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int prev = j ? ids[j - 1] : cur;
-      tn[j] = make_int4(0, 0, 0, 0);
-      if (ids[j] != prev) tn[j] = tab[max(ids[j], 0)];  // empty pixels read triangle 0 harmlessly
-    }
-    float d[3][4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int id = ids[j];
-      if (id != cur) {  // run boundary (uniform across the four lanes of the walker)
-        if (NEED_VERT && (cur | off_mask) >= 0) {
-          red_add_v4(vg + (unsigned)t.x * Cs, a0[0], a0[1], a0[2], a0[3]);
-          red_add_v4(vg + (unsigned)t.y * Cs, a1[0], a1[1], a1[2], a1[3]);
-          red_add_v4(vg + (unsigned)t.z * Cs, a2[0], a2[1], a2[2], a2[3]);
-        }
-        t = tn[j];
-        R0 = *reinterpret_cast<const float4*>(arow + (unsigned)t.x * rs);
-        R1 = *reinterpret_cast<const float4*>(arow + (unsigned)t.y * rs);
-        R2 = *reinterpret_cast<const float4*>(arow + (unsigned)t.z * rs);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) a0[k] = a1[k] = a2[k] = 0.f;
-        cur = id;
-      }
-      if (NEED_VERT) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          a0[k] = fmaf(g[k][j], q0[j], a0[k]);
-          a1[k] = fmaf(g[k][j], q1[j], a1[k]);
-          a2[k] = fmaf(g[k][j], q2[j], a2[k]);
-        }
-      }
-      // bary gradient of pixel j: this lane's four channels, then the butterfly over the walker's four lanes
-      const float live = (id >= 0) ? on : 0.f;  // (:282-297) zeros where empty
-      float e0 = fmaf(g[3][j], R0.w, fmaf(g[2][j], R0.z, fmaf(g[1][j], R0.y, g[0][j] * R0.x))) * live;
-      float e1 = fmaf(g[3][j], R1.w, fmaf(g[2][j], R1.z, fmaf(g[1][j], R1.y, g[0][j] * R1.x))) * live;
-      float e2 = fmaf(g[3][j], R2.w, fmaf(g[2][j], R2.z, fmaf(g[1][j], R2.y, g[0][j] * R2.x))) * live;
-      e0 += __shfl_xor_sync(0xffffffffu, e0, 1); e1 += __shfl_xor_sync(0xffffffffu, e1, 1); e2 += __shfl_xor_sync(0xffffffffu, e2, 1);
-      e0 += __shfl_xor_sync(0xffffffffu, e0, 2); e1 += __shfl_xor_sync(0xffffffffu, e1, 2); e2 += __shfl_xor_sync(0xffffffffu, e2, 2);
-      d[0][j] = e0; d[1][j] = e1; d[2][j] = e2;
-    }
-    // lane q < 3 owns plane q of the output; the four pixels of this group were consumed above
-    if (q < 3) {
-      const float4 o = q == 0 ? make_float4(d[0][0], d[0][1], d[0][2], d[0][3])
-                     : q == 1 ? make_float4(d[1][0], d[1][1], d[1][2], d[1][3])
-                              : make_float4(d[2][0], d[2][1], d[2][2], d[2][3]);
-      *reinterpret_cast<float4*>(bp + q * TP + x) = o;
-    }
-  }
-  if (NEED_VERT && (cur | off_mask) >= 0) {
-    red_add_v4(vg + (unsigned)t.x * Cs, a0[0], a0[1], a0[2], a0[3]);
-    red_add_v4(vg + (unsigned)t.y * Cs, a1[0], a1[1], a1[2], a1[3]);
-    red_add_v4(vg + (unsigned)t.z * Cs, a2[0], a2[1], a2[2], a2[3]);
-  }
-}
-
-template <int TP, bool NEED_VERT>
-__global__ void __launch_bounds__(32 * (TP / kQUnit * 2 + kQProducers), (TP <= 512) ? 2 : 1)
-interp_bwd_merged_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __restrict__ bary_grad,
-                         const int4* __restrict__ tab, int tab_img_stride, int tiles_per_img, int num_tiles) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  QSmem<TP>& S = *reinterpret_cast<QSmem<TP>*>(smem_raw);
-  constexpr int TEAM = TP / kQUnit;    // warps per team; team k consumes the tiles with sequence number = k mod 2
-  constexpr int CONSUMERS = 2 * TEAM;
-  const InterpArgs& a = b.f;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int HW = a.H * a.W;
-  if (tid == 0) {
-    for (int s = 0; s < kBwdStages; ++s) {
-      mbar_init(reinterpret_cast<uint64_t*>(&S.full[s]), kQProducers);
-      mbar_init(reinterpret_cast<uint64_t*>(&S.empty[s]), TEAM);  // stage s belongs to team s
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-  const int warp_role = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  auto decode = [&](int t, int& n, int& tl) {
-    n = t / tiles_per_img;
-    tl = t - n * tiles_per_img;
-  };
-  const int nc = a.C;  // <= kQCh
-
-  if (warp_role >= CONSUMERS) {  // ---- producer warps (as in interp_bwd_quad_kernel, one channel pass) ----
-    if (lane == 0) {
-      const int pw = warp_role - CONSUMERS;
-      int item = 0;
-      for (int t0 = blockIdx.x * kQChunk; t0 < num_tiles; t0 += gridDim.x * kQChunk)
-      for (int tile = t0; tile < min(t0 + kQChunk, num_tiles); ++tile, ++item) {
-        int n, tl;
-        decode(tile, n, tl);
-        const int p0 = tl * TP;
-        const uint32_t bytes = (uint32_t)min(TP, HW - p0) * 4u;
-        const int s = item & 1;
-        if (item >= kBwdStages)
-          mbar_wait_backoff(reinterpret_cast<uint64_t*>(&S.empty[s]), (uint32_t)((item / kBwdStages - 1) & 1), 100);
-        const int ncopies = nc + (NEED_VERT ? 3 : 0) + 1;
-        uint64_t* bar = reinterpret_cast<uint64_t*>(&S.full[s]);
-        QStage<TP>& st = S.st[s];
-        const int mine = (ncopies - pw + kQProducers - 1) / kQProducers;
-        fence_proxy_async_smem();
-        mbar_arrive_expect_tx(bar, (uint32_t)mine * bytes);
-        for (int k = pw; k < ncopies; k += kQProducers) {
-          const void* src;
-          void* dst;
-          if (k < nc) {
-            src = b.grad_out + (int64_t)n * b.gs.s0 + (int64_t)k * b.gs.s1 + p0;
-            dst = st.g + k * TP + (k >> 2) * 4;
-          } else if (NEED_VERT && k < nc + 3) {
-            src = a.bary + (int64_t)n * a.bs.s0 + (int64_t)(k - nc) * a.bs.s1 + p0;
-            dst = st.bary + (k - nc) * TP;
-          } else {
-            src = a.index_img + (int64_t)n * a.is.s0 + p0;
-            dst = st.idx;
-          }
-          bulk_g2s(dst, src, bytes, bar);
-        }
-      }
-    }
-    return;
-  }
-
-  // ---- consumer warps: team = stage ----
-  const int team = warp_role / TEAM, unit = warp_role - team * TEAM;
-  const int ttid = tid - team * TEAM * 32;  // thread index inside the team
-  QStage<TP>& st = S.st[team];
-  uint32_t phase = 0;
-  int seq = 0;
-  for (int t0 = blockIdx.x * kQChunk; t0 < num_tiles; t0 += gridDim.x * kQChunk)
-  for (int tile = t0; tile < min(t0 + kQChunk, num_tiles); ++tile, ++seq) {
-    if ((seq & 1) != team) continue;  // the other team's tile (uniform over the warp)
-    int n, tl;
-    decode(tile, n, tl);
-    const int p0 = tl * TP;
-    const int npx = min(TP, HW - p0);
-    const int4* tabn = tab + (size_t)((unsigned)n * (unsigned)tab_img_stride);
-    mbar_wait_backoff(reinterpret_cast<uint64_t*>(&S.full[team]), phase, 32);
-    phase ^= 1u;
-    if (npx < TP) {  // last tile of an image: pad with "no triangle" (and defined gradients / barycentrics)
-      for (int i = npx + ttid; i < TP; i += 32 * TEAM) {
-        st.idx[i] = -1;
-        for (int k = 0; k < nc; ++k) st.g[k * TP + (k >> 2) * 4 + i] = 0.f;
-        if (NEED_VERT) { st.bary[i] = 0.f; st.bary[TP + i] = 0.f; st.bary[2 * TP + i] = 0.f; }
-      }
-      if (team == 0) asm volatile("bar.sync 1, %0;" :: "n"(32 * TEAM) : "memory");
-      else asm volatile("bar.sync 2, %0;" :: "n"(32 * TEAM) : "memory");
-    }
-    {
-      const int q = lane & 3, seg = unit * kQUnit + (lane >> 2) * kQSeg;
-      const bool c_on = 4 * q < nc;
-      const int qq = c_on ? q : 0;
-      const float* arow = a.attr + ((size_t)n * (size_t)a.as.s0 + (size_t)(4 * qq));  // s2 == 1 on this path
-      walk_runs_merged<TP, NEED_VERT>(st.g + (4 * qq) * TP + qq * 4 + seg, st.idx + seg, st.bary + seg,
-                                      vert_grad + ((size_t)n * (size_t)a.V * (size_t)a.C + (size_t)(4 * qq)), tabn,
-                                      (unsigned)a.C, arow, (unsigned)a.as.s1, c_on ? 0 : -1, q);
-    }
-    // the team's bary gradients now sit in the stage's bary planes: coalesced write-out
-    if (team == 0) asm volatile("bar.sync 1, %0;" :: "n"(32 * TEAM) : "memory");
-    else asm volatile("bar.sync 2, %0;" :: "n"(32 * TEAM) : "memory");
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      float* gp = bary_grad + ((size_t)n * 3 * (size_t)HW + (size_t)k * HW + (size_t)p0);
-      for (int i = ttid * 4; i < npx; i += 32 * TEAM * 4)
-        stg_stream_f4(gp + i, *reinterpret_cast<const float4*>(st.bary + k * TP + i));
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&S.empty[team]));
-  }
-}
-
 // Developer switches, read ONCE per process (never on the launch path):
 //   DRTK_B200_BWD_V4=1   take the round-1 v4 tile kernel instead of the quad-walker kernel (A/B runs)
-//   DRTK_B200_MERGED=1   take the merged-walker experiment (phase B folded into the run walkers)
 struct BwdSwitches {
-  bool v4, merged;
-  BwdSwitches() : v4(getenv("DRTK_B200_BWD_V4") != nullptr), merged(getenv("DRTK_B200_MERGED") != nullptr) {}
+  bool v4;
+  BwdSwitches() : v4(getenv("DRTK_B200_BWD_V4") != nullptr) {}
 };
 inline const BwdSwitches& bwd_switches() {
   static const BwdSwitches s;
@@ -1275,20 +1065,7 @@ extern "C" int drtk_b200_interpolate_backward(
         else { if (avec) launch5(interp_bwd_quad_kernel<QTP, false, true, true, MULTI>);                     \
                else launch5(interp_bwd_quad_kernel<QTP, false, true, false, MULTI>); }                       \
       } while (0)
-      if (bwd_switches().merged && C <= kQCh && nb && avec) {
-        auto launchm = [&](auto kern) {
-          const size_t smem = sizeof(QSmem<QTP>) + 128;
-          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          if (e != cudaSuccess) { rc2 = (int)e; return; }
-          const int tiles_per_img = (int)((H * W + QTP - 1) / QTP);
-          const int64_t ctas = 2 * num_sms();
-          const int64_t chunks = (tiles_q + kQChunk - 1) / kQChunk;
-          const unsigned grid = (unsigned)(chunks < ctas ? chunks : ctas);
-          kern<<<grid, 32 * (QTP / kQUnit * 2 + kQProducers), smem, stream>>>(
-              b, vert_attributes_grad, bary_img_grad, tab, tab_imgs == 1 ? 0 : (int)F, tiles_per_img, (int)tiles_q);
-        };
-        if (nv) launchm(interp_bwd_merged_kernel<QTP, true>); else launchm(interp_bwd_merged_kernel<QTP, false>);
-      } else if (C > kQCh) DRTK_Q5(true); else DRTK_Q5(false);
+      if (C > kQCh) DRTK_Q5(true); else DRTK_Q5(false);
 #undef DRTK_Q5
       if (rc2) return rc2;
       DRTK_CHECK_LAUNCH();

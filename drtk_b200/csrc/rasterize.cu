@@ -55,8 +55,24 @@ inline bool use_v1() {
 constexpr int kTileLog = 5;
 constexpr int kTile = 1 << kTileLog;        // 32 x 32 pixels
 constexpr int kTilePix = kTile * kTile;     // 1024
+// tuning knobs (compile-time; tools/build_variants.sh builds A/B libraries with other values)
+#ifndef RV_PASS
+#define RV_PASS 248
+#endif
+#ifndef RV_SWIZZLE
+#define RV_SWIZZLE 1
+#endif
+#ifndef RV_CAS_BATCH
+#define RV_CAS_BATCH 4
+#endif
+#ifndef RV_MIN_CTAS
+#define RV_MIN_CTAS 4
+#endif
+#ifndef RV_ABLATE  // measurement builds only: 1 = no owner claims, 2 = no spans + no claims, 3 = no shading (results wrong)
+#define RV_ABLATE 0
+#endif
 constexpr int kRasterThreads = 256;
-constexpr int kPassRecs = 248;              // records per pass: slot ids are bytes, 0xFF = "no owner"
+constexpr int kPassRecs = RV_PASS;          // records per pass (<= 248): slot ids are bytes, 0xFF = "no owner"
 constexpr int kRecF4 = 5;                   // a record is 5 x 16 B
 constexpr uint32_t kOwnEmpty = 0xFFFFFFFFu;
 constexpr int kLargeBlock = 128;            // large-list entries examined per round of a tile CTA
@@ -274,6 +290,18 @@ struct __align__(16) TileSmem {
   unsigned long long bar;                  // mbarrier of the record copy
 };
 
+// Position of tile pixel (lx, ly) in the per-pixel arrays.  Phase 1 has the lanes of a warp on consecutive ROWS of one
+// triangle at nearly the same column: with the plain row-major layout (row pitch = 32 banks) their shared-memory
+// atomics would all hit one bank.  Rotating row ly by 4*ly columns spreads them over the banks and keeps every aligned
+// pixel quad contiguous (128-bit accesses of phase 2 and of the resolve).
+__device__ __forceinline__ int pix_slot(int ly, int lx) {
+#if RV_SWIZZLE
+  return (ly << kTileLog) | ((lx + 4 * ly) & (kTile - 1));
+#else
+  return (ly << kTileLog) | lx;
+#endif
+}
+
 // key of one owner at pixel (px, py): depth exactly as the reference computes it for a covered sample
 __device__ __forceinline__ unsigned long long shade_key(const float4* __restrict__ rec, float px, float py) {
   const float4 e0 = rec[0], e1 = rec[1], e2 = rec[2], z = rec[3];
@@ -284,9 +312,10 @@ __device__ __forceinline__ unsigned long long shade_key(const float4* __restrict
   return ((unsigned long long)depth_bits_of(b0, b1, b2, z.w, z.x, z.y, z.z) << 32) | id;
 }
 
-// Register `slot` as an owner of pixel p.  First owner: one CAS against "all free".  Bytes fill from the low end.
-__device__ __forceinline__ void claim_pixel(TileSmem& S, int p, uint32_t slot, float px, float py) {
-  uint32_t old = atomicCAS(&S.own[p], kOwnEmpty, 0xFFFFFF00u | slot);
+// Register `slot` as an owner of the pixel at array position p.  First owner: one CAS against "all free" (issued by the
+// caller, several pixels at a time); this is the continuation for a pixel that already has owners.  Bytes fill from
+// the low end.
+__device__ __forceinline__ void claim_taken(TileSmem& S, int p, uint32_t old, uint32_t slot, float px, float py) {
   while (old != kOwnEmpty) {
     if ((old >> 24) != 0xFFu) {  // four owners already: shade here, 64-bit minimum (rare)
       atomicMin(&S.zbuf[p], shade_key(S.rec + slot * kRecF4, px, py));
@@ -346,19 +375,34 @@ __device__ __forceinline__ void tile_pass(TileSmem& S, int m, int x_lo, int y_lo
     const int xs0 = x_lo + ((meta >> RASTER_META_BX0) & 31), xe0 = x_lo + ((meta >> RASTER_META_BX1) & 31);
     int xs = xs0, xe = xe0;
     const bool wild = (meta & RASTER_META_WILD) != 0;
+#if RV_ABLATE != 2
     if (!wild) row_span_exact(ox, ay, row, tl, xs0, xe0, xs, xe);
-    const int pbase = (ly << kTileLog) - x_lo;
-    for (int x = xs; x <= xe; ++x) {
-      if (wild && !sample_covered(ox, ay, row, tl, (float)x)) continue;
-      claim_pixel(S, pbase + x, (uint32_t)slot, (float)x, py);
+#endif
+#if RV_ABLATE == 1 || RV_ABLATE == 2
+    if (xs + xe == 0x7fffff00) S.own[0] = (uint32_t)(xs ^ xe);  // keeps the span computation alive
+    xe = xs - 1;
+#endif
+    // RV_CAS_BATCH first-owner CAS in flight per lane (their round trips overlap), then the rare continuations
+    const uint32_t mine = 0xFFFFFF00u | (uint32_t)slot;
+    for (int x = xs; x <= xe; x += RV_CAS_BATCH) {
+      uint32_t old[RV_CAS_BATCH];
+#pragma unroll
+      for (int j = 0; j < RV_CAS_BATCH; ++j) {
+        old[j] = kOwnEmpty;
+        if (x + j <= xe && !(wild && !sample_covered(ox, ay, row, tl, (float)(x + j))))
+          old[j] = atomicCAS(&S.own[pix_slot(ly, x + j - x_lo)], kOwnEmpty, mine);
+      }
+#pragma unroll
+      for (int j = 0; j < RV_CAS_BATCH; ++j)
+        if (old[j] != kOwnEmpty) claim_taken(S, pix_slot(ly, x + j - x_lo), old[j], (uint32_t)slot, (float)(x + j), py);
     }
   }
   __syncthreads();
 
   // ---- C. phase 2: one pixel quad per thread: shade the owners, keep the minimum ----
   {
-    const int p4 = tid * 4;
-    const int ly = p4 >> kTileLog, lx = p4 & (kTile - 1);
+    const int ly = tid >> 3, lx = (tid & 7) * 4;
+    const int p4 = pix_slot(ly, lx);
     const uint4 w4 = *reinterpret_cast<const uint4*>(&S.own[p4]);
     if ((w4.x & w4.y & w4.z & w4.w) != kOwnEmpty) {
       *reinterpret_cast<uint4*>(&S.own[p4]) = make_uint4(kOwnEmpty, kOwnEmpty, kOwnEmpty, kOwnEmpty);  // for the next pass
@@ -369,7 +413,11 @@ __device__ __forceinline__ void tile_pass(TileSmem& S, int m, int x_lo, int y_lo
         uint32_t w = ws[j];
         const float px = (float)(x_lo + lx + j);
         while ((w & 0xFFu) != 0xFFu) {
+#if RV_ABLATE == 3
+          const unsigned long long key = (unsigned long long)(w & 0xFFu);
+#else
           const unsigned long long key = shade_key(S.rec + (w & 0xFFu) * kRecF4, px, py);
+#endif
           best[j] = key < best[j] ? key : best[j];
           w = (w >> 8) | 0xFF000000u;
         }
@@ -379,7 +427,7 @@ __device__ __forceinline__ void tile_pass(TileSmem& S, int m, int x_lo, int y_lo
   __syncthreads();  // S.rec may be overwritten now
 }
 
-__global__ void __launch_bounds__(kRasterThreads, 4) raster_tiles_kernel(
+__global__ void __launch_bounds__(kRasterThreads, RV_MIN_CTAS) raster_tiles_kernel(
     RasterArgs a, const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_offset,
     const float4* __restrict__ recs, const uint32_t* __restrict__ large_count, const uint32_t* __restrict__ large_id,
     const int4* __restrict__ large_bbox, float* __restrict__ depth_img, int32_t* __restrict__ index_img) {
@@ -462,8 +510,8 @@ __global__ void __launch_bounds__(kRasterThreads, 4) raster_tiles_kernel(
   }
 
   // (3) resolve + store (:402-415): empty -> index -1 (low word all ones), depth 0
-  const int p4 = tid * 4;
-  const int ly = p4 >> kTileLog, lx = p4 & (kTile - 1);
+  const int ly = tid >> 3, lx = (tid & 7) * 4;
+  const int p4 = pix_slot(ly, lx);
   const int x = x_lo + lx, y = y_lo + ly;
   if (y > y_hi || x > x_hi) return;
   int ids[4];

@@ -479,12 +479,13 @@ extern "C" int drtk_b200_render_forward(const float* v, const int64_t* v_strides
                                         void* stream_) {
   if (N < 0 || H < 0 || W < 0) return DRTK_B200_EINVAL;
   if (N * H * W == 0) return 0;
-  if (!v || !vi || !index_img || !depth_img || !bary_img) return DRTK_B200_EINVAL;
+  // an empty face list (F == 0) may come with null v / vi pointers: no pixel can reference a triangle then
+  if (((!v || !vi) && F > 0) || !index_img || !depth_img || !bary_img) return DRTK_B200_EINVAL;
   if (H > (1 << 30) || W > (1 << 30) || N > (1 << 30)) return DRTK_B200_EUNSUPPORTED;
   if (N > kMaxBatchPerLaunch) {  // batch index rides on gridDim.y: slices of the batch
     for (int64_t n0 = 0; n0 < N; n0 += kMaxBatchPerLaunch) {
       const int64_t nn = (N - n0 < kMaxBatchPerLaunch) ? N - n0 : kMaxBatchPerLaunch;
-      const int rc = drtk_b200_render_forward(v + n0 * v_strides[0], v_strides, vi + n0 * vi_strides[0], vi_strides,
+      const int rc = drtk_b200_render_forward(v ? v + n0 * v_strides[0] : nullptr, v_strides, vi ? vi + n0 * vi_strides[0] : nullptr, vi_strides,
                                               index_img + n0 * index_strides[0], index_strides, nn, V, F, H, W,
                                               depth_img + n0 * H * W, bary_img + n0 * 3 * H * W, stream_);
       if (rc) return rc;

@@ -64,7 +64,8 @@ inline bool is_f64(const Tensor& t) { return t.scalar_type() == at::kDouble; }
 inline void need_real(const Tensor& t, const char* who, const char* name) {
   TORCH_CHECK(t.is_floating_point(), who, "(): expected ", name, " to have floating point type, but ", name, " has ", t.dtype());
   TORCH_CHECK(t.scalar_type() == at::kFloat || t.scalar_type() == at::kDouble, who,
-              "(): drtk_b200 computes in float32 / float64, but ", name, " has ", t.dtype(), "; cast it (or use torch.autocast)");
+              "(): drtk_b200 computes in float32 only (float64: the plain double kernels), but ", name, " has ", t.dtype(),
+              "; cast it to float32 or run under torch.autocast");
 }
 
 // ---- rasterize (checks: src/rasterize/rasterize_kernel.cu:423-468) ----------------------------------------------
