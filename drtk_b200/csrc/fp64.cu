@@ -90,6 +90,94 @@ __global__ void raster_tri_kernel(const T* __restrict__ v, Strides3 vs, const in
     }
 }
 
+// ---- wireframe (src/rasterize/rasterize_kernel.cu:171-400, instantiated for double at :492-535) -------------------
+// A pixel carries a triangle's id when one of its VISIBLE edges (bits 0-2 of the top nibble of vi[...,0], :293-303)
+// crosses the diamond |dx| + |dy| = 0.5 around the pixel centre (:220-259); the interior still writes depth with id
+// 0xFFFFFFFF (= -1) so that surfaces occlude the lines behind them (:376-393).
+struct Line64 { T a, b, c; };
+__device__ __forceinline__ Line64 line_through(T p1x, T p1y, T p2x, T p2y) {  // :171-181
+  return Line64{p1y - p2y, p2x - p1x, p1x * p2y - p2x * p1y};
+}
+__device__ __forceinline__ bool in_segment(T p1x, T p1y, T p2x, T p2y, T cx, T cy) {  // :183-191
+  return (((p2x >= cx) && (cx >= p1x)) || ((p2x <= cx) && (cx <= p1x))) &&
+         (((p2y >= cy) && (cy >= p1y)) || ((p2y <= cy) && (cy <= p1y)));
+}
+__device__ __forceinline__ bool crosses_side(const Line64& l, T p1x, T p1y, T p2x, T p2y, T s0x, T s0y, T s1x, T s1y) {
+  const Line64 m = line_through(s0x, s0y, s1x, s1y);
+  const T d = l.a * m.b - m.a * l.b;  // :205-218
+  T cx = 1.7976931348623157e308, cy = 0;  // TVec2{max}: x = DBL_MAX, y = 0
+  if (d != 0) {
+    cx = (l.b * m.c - m.b * l.c) / d;
+    cy = (m.a * l.c - l.a * m.c) / d;
+  }
+  return in_segment(s0x, s0y, s1x, s1y, cx, cy) && in_segment(p1x, p1y, p2x, p2y, cx, cy);
+}
+__device__ __forceinline__ bool crosses_diamond(T p1x, T p1y, T p2x, T p2y, T px, T py) {  // :220-259
+  const Line64 l = line_through(p1x, p1y, p2x, p2y);
+  const T h = 0.5;
+  bool hit = crosses_side(l, p1x, p1y, p2x, p2y, px, py - h, px + h, py);
+  hit |= crosses_side(l, p1x, p1y, p2x, p2y, px + h, py, px, py + h);
+  hit |= crosses_side(l, p1x, p1y, p2x, p2y, px, py + h, px - h, py);
+  hit |= crosses_side(l, p1x, p1y, p2x, p2y, px - h, py, px, py - h);
+  return hit;
+}
+
+// one WARP per triangle: the lanes stride over the padded bounding box (the reference walks it with one thread)
+__global__ void raster_lines_kernel64(const T* __restrict__ v, Strides3 vs, const int32_t* __restrict__ vi, Strides3 is,
+                                      int N, int F, int H, int W, unsigned long long* __restrict__ packed) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5, nwarps = (gridDim.x * int64_t(blockDim.x)) >> 5;
+  for (int64_t idx = warp0; idx < int64_t(N) * F; idx += nwarps) {
+    const int n = int(idx / F), id = int(idx % F);
+    int i0, i1, i2;
+    load_tri(vi + n * is.s0, is, id, i0, i1, i2);
+    const int flag = int((unsigned(i0) & 0xF0000000u) >> 28);
+    i0 &= 0x0FFFFFFF;
+    if (i0 == i1 && i1 == i2) continue;  // :296
+    const bool vis0 = flag & 1, vis1 = flag & 2, vis2 = flag & 4;
+    const T* vn = v + n * vs.s0;
+    const Vert p0 = load_vert(vn, vs, i0), p1 = load_vert(vn, vs, i1), p2 = load_vert(vn, vs, i2);
+    if (!(p0.z > 1e-8f && p1.z > 1e-8f && p2.z > 1e-8f)) continue;  // :321
+    const T mnx = fmin(fmin(p0.x, p1.x), p2.x), mny = fmin(fmin(p0.y, p1.y), p2.y);
+    const T mxx = fmax(fmax(p0.x, p1.x), p2.x), mxy = fmax(fmax(p0.y, p1.y), p2.y);
+    if (!(mnx <= T(W - 1) && mny <= T(H - 1) && mxx > 0 && mxy > 0)) continue;  // :322-323
+    const T v01x = p1.x - p0.x, v01y = p1.y - p0.y, v02x = p2.x - p0.x, v02y = p2.y - p0.y;
+    const T v12x = p2.x - p1.x, v12y = p2.y - p1.y;
+    const T den = v01x * v02y - v01y * v02x;  // :330
+    if (den == 0) continue;
+    // bounds with the extra border (:333-337); the clamps before the conversions keep them from overflowing
+    const int bx0 = max(1, int(fmax(mnx, T(-4))) - 2), by0 = max(1, int(fmax(mny, T(-4))) - 2);
+    const int bx1 = min(W - 2, int(fmin(mxx, T(W))) + 2), by1 = min(H - 2, int(fmin(mxy, T(H))) + 2);
+    if (bx0 > bx1 || by0 > by1) continue;
+    bool tl[3];
+    top_left(den, v01x, v01y, v02x, v02y, v12x, v12y, tl);
+    const T s = sign_d(den), aden = fabs(den);
+    const T d0 = T(1) / epsclamp_d(p0.z), d1 = T(1) / epsclamp_d(p1.z), d2 = T(1) / epsclamp_d(p2.z);
+    unsigned long long* pk = packed + int64_t(n) * H * W;
+    const int bw = bx1 - bx0 + 1;
+    const int64_t count = int64_t(bw) * (by1 - by0 + 1);
+    for (int64_t q = lane; q < count; q += 32) {
+      const int y = by0 + int(q / bw), x = bx0 + int(q % bw);
+      const T px = T(x), py = T(y);
+      bool hit = crosses_diamond(p0.x, p0.y, p1.x, p1.y, px, py) && vis0;  // :343-346
+      hit |= crosses_diamond(p1.x, p1.y, p2.x, p2.y, px, py) && vis1;
+      hit |= crosses_diamond(p0.x, p0.y, p2.x, p2.y, px, py) && vis2;
+      T b0 = canon_edge(i1, i2, p1.x, p1.y, p2.x, p2.y, px, py) * s;  // :348-353
+      T b1 = canon_edge(i2, i0, p2.x, p2.y, p0.x, p0.y, px, py) * s;
+      T b2 = canon_edge(i0, i1, p0.x, p0.y, p1.x, p1.y, px, py) * s;
+      const bool inside = b0 >= 0 && b1 >= 0 && b2 >= 0;
+      const bool keep = inside && !((b0 == 0 && !tl[0]) || (b1 == 0 && !tl[1]) || (b2 == 0 && !tl[2]));
+      if (!(keep || hit)) continue;  // :375
+      b0 = fmin(fmax(b0 / aden, T(0)), T(1)); b1 = fmin(fmax(b1 / aden, T(0)), T(1)); b2 = fmin(fmax(b2 / aden, T(0)), T(1));
+      const T sum = b0 + b1 + b2;
+      b0 /= sum; b1 /= sum; b2 /= sum;
+      const float depth = float(T(1) / epsclamp_d(d0 * b0 + d1 * b1 + d2 * b2));
+      atomicMin(pk + int64_t(y) * W + x,
+                (static_cast<unsigned long long>(__float_as_uint(depth)) << 32) | (hit ? (unsigned long long)unsigned(id) : 0xFFFFFFFFull));
+    }
+  }
+}
+
 __global__ void unpack_kernel(const unsigned long long* __restrict__ packed, int64_t total, float* __restrict__ depth,
                               int32_t* __restrict__ index) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
@@ -359,7 +447,6 @@ extern "C" int drtk_b200_rasterize_f64(const double* v, const int64_t* v_strides
                                        int wireframe, float* depth_img, int32_t* index_img, void* workspace,
                                        size_t workspace_bytes, void* stream) {
   if (!v_strides || !vi_strides || N < 0 || V < 0 || F < 0 || H <= 0 || W <= 0) return DRTK_B200_EINVAL;
-  if (wireframe) return DRTK_B200_EUNSUPPORTED;
   if (too_big(N, H, W) || N * F / 256 > INT32_MAX || F > INT32_MAX) return DRTK_B200_EUNSUPPORTED;
   if (N == 0) return 0;
   if (!depth_img || !index_img || (F > 0 && (!v || !vi))) return DRTK_B200_EINVAL;
@@ -367,7 +454,12 @@ extern "C" int drtk_b200_rasterize_f64(const double* v, const int64_t* v_strides
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto* packed = static_cast<unsigned long long*>(workspace);
   DRTK_CUDA(cudaMemsetAsync(packed, 0xFF, size_t(N) * H * W * 8, st));  // :484-488
-  if (F > 0) {
+  if (F > 0 && wireframe) {
+    const int64_t want = (N * F * 32 + 255) / 256, cap = int64_t(num_sms()) * 32;
+    raster_lines_kernel64<<<unsigned(want < cap ? want : cap), 256, 0, st>>>(v, make3(v_strides), vi, make3(vi_strides), int(N),
+                                                                             int(F), int(H), int(W), packed);
+    DRTK_CHECK_LAUNCH();
+  } else if (F > 0) {
     raster_tri_kernel<<<nblk(N * F), 256, 0, st>>>(v, make3(v_strides), vi, make3(vi_strides), int(N), int(F), int(H),
                                                    int(W), packed);
     DRTK_CHECK_LAUNCH();

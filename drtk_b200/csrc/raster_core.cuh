@@ -41,6 +41,7 @@ __device__ __forceinline__ float core_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+
 }  // namespace drtk
 #else
 #include <math.h>
@@ -63,6 +64,7 @@ inline float core_rcp(float x) {
   }
   return r;
 }
+
 }  // namespace drtk
 #endif
 
@@ -170,6 +172,51 @@ DRTK_HD void row_span_exact(const float (&ox)[3], const float (&ay)[3], const fl
   }
   xs = (int)lo;
   xe = (int)hi;
+}
+
+// int <-> float for small integers on the ALU / FMA pipes (I2F / F2I / FRND are XU instructions, the most loaded pipe
+// of the tile kernel).  small_i2f: exact for 0 <= i < 2^23; small_f2i: exact for integer-valued |f| < 2^22.
+#if defined(__CUDA_ARCH__)
+#define DRTK_I2F_BITS(i) __int_as_float(i)
+#define DRTK_F2I_BITS(f) __float_as_int(f)
+#else
+inline float drtk_bits_to_float(int32_t i) { union { int32_t i; float f; } u; u.i = i; return u.f; }
+inline int32_t drtk_float_to_bits(float f) { union { int32_t i; float f; } u; u.f = f; return u.i; }
+#define DRTK_I2F_BITS(i) drtk_bits_to_float(i)
+#define DRTK_F2I_BITS(f) drtk_float_to_bits(f)
+#endif
+DRTK_HD float small_i2f(int i) { return DRTK_SUB(DRTK_I2F_BITS(0x4B000000 | i), 8388608.f); }
+DRTK_HD int small_f2i(float f) { return DRTK_F2I_BITS(DRTK_ADD(f, 12582912.f)) - 0x4B400000; }
+
+// row_span_exact as the tile kernel runs it: the three reciprocals ray[k] = MUFU.RCP(ay[k]) are supplied (computed once
+// per record), floor() is done with the add-magic-number trick and the bounds stay in float (no XU instruction).
+// Same decisions as row_span_exact; tests/span_harness.cpp checks both against the per-sample test.
+// lo0 / hi0: the clipped bounding-box columns as floats; result: first / last covered column (empty when lo > hi).
+DRTK_HD void row_span_fast(const float (&ox)[3], const float (&ay)[3], const float (&row)[3], const float (&ray)[3],
+                           unsigned tl_bits, float lo0, float hi0, float& lo_out, float& hi_out) {
+  float lo = lo0, hi = hi0;
+  const float cl = DRTK_SUB(lo0, 1.f), ch = DRTK_ADD(hi0, 1.f);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float thr = ((tl_bits >> k) & 1u) ? DRTK_NEG_FLT_MIN : 0.f;
+    const bool inc = ay[k] < 0.f;
+    const float rho = row[k] * ray[k];
+    const bool near = fabsf(rho) <= kSpanNear;
+    const float t = (rho + ox[k]) + (inc ? 0.26f : 0.74f);
+    const float r = DRTK_SUB(DRTK_ADD(t, 12582912.f), 12582912.f);  // round to nearest integer (|t| < 2^22 when near)
+    float u = r > t ? DRTK_SUB(r, 1.f) : r;                          // floor(t)
+    u = near ? u : lo0;
+    u = fminf(fmaxf(u, cl), ch);
+    const bool p = edge_value(ay[k], ox[k], row[k], u) > thr;
+    if (near) {
+      if (inc) lo = fmaxf(lo, p ? u : DRTK_ADD(u, 1.f));
+      else hi = fminf(hi, p ? u : DRTK_SUB(u, 1.f));
+    } else if (!p) {
+      hi = cl;
+    }
+  }
+  lo_out = lo;
+  hi_out = hi;
 }
 
 }  // namespace drtk

@@ -57,25 +57,20 @@ constexpr int kTile = 1 << kTileLog;        // 32 x 32 pixels
 constexpr int kTilePix = kTile * kTile;     // 1024
 // tuning knobs (compile-time; tools/build_variants.sh builds A/B libraries with other values)
 #ifndef RV_PASS
-#define RV_PASS 248
-#endif
-#ifndef RV_SWIZZLE
-#define RV_SWIZZLE 1
-#endif
-#ifndef RV_CAS_BATCH
-#define RV_CAS_BATCH 4
+#define RV_PASS 120
 #endif
 #ifndef RV_MIN_CTAS
-#define RV_MIN_CTAS 4
+#define RV_MIN_CTAS 7
 #endif
-#ifndef RV_ABLATE  // measurement builds only: 1 = no owner claims, 2 = no spans + no claims, 3 = no shading (results wrong)
-#define RV_ABLATE 0
+#ifndef RV_THREADS
+#define RV_THREADS 128
 #endif
-constexpr int kRasterThreads = 256;
-constexpr int kPassRecs = RV_PASS;          // records per pass (<= 248): slot ids are bytes, 0xFF = "no owner"
+constexpr int kRasterThreads = RV_THREADS;  // 128 or 256
+constexpr int kPassRecs = RV_PASS;          // records per pass (<= 248, <= threads): slot ids are bytes, 0xFF = "no owner"
 constexpr int kRecF4 = 5;                   // a record is 5 x 16 B
 constexpr uint32_t kOwnEmpty = 0xFFFFFFFFu;
-constexpr int kLargeBlock = 128;            // large-list entries examined per round of a tile CTA
+constexpr int kLargeBlock = 64;             // large-list entries examined per round of a tile CTA
+static_assert(kPassRecs <= kRasterThreads && kPassRecs <= 248 && kPassRecs > kLargeBlock, "pass size");
 
 struct RasterArgs {
   const float* v;
@@ -278,11 +273,15 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* count, uint32_t* o
 // ------------------------------------------------------------------------------------------
 // per-tile resolve
 // ------------------------------------------------------------------------------------------
+constexpr uint32_t kCellNone = 0xFFFFFFFFu;
+constexpr int kRowsPerWarp = kTile / (kRasterThreads / 32);  // tile rows owned by one warp in phase 2 (4 or 8)
+
 struct __align__(16) TileSmem {
-  float4 rec[kPassRecs * kRecF4];          // 19 840 B: the records of this pass (bulk-async copy / built in place)
-  unsigned long long zbuf[kTilePix];       //  8 192 B: packed minimum of the deep-overlap path (5th+ owner of a pixel)
-  uint32_t own[kTilePix];                  //  4 096 B: four owner slots per pixel, 0xFF = free
-  uint8_t rowmap[kPassRecs * kTile];       //  7 936 B: row item -> record slot
+  float4 rec[kPassRecs * kRecF4];          // the records of this pass (bulk-async copy / built in place)
+  float4 srcp[kPassRecs];                  // per record: MUFU.RCP(ay_k), k = 0..2 (the span solver's only reciprocals)
+  unsigned long long zbuf[kTilePix];       // packed minimum of the collision path (two spans starting on one pixel)
+  uint32_t cell[kTilePix];                 // span starts: cell(ly, xs) = slot | xe << 8, kCellNone = no span starts here
+  uint8_t rowmap[kPassRecs * kTile];       // row item -> record slot
   int prefix[kPassRecs + 1];               // exclusive scan of the per-record row counts
   int warp_tot[kRasterThreads / 32];
   uint32_t mlist[kPassRecs];               // large triangles that touch this tile (ids), current round
@@ -290,19 +289,12 @@ struct __align__(16) TileSmem {
   unsigned long long bar;                  // mbarrier of the record copy
 };
 
-// Position of tile pixel (lx, ly) in the per-pixel arrays.  Phase 1 has the lanes of a warp on consecutive ROWS of one
-// triangle at nearly the same column: with the plain row-major layout (row pitch = 32 banks) their shared-memory
-// atomics would all hit one bank.  Rotating row ly by 4*ly columns spreads them over the banks and keeps every aligned
-// pixel quad contiguous (128-bit accesses of phase 2 and of the resolve).
-__device__ __forceinline__ int pix_slot(int ly, int lx) {
-#if RV_SWIZZLE
-  return (ly << kTileLog) | ((lx + 4 * ly) & (kTile - 1));
-#else
-  return (ly << kTileLog) | lx;
-#endif
-}
+// Span-start cells: row ly is rotated by ly columns.  Phase 1 has the lanes of a warp on consecutive ROWS of one triangle
+// whose spans start at nearly the same column (one bank in a plain row-major layout); phase 2 reads one whole row per
+// warp, for which any rotation is conflict free.
+__device__ __forceinline__ int cell_slot(int ly, int lx) { return (ly << kTileLog) | ((lx + ly) & (kTile - 1)); }
 
-// key of one owner at pixel (px, py): depth exactly as the reference computes it for a covered sample
+// key of record `rec` at pixel (px, py): depth exactly as the reference computes it for a covered sample
 __device__ __forceinline__ unsigned long long shade_key(const float4* __restrict__ rec, float px, float py) {
   const float4 e0 = rec[0], e1 = rec[1], e2 = rec[2], z = rec[3];
   const uint32_t id = __float_as_uint(rec[4].x);
@@ -312,32 +304,17 @@ __device__ __forceinline__ unsigned long long shade_key(const float4* __restrict
   return ((unsigned long long)depth_bits_of(b0, b1, b2, z.w, z.x, z.y, z.z) << 32) | id;
 }
 
-// Register `slot` as an owner of the pixel at array position p.  First owner: one CAS against "all free" (issued by the
-// caller, several pixels at a time); this is the continuation for a pixel that already has owners.  Bytes fill from
-// the low end.
-__device__ __forceinline__ void claim_taken(TileSmem& S, int p, uint32_t old, uint32_t slot, float px, float py) {
-  while (old != kOwnEmpty) {
-    if ((old >> 24) != 0xFFu) {  // four owners already: shade here, 64-bit minimum (rare)
-      atomicMin(&S.zbuf[p], shade_key(S.rec + slot * kRecF4, px, py));
-      return;
-    }
-    const int sh = ((old >> 8) & 0xFFu) == 0xFFu ? 8 : (((old >> 16) & 0xFFu) == 0xFFu ? 16 : 24);
-    const uint32_t want = (old & ~(0xFFu << sh)) | (slot << sh);
-    const uint32_t prev = atomicCAS(&S.own[p], old, want);
-    if (prev == old) return;
-    old = prev;
-  }
-}
-
 // One pass over the m records in S.rec (m <= kPassRecs).  Entered and left by all threads of the CTA.
-__device__ __forceinline__ void tile_pass(TileSmem& S, int m, int x_lo, int y_lo, unsigned long long (&best)[4]) {
+__device__ __forceinline__ void tile_pass(TileSmem& S, int m, int x_lo, int y_lo, float x_lo_f, float y_lo_f,
+                                          unsigned long long (&best)[kRowsPerWarp]) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // ---- A. row items: exclusive block scan of the row counts, row item -> slot map ----
-  int rows = 0, my_by0 = 0;
+  // ---- A. per record: reciprocals of the edge slopes; row items: exclusive block scan, row item -> slot map ----
+  int rows = 0;
   if (tid < m) {
-    const int meta = __float_as_int(S.rec[tid * kRecF4 + 4].y);
-    my_by0 = (meta >> RASTER_META_BY0) & 31;
-    rows = max(0, ((meta >> RASTER_META_BY1) & 31) - my_by0 + 1);
+    const float4* rec = S.rec + tid * kRecF4;
+    const int meta = __float_as_int(rec[4].y);
+    rows = max(0, ((meta >> RASTER_META_BY1) & 31) - ((meta >> RASTER_META_BY0) & 31) + 1);
+    S.srcp[tid] = make_float4(core_rcp(rec[0].w), core_rcp(rec[1].w), core_rcp(rec[2].w), 0.f);
   }
   int inc = rows;
 #pragma unroll
@@ -361,66 +338,64 @@ __device__ __forceinline__ void tile_pass(TileSmem& S, int m, int x_lo, int y_lo
   }
   __syncthreads();
 
-  // ---- B. phase 1: one (triangle, row) per thread: exact span, owners ----
+  // ---- B. phase 1: one (triangle, row) per thread: exact span -> ONE span-start cell ----
   for (int item = tid; item < total; item += kRasterThreads) {
     const int slot = S.rowmap[item];
     const float4* rec = S.rec + slot * kRecF4;
-    const float4 e0 = rec[0], e1 = rec[1], e2 = rec[2];
+    const float4 e0 = rec[0], e1 = rec[1], e2 = rec[2], rc = S.srcp[slot];
     const int meta = __float_as_int(rec[4].y);
     const int ly = ((meta >> RASTER_META_BY0) & 31) + (item - S.prefix[slot]);
-    const float py = (float)(y_lo + ly);
-    const float ox[3] = {e0.x, e1.x, e2.x}, ay[3] = {e0.w, e1.w, e2.w};
+    const float py = y_lo_f + small_i2f(ly);
+    const float ox[3] = {e0.x, e1.x, e2.x}, ay[3] = {e0.w, e1.w, e2.w}, ray[3] = {rc.x, rc.y, rc.z};
     const float row[3] = {edge_row_term(py, e0.y, e0.z), edge_row_term(py, e1.y, e1.z), edge_row_term(py, e2.y, e2.z)};
     const unsigned tl = (unsigned)meta & RASTER_META_TL_MASK;
-    const int xs0 = x_lo + ((meta >> RASTER_META_BX0) & 31), xe0 = x_lo + ((meta >> RASTER_META_BX1) & 31);
-    int xs = xs0, xe = xe0;
-    const bool wild = (meta & RASTER_META_WILD) != 0;
-#if RV_ABLATE != 2
-    if (!wild) row_span_exact(ox, ay, row, tl, xs0, xe0, xs, xe);
-#endif
-#if RV_ABLATE == 1 || RV_ABLATE == 2
-    if (xs + xe == 0x7fffff00) S.own[0] = (uint32_t)(xs ^ xe);  // keeps the span computation alive
-    xe = xs - 1;
-#endif
-    // RV_CAS_BATCH first-owner CAS in flight per lane (their round trips overlap), then the rare continuations
-    const uint32_t mine = 0xFFFFFF00u | (uint32_t)slot;
-    for (int x = xs; x <= xe; x += RV_CAS_BATCH) {
-      uint32_t old[RV_CAS_BATCH];
-#pragma unroll
-      for (int j = 0; j < RV_CAS_BATCH; ++j) {
-        old[j] = kOwnEmpty;
-        if (x + j <= xe && !(wild && !sample_covered(ox, ay, row, tl, (float)(x + j))))
-          old[j] = atomicCAS(&S.own[pix_slot(ly, x + j - x_lo)], kOwnEmpty, mine);
-      }
-#pragma unroll
-      for (int j = 0; j < RV_CAS_BATCH; ++j)
-        if (old[j] != kOwnEmpty) claim_taken(S, pix_slot(ly, x + j - x_lo), old[j], (uint32_t)slot, (float)(x + j), py);
+    const int lx0 = (meta >> RASTER_META_BX0) & 31, lx1 = (meta >> RASTER_META_BX1) & 31;
+    int lxs, lxe;  // covered interval, tile-local
+    if (!(meta & RASTER_META_WILD)) {
+      float lo, hi;
+      row_span_fast(ox, ay, row, ray, tl, x_lo_f + small_i2f(lx0), x_lo_f + small_i2f(lx1), lo, hi);
+      lxs = small_f2i(lo - x_lo_f);
+      lxe = small_f2i((hi - x_lo_f) + 1.f) - 1;  // hi may be lo0 - 1
+    } else {  // huge coordinates: per-sample tests (the covered set is still one interval)
+      lxs = kTile; lxe = -1;
+      for (int lx = lx0; lx <= lx1; ++lx)
+        if (sample_covered(ox, ay, row, tl, (float)(x_lo + lx))) { lxs = min(lxs, lx); lxe = max(lxe, lx); }
+    }
+    if (lxs > lxe) continue;
+    const uint32_t mine = (uint32_t)slot | ((uint32_t)lxe << 8);
+    if (atomicCAS(&S.cell[cell_slot(ly, lxs)], kCellNone, mine) != kCellNone) {
+      // another span of this pass starts on the same pixel (overlapping surfaces): shade this span here
+      for (int lx = lxs; lx <= lxe; ++lx)
+        atomicMin(&S.zbuf[(ly << kTileLog) + lx], shade_key(rec, x_lo_f + small_i2f(lx), py));
     }
   }
   __syncthreads();
 
-  // ---- C. phase 2: one pixel quad per thread: shade the owners, keep the minimum ----
-  {
-    const int ly = tid >> 3, lx = (tid & 7) * 4;
-    const int p4 = pix_slot(ly, lx);
-    const uint4 w4 = *reinterpret_cast<const uint4*>(&S.own[p4]);
-    if ((w4.x & w4.y & w4.z & w4.w) != kOwnEmpty) {
-      *reinterpret_cast<uint4*>(&S.own[p4]) = make_uint4(kOwnEmpty, kOwnEmpty, kOwnEmpty, kOwnEmpty);  // for the next pass
-      const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
-      const float py = (float)(y_lo + ly);
+  // ---- C. phase 2: warp = tile row, lane = pixel: find the spans covering the pixel, shade, keep the minimum ----
+  const float px = x_lo_f + small_i2f(lane);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t w = ws[j];
-        const float px = (float)(x_lo + lx + j);
-        while ((w & 0xFFu) != 0xFFu) {
-#if RV_ABLATE == 3
-          const unsigned long long key = (unsigned long long)(w & 0xFFu);
-#else
-          const unsigned long long key = shade_key(S.rec + (w & 0xFFu) * kRecF4, px, py);
-#endif
-          best[j] = key < best[j] ? key : best[j];
-          w = (w >> 8) | 0xFF000000u;
-        }
+  for (int r = 0; r < kRowsPerWarp; ++r) {
+    const int ly = wid * kRowsPerWarp + r;
+    const int cs = cell_slot(ly, lane);
+    const uint32_t c = S.cell[cs];
+    const bool is_start = c != kCellNone;
+    const int len = is_start ? (int)((c >> 8) & 31u) - lane + 1 : 0;
+    const int L = __reduce_max_sync(0xffffffffu, len);  // longest span of this row
+    if (L == 0) continue;                               // nothing in this row (uniform)
+    if (is_start) S.cell[cs] = kCellNone;               // for the next pass
+    const unsigned starts = __ballot_sync(0xffffffffu, is_start);
+    // starts that can cover this pixel: those in [lane - L + 1, lane]
+    const int first = max(lane - L + 1, 0);
+    unsigned cand = starts & ((2u << lane) - 1u) & ~((1u << first) - 1u);
+    const float py = y_lo_f + small_i2f(ly);
+    while (__any_sync(0xffffffffu, cand != 0u)) {
+      const int s = cand ? 31 - __clz(cand) : lane;
+      const uint32_t sc = __shfl_sync(0xffffffffu, c, s);
+      const bool hit = cand != 0u && lane <= (int)((sc >> 8) & 31u);
+      cand &= ~(1u << s);
+      if (hit) {
+        const unsigned long long key = shade_key(S.rec + (sc & 0xFFu) * kRecF4, px, py);
+        best[r] = key < best[r] ? key : best[r];
       }
     }
   }
@@ -432,11 +407,12 @@ __global__ void __launch_bounds__(kRasterThreads, RV_MIN_CTAS) raster_tiles_kern
     const float4* __restrict__ recs, const uint32_t* __restrict__ large_count, const uint32_t* __restrict__ large_id,
     const int4* __restrict__ large_bbox, float* __restrict__ depth_img, int32_t* __restrict__ index_img) {
   __shared__ TileSmem S;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = blockIdx.z;
   const int64_t t = ((int64_t)n * a.tilesY + tile_y) * a.tilesX + tile_x;
   const int x_lo = tile_x << kTileLog, y_lo = tile_y << kTileLog;
   const int x_hi = min(x_lo + kTile - 1, a.W - 1), y_hi = min(y_lo + kTile - 1, a.H - 1);
+  const float x_lo_f = (float)x_lo, y_lo_f = (float)y_lo;
   uint64_t* bar = reinterpret_cast<uint64_t*>(&S.bar);
 
   const uint32_t cnt = a.F > 0 ? tile_count[t] : 0u;  // after bin_kernel<true>: entries of this tile
@@ -451,10 +427,14 @@ __global__ void __launch_bounds__(kRasterThreads, RV_MIN_CTAS) raster_tiles_kern
       bulk_g2s(S.rec, recs + (size_t)off * kRecF4, bytes, bar);
     }
   }
-  *reinterpret_cast<uint4*>(&S.own[tid * 4]) = make_uint4(kOwnEmpty, kOwnEmpty, kOwnEmpty, kOwnEmpty);
-  *reinterpret_cast<ulonglong2*>(&S.zbuf[tid * 4]) = make_ulonglong2(~0ull, ~0ull);
-  *reinterpret_cast<ulonglong2*>(&S.zbuf[tid * 4 + 2]) = make_ulonglong2(~0ull, ~0ull);
-  unsigned long long best[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+  for (int i = tid * 4; i < kTilePix; i += kRasterThreads * 4) {
+    *reinterpret_cast<uint4*>(&S.cell[i]) = make_uint4(kCellNone, kCellNone, kCellNone, kCellNone);
+    *reinterpret_cast<ulonglong2*>(&S.zbuf[i]) = make_ulonglong2(~0ull, ~0ull);
+    *reinterpret_cast<ulonglong2*>(&S.zbuf[i + 2]) = make_ulonglong2(~0ull, ~0ull);
+  }
+  unsigned long long best[kRowsPerWarp];
+#pragma unroll
+  for (int r = 0; r < kRowsPerWarp; ++r) best[r] = ~0ull;
   __syncthreads();  // barrier initialised, pixel state initialised
 
   // (1) small triangles: the tile's own record list, kPassRecs at a time
@@ -468,7 +448,7 @@ __global__ void __launch_bounds__(kRasterThreads, RV_MIN_CTAS) raster_tiles_kern
     }
     mbar_wait(bar, parity);
     parity ^= 1u;
-    tile_pass(S, m, x_lo, y_lo, best);
+    tile_pass(S, m, x_lo, y_lo, x_lo_f, y_lo_f, best);
   }
 
   // (2) large triangles of this image: scan the bounding boxes, build the records of those touching the tile
@@ -499,39 +479,32 @@ __global__ void __launch_bounds__(kRasterThreads, RV_MIN_CTAS) raster_tiles_kern
         if (tri_full(a, n, (int)S.mlist[tid], s) && max(s.bx0, x_lo) <= min(s.bx1, x_hi) && max(s.by0, y_lo) <= min(s.by1, y_hi)) {
           write_record(s, (int)S.mlist[tid], record_meta(s, x_lo, y_lo, x_hi, y_hi, a.W), [&](int q, float4 val) { dst[q] = val; });
         } else {  // cannot happen for a listed triangle; an empty record keeps the pass well defined
+          dst[0] = dst[1] = dst[2] = dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
           dst[4] = make_float4(0.f, __int_as_float((1 << RASTER_META_BY0) | (0 << RASTER_META_BY1)), 0.f, 0.f);
         }
       }
       __syncthreads();
-      tile_pass(S, m, x_lo, y_lo, best);
+      tile_pass(S, m, x_lo, y_lo, x_lo_f, y_lo_f, best);
       if (tid == 0) S.nmatch = 0;
       __syncthreads();
     }
   }
 
-  // (3) resolve + store (:402-415): empty -> index -1 (low word all ones), depth 0
-  const int ly = tid >> 3, lx = (tid & 7) * 4;
-  const int p4 = pix_slot(ly, lx);
-  const int x = x_lo + lx, y = y_lo + ly;
-  if (y > y_hi || x > x_hi) return;
-  int ids[4];
-  float dps[4];
+  // (3) resolve + store (:402-415): empty -> index -1 (low word all ones), depth 0.  Lane = pixel of a row: every warp
+  // store is one full 128-byte line of index_img / depth_img.
+  const int x = x_lo + lane;
+  if (x > x_hi) return;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const unsigned long long zb = S.zbuf[p4 + j];
-    const unsigned long long k = zb < best[j] ? zb : best[j];
+  for (int r = 0; r < kRowsPerWarp; ++r) {
+    const int ly = wid * kRowsPerWarp + r;
+    const int y = y_lo + ly;
+    if (y > y_hi) break;
+    const unsigned long long zb = S.zbuf[(ly << kTileLog) + lane];
+    const unsigned long long k = zb < best[r] ? zb : best[r];
     const uint32_t d = (uint32_t)(k >> 32);
-    ids[j] = (int)(uint32_t)k;
-    dps[j] = d == 0xFFFFFFFFu ? 0.f : __uint_as_float(d);
-  }
-  const int64_t o = (int64_t)n * a.H * a.W + (int64_t)y * a.W + x;
-  if ((a.W & 3) == 0) {  // the quad is entirely inside the image and 16-B aligned
-    stg_stream_i4(index_img + o, make_int4(ids[0], ids[1], ids[2], ids[3]));
-    stg_stream_f4(depth_img + o, make_float4(dps[0], dps[1], dps[2], dps[3]));
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (x + j <= x_hi) { index_img[o + j] = ids[j]; depth_img[o + j] = dps[j]; }
+    const int64_t o = (int64_t)n * a.H * a.W + (int64_t)y * a.W + x;
+    index_img[o] = (int)(uint32_t)k;
+    depth_img[o] = d == 0xFFFFFFFFu ? 0.f : __uint_as_float(d);
   }
 }
 

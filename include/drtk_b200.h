@@ -313,7 +313,7 @@ int drtk_b200_batch_sum_allreduce(const float* x, int64_t N, int64_t M, int64_t 
  * float64 dispatch of the six hot-path launchers (the reference instantiates every kernel for float and double,
  * src/include/kernel_utils.h:47-57).  Same arguments and contracts as the float entry points above, with double
  * data; no workspace except the packed 64-bit z-buffer of the rasteriser; `rasterize_f64` still writes a float
- * depth_img (src/rasterize/rasterize_kernel.cu:481) and does not offer wireframe mode.  Plain kernels (thread per
+ * depth_img (src/rasterize/rasterize_kernel.cu:481); wireframe mode included (:492-535).  Plain kernels (thread per
  * pixel, atomicAdd(double)): fp64 is for gradient checks, not throughput.
  * ------------------------------------------------------------------------------------- */
 size_t drtk_b200_rasterize_f64_workspace_bytes(int64_t N, int64_t H, int64_t W);

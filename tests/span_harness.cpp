@@ -111,6 +111,16 @@ int main(int argc, char** argv) {
       for (int k = 0; k < 3; ++k) row[k] = edge_row_term((float)y, s.oy[k], s.ax[k]);
       int xs, xe;
       row_span_exact(s.ox, s.ay, row, s.tl_bits, xs0, xe0, xs, xe);
+      // the tile kernel's variant (supplied reciprocals, float bounds, no XU instructions) must agree
+      {
+        const float ray[3] = {core_rcp(s.ay[0]), core_rcp(s.ay[1]), core_rcp(s.ay[2])};
+        const float x_lo_f = (float)(tx * 32);
+        float lo, hi;
+        row_span_fast(s.ox, s.ay, row, ray, s.tl_bits, x_lo_f + small_i2f(xs0 - tx * 32), x_lo_f + small_i2f(xe0 - tx * 32), lo, hi);
+        const int fxs = tx * 32 + small_f2i(lo - x_lo_f), fxe = tx * 32 + small_f2i((hi - x_lo_f) + 1.f) - 1;
+        const bool e1 = xs > xe, e2 = fxs > fxe;
+        if (e1 != e2 || (!e1 && (fxs != xs || fxe != xe))) { ++mism; if (printed++ < 10) fprintf(stderr, "FAST variant differs: [%d,%d] vs [%d,%d]\n", fxs, fxe, xs, xe); }
+      }
       bool bad = false;
       int n_in = 0;
       for (int x = xs0; x <= xe0; ++x) {

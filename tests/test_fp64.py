@@ -114,7 +114,31 @@ def test_f64_strided_and_errors():
     d1, b1 = drtk_b200.render(vs, vid, i1)
     d2, b2 = drtk_b200.render(vs.contiguous(), vid, i1)
     assert th.equal(b1, b2) and th.equal(d1, d2)
-    with pytest.raises(RuntimeError, match="unsupported"):
-        drtk_b200.rasterize(vs, vid, H, W, wireframe=True)
+    # wireframe is served in double as well (the reference instantiates rasterize_lines_kernel<double>)
+    iw1 = drtk_b200.rasterize(vs, vid, H, W, wireframe=True)
+    iw2 = drtk_b200.rasterize(vs.contiguous(), vid, H, W, wireframe=True)
+    assert th.equal(iw1, iw2)
     with pytest.raises(RuntimeError, match="same dtype"):
         drtk_b200.interpolate(vs.float(), vid, i1, b1)
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["grid", "overdraw", "two_tri"])
+def test_f64_wireframe_vs_reference_cuda_and_f32(name):
+    """rasterize(..., wireframe=True) for float64 vertices (src/rasterize/rasterize_kernel.cu:492-535 dispatches
+    rasterize_lines_kernel<double>): index_img / depth_img against the reference's CUDA double kernel, and -- away from
+    knife-edge diamond crossings -- against this package's bit-exact float32 wireframe."""
+    v, vi, H, W = scene(name)
+    vid = vi.to(DEV).clone()
+    vid[:, 0] |= (7 << 28)  # all three edges visible (:293-303)
+    v64 = v.to(DEV).double()
+    d, i = drtk_b200.rasterize_with_depth(v64, vid, H, W, wireframe=True)
+    dr, ir = R.rasterize_with_depth(v64, vid, H, W, wireframe=True)
+    assert d.dtype == th.float32 and i.dtype == th.int32
+    assert int((i >= 0).sum()) > 0
+    # double arithmetic, same expressions: the discrete decisions agree except (at most) a handful of exact ties
+    assert int((i != ir).sum()) <= max(2, int(1e-5 * i.numel())), f"{int((i != ir).sum())} pixels differ from the reference"
+    same = i == ir
+    assert float((d - dr).abs()[same].max()) <= 1e-6 * float(dr.abs().max())
+    d32, i32 = drtk_b200.rasterize_with_depth(v.to(DEV), vid, H, W, wireframe=True)
+    assert float((i != i32).float().mean()) < 2e-3

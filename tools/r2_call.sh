@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU visit of round 2 (content is whatever the repo holds when the call is accepted).
-mkdir -p gpurun_out; T=${TAG:-r2b}
+mkdir -p gpurun_out; T=${TAG:-r2c}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/${T}_smi.txt
 timeout 240 python tools/raster_sanity.py > gpurun_out/${T}_sanity.txt 2>&1; rc=$?
 if [ $rc -ne 0 ]; then export DRTK_B200_RASTER_V1=1; echo "SANITY rc=$rc -> falling back to DRTK_B200_RASTER_V1" >> gpurun_out/${T}_sanity.txt; fi
@@ -11,7 +11,7 @@ DRTK_B200_DISPATCH=torch timeout 600 python -m pytest tests/test_gpu_parity.py -
 tail -8 gpurun_out/${T}_pytest_torchops.txt
 O=gpurun_out/${T}_opbench.txt; : > $O
 timeout 200 python tools/opbench.py --ops rasterize --dump /tmp/a.pt >> $O 2>&1
-for v in base swz p120 t128 abl1 abl2 abl3; do
+for v in t256 p104; do
   echo "variant $v" >> $O
   DRTK_B200_LIB=$PWD/drtk_b200/variants/lib_$v.so timeout 200 python tools/opbench.py --ops rasterize --cmp /tmp/a.pt >> $O 2>&1
 done
@@ -19,7 +19,7 @@ DRTK_B200_RASTER_V1=1 timeout 200 python tools/opbench.py --ops rasterize --cmp 
 for cfg in 3 5; do
   echo "config $cfg" >> $O
   timeout 200 python tools/opbench.py --config $cfg --ops rasterize --dump /tmp/c.pt >> $O 2>&1
-  DRTK_B200_LIB=$PWD/drtk_b200/variants/lib_p120.so timeout 200 python tools/opbench.py --config $cfg --ops rasterize --cmp /tmp/c.pt >> $O 2>&1
+  DRTK_B200_LIB=$PWD/drtk_b200/variants/lib_t256.so timeout 200 python tools/opbench.py --config $cfg --ops rasterize --cmp /tmp/c.pt >> $O 2>&1
   DRTK_B200_RASTER_V1=1 timeout 200 python tools/opbench.py --config $cfg --ops rasterize --cmp /tmp/c.pt >> $O 2>&1
 done
 echo "config 4 overdraw" >> $O
