@@ -358,82 +358,158 @@ __device__ __forceinline__ void scatter_pixel(const EdgeArgs& a, const FusedArgs
   }
 }
 
-__global__ void __launch_bounds__(kStripWarps * 32, 4) edge_grad_strip_kernel(EdgeArgs a, FusedArgs fz,
+// The RARE part of a pair -- everything after the two inside tests of pair_eval, plus the scatter through the conduit.
+// The strip kernel runs it in a loop of its own over the few pairs that survive classification, so that its
+// registers and 64-bit address arithmetic do not burden the loop that classifies the bulk of the pairs (neighbouring
+// triangles of a watertight mesh: "adjacent", no contribution).
+__device__ __forceinline__ void pair_contribute(const EdgeArgs& a, const FusedArgs& fz, int n, int ci, int ni, int cx, int cy,
+                                             int axis, bool c_in_n, bool n_in_c) {
+  const int nx = cx + (axis == 0), ny = cy + (axis == 1);
+  const bool cv = ci >= 0, nv = ni >= 0;
+  float4 r;
+  if (!(c_in_n && n_in_c)) {                               // no intersection (:391-393, :408-410)
+    const bool adj = cv && nv && !c_in_n && !n_in_c;      // (:338-341)
+    const bool c_over = c_in_n && !n_in_c, n_over = n_in_c && !c_in_n;
+    const bool c_zero = !cv || n_over || adj, n_zero = !nv || c_over || adj;
+    if (c_zero && n_zero) return;
+    const float g = grad_dot(a, n, cx, cy, nx, ny);
+    r = make_float4(c_zero ? 0.f : g, 0.f, n_zero ? 0.f : g, 0.f);
+  } else {                                                 // intersection (:394-406, :411-423)
+    const float g = grad_dot(a, n, cx, cy, nx, ny);
+    const float3 nc = tri_normal(a, n, ci), nn = tri_normal(a, n, ni);
+    const float nca = axis == 0 ? nc.x : nc.y, nna = axis == 0 ? nn.x : nn.y;
+    const float2 dc = dp_dr(nca, nc.z, nna, nn.z, a.max_dp_dr);
+    const float2 dn = dp_dr(nna, nn.z, nca, nc.z, a.max_dp_dr);
+    r = make_float4(g * dc.x, g * dc.y, g * dn.x, g * dn.y);
+  }
+  // final negation of the reference (:431-445) folded in
+  scatter_pixel(a, fz, n, ci, cx, cy, axis, -r.x, -r.y);
+  scatter_pixel(a, fz, n, ni, nx, ny, axis, -r.z, -r.w);
+}
+
+// Work item of a warp: a block of kStripRows consecutive centre rows x 256 columns.  The row below a centre row is the
+// next centre row, so it stays in registers (one index-row load per row instead of two).
+constexpr int kStripRows = 4;
+
+__global__ void __launch_bounds__(kStripWarps * 32, 4) edge_grad_strip_kernel(const __grid_constant__ EdgeArgs a,
+                                                                           const __grid_constant__ FusedArgs fz,
                                                                            const float4* __restrict__ table,
-                                                                           int strips_per_row, int64_t num_strips) {
+                                                                           int strips_per_row, int row_blocks,
+                                                                           int64_t num_items) {
   __shared__ int s_own[kStripWarps][kStripPx + 1];
   __shared__ int s_below[kStripWarps][kStripPx];
   __shared__ unsigned short s_jobs[kStripWarps][2 * kStripPx];
+  __shared__ unsigned short s_keep[kStripWarps][2 * kStripPx];  // pairs that survive classification
+  __shared__ int n_keep[kStripWarps];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int* own = s_own[wid];
   int* below = s_below[wid];
   unsigned short* jobs = s_jobs[wid];
+  unsigned short* keepq = s_keep[wid];
+  if (lane == 0) n_keep[wid] = 0;
+  __syncwarp();
   const int64_t warp0 = (int64_t)blockIdx.x * kStripWarps + wid, nwarps = (int64_t)gridDim.x * kStripWarps;
-  const int64_t strips_per_img = (int64_t)strips_per_row * (a.H - 1);  // the last row holds no centre pixel (:270)
+  const int items_per_img = strips_per_row * row_blocks;
 
-  for (int64_t s = warp0; s < num_strips; s += nwarps) {
-    const int n = (int)(s / strips_per_img);
-    const int r = (int)(s - (int64_t)n * strips_per_img);
-    const int y = r / strips_per_row, sx = r - y * strips_per_row;
+  for (int64_t s = warp0; s < num_items; s += nwarps) {
+    const int n = (int)(s / items_per_img);
+    const int r = (int)(s - (int64_t)n * items_per_img);
+    const int yb = r / strips_per_row, sx = r - yb * strips_per_row;
+    const int y0 = yb * kStripRows;
     const int x = sx * kStripPx + lane * 8;
-    const int32_t* row = a.index_img + (int64_t)n * a.is.s0 + (int64_t)y * a.is.s1;
-    int id[9], dn[8];
     const bool live = x < a.W;  // W % 8 == 0: a lane's eight pixels are all inside or all outside
-    if (live) {
-      const int4 p = ldg_stream_i4(row + x), q = ldg_stream_i4(row + x + 4);
-      const int4 u = __ldg(reinterpret_cast<const int4*>(row + a.is.s1 + x)),
-                 w = __ldg(reinterpret_cast<const int4*>(row + a.is.s1 + x + 4));  // re-read as "own" by the next row
-      id[0] = p.x; id[1] = p.y; id[2] = p.z; id[3] = p.w; id[4] = q.x; id[5] = q.y; id[6] = q.z; id[7] = q.w;
-      dn[0] = u.x; dn[1] = u.y; dn[2] = u.z; dn[3] = u.w; dn[4] = w.x; dn[5] = w.y; dn[6] = w.z; dn[7] = w.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { id[j] = -1; dn[j] = -1; }
-    }
-    id[8] = __shfl_down_sync(0xffffffffu, id[0], 1);
-    if (lane == 31) id[8] = (live && x + 8 < a.W) ? row[x + 8] : -1;
-    // candidate pairs: bit j = (j, j+1) horizontal, bit 8+j = (j, below) vertical; centres need x < W-1
-    unsigned m = 0;
-    if (live) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const bool centre = x + j < a.W - 1;
-        m |= (centre && id[j] != id[j + 1]) ? (1u << j) : 0u;
-        m |= (centre && id[j] != dn[j]) ? (0x100u << j) : 0u;
-      }
-    }
-    if (__all_sync(0xffffffffu, m == 0u)) continue;
-    // stage the ids for the job phase, compact the jobs
-    __syncwarp();  // previous strip's readers are done
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { own[lane * 8 + j] = id[j]; below[lane * 8 + j] = dn[j]; }
-    if (lane == 31) own[kStripPx] = id[8];
-    const int cnt = __popc(m);
-    int off = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, off, d);
-      if (lane >= d) off += t;
-    }
-    const int total = __shfl_sync(0xffffffffu, off, 31);
-    off -= cnt;
-    while (m) {
-      const int bit = __ffs(m) - 1;
-      m &= m - 1;
-      jobs[off++] = (unsigned short)(((bit >> 3) << 8) | (lane * 8 + (bit & 7)));
-    }
-    __syncwarp();
+    const int32_t* img_n = a.index_img + (int64_t)n * a.is.s0;
     const TableFetch fetch{table + (int64_t)n * a.F * 2};
-    for (int q = lane; q < total; q += 32) {
-      const int job = jobs[q];
-      const int axis = job >> 8, lx = job & 0xff;
-      const int ci = own[lx];
-      const int ni = axis == 0 ? own[lx + 1] : below[lx];
-      const int cx = sx * kStripPx + lx, cy = y;
-      const int nx = cx + (axis == 0), ny = cy + (axis == 1);
-      const float4 rr = pair_eval(a, n, ci, ni, cx, cy, nx, ny, axis, fetch);
-      // final negation of the reference (:431-445) folded in
-      scatter_pixel(a, fz, n, ci, cx, cy, axis, -rr.x, -rr.y);
-      scatter_pixel(a, fz, n, ni, nx, ny, axis, -rr.z, -rr.w);
+    int id[9], dn[8];
+    int next_first = -1;  // first pixel of the next lane's... (right neighbour of this lane's last pixel), row below
+    {
+      const int32_t* row = img_n + (int64_t)y0 * a.is.s1;
+      if (live) {
+        const int4 p = ldg_stream_i4(row + x), q = ldg_stream_i4(row + x + 4);
+        dn[0] = p.x; dn[1] = p.y; dn[2] = p.z; dn[3] = p.w; dn[4] = q.x; dn[5] = q.y; dn[6] = q.z; dn[7] = q.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dn[j] = -1;
+      }
+      next_first = __shfl_down_sync(0xffffffffu, dn[0], 1);
+      if (lane == 31) next_first = (live && x + 8 < a.W) ? row[x + 8] : -1;
+    }
+#pragma unroll 1
+    for (int ry = 0; ry < kStripRows; ++ry) {
+      const int y = y0 + ry;
+      if (y >= a.H - 1) break;  // the last image row holds no centre pixel (:270); uniform over the warp
+      // the row loaded as "below" in the previous step is this step's centre row
+#pragma unroll
+      for (int j = 0; j < 8; ++j) id[j] = dn[j];
+      id[8] = next_first;
+      const int32_t* row = img_n + (int64_t)(y + 1) * a.is.s1;
+      if (live) {
+        const int4 u = ldg_stream_i4(row + x), w = ldg_stream_i4(row + x + 4);
+        dn[0] = u.x; dn[1] = u.y; dn[2] = u.z; dn[3] = u.w; dn[4] = w.x; dn[5] = w.y; dn[6] = w.z; dn[7] = w.w;
+      }
+      next_first = __shfl_down_sync(0xffffffffu, dn[0], 1);
+      if (lane == 31) next_first = (live && x + 8 < a.W) ? row[x + 8] : -1;
+      // candidate pairs: bit j = (j, j+1) horizontal, bit 8+j = (j, below) vertical; centres need x < W-1
+      unsigned m = 0;
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool centre = x + j < a.W - 1;
+          m |= (centre && id[j] != id[j + 1]) ? (1u << j) : 0u;
+          m |= (centre && id[j] != dn[j]) ? (0x100u << j) : 0u;
+        }
+      }
+      if (__all_sync(0xffffffffu, m == 0u)) continue;
+      // stage the ids for the job phase, compact the jobs
+      __syncwarp();  // previous step's readers are done
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { own[lane * 8 + j] = id[j]; below[lane * 8 + j] = dn[j]; }
+      if (lane == 31) own[kStripPx] = id[8];
+      const int cnt = __popc(m);
+      int off = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, off, d);
+        if (lane >= d) off += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, off, 31);
+      off -= cnt;
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        jobs[off++] = (unsigned short)(((bit >> 3) << 8) | (lane * 8 + (bit & 7)));
+      }
+      __syncwarp();
+      for (int q = lane; q < total; q += 32) {
+        const int job = jobs[q];
+        const int axis = job >> 8, lx = job & 0xff;
+        const int ci = own[lx];
+        const int ni = axis == 0 ? own[lx + 1] : below[lx];
+        const int cx = sx * kStripPx + lx;
+        bool c_in_n = false, n_in_c = false, keep = true;
+        if (ci >= 0 && ni >= 0) {  // (:320-325) the bulk: two neighbouring triangles, neither covers the other's pixel
+          Tri2 tc, tn;
+          fetch(ci, tc);
+          fetch(ni, tn);
+          c_in_n = pix_in_tri(tn, cx, y);
+          n_in_c = pix_in_tri(tc, cx + (axis == 0), y + (axis == 1));
+          keep = c_in_n || n_in_c;  // else adjacent (:338-341): no contribution
+        }
+        if (keep) keepq[atomicAdd(&n_keep[wid], 1)] = (unsigned short)(job | (c_in_n ? 0x4000 : 0) | (n_in_c ? 0x8000 : 0));
+      }
+      __syncwarp();
+      const int nk = n_keep[wid];
+      __syncwarp();
+      if (nk == 0) continue;
+      if (lane == 0) n_keep[wid] = 0;
+      // survivors: silhouettes, occlusions, intersections
+      for (int q = lane; q < nk; q += 32) {
+        const int job = keepq[q];
+        const int axis = (job >> 8) & 1, lx = job & 0xff;
+        const int ci = own[lx];
+        const int ni = axis == 0 ? own[lx + 1] : below[lx];
+        pair_contribute(a, fz, n, ci, ni, sx * kStripPx + lx, y, axis, (job & 0x4000) != 0, (job & 0x8000) != 0);
+      }
     }
   }
 }
@@ -493,11 +569,12 @@ static int edge_launch(const float* v_pix, const int64_t* v_strides, const float
     float4* table = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(workspace) + 31) & ~uintptr_t(31));
     xy_table_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)N), 256, 0, stream>>>(a, table, grad_v_pix, N * V * 3);
     const int strips_per_row = (int)((W + kStripPx - 1) / kStripPx);
-    const int64_t num_strips = N * (H - 1) * strips_per_row;
-    const int64_t need = (num_strips + kStripWarps - 1) / kStripWarps;
-    const int64_t cap = (int64_t)num_sms() * 8 * 4;  // a few strips per warp: short tail, ids loads of neighbours overlap
+    const int row_blocks = (int)((H - 1 + kStripRows - 1) / kStripRows);
+    const int64_t num_items = N * (int64_t)row_blocks * strips_per_row;
+    const int64_t need = (num_items + kStripWarps - 1) / kStripWarps;
+    const int64_t cap = (int64_t)num_sms() * 4 * 4;  // a few items per warp: short tail
     edge_grad_strip_kernel<<<(unsigned)(need < cap ? need : cap), kStripWarps * 32, 0, stream>>>(a, fz, table, strips_per_row,
-                                                                                          num_strips);
+                                                                                          row_blocks, num_items);
     DRTK_CHECK_LAUNCH();
     return 0;
   }

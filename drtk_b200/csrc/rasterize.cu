@@ -379,23 +379,42 @@ __device__ __forceinline__ void tile_pass(TileSmem& S, int m, int x_lo, int y_lo
     const int cs = cell_slot(ly, lane);
     const uint32_t c = S.cell[cs];
     const bool is_start = c != kCellNone;
-    const int len = is_start ? (int)((c >> 8) & 31u) - lane + 1 : 0;
-    const int L = __reduce_max_sync(0xffffffffu, len);  // longest span of this row
-    if (L == 0) continue;                               // nothing in this row (uniform)
-    if (is_start) S.cell[cs] = kCellNone;               // for the next pass
     const unsigned starts = __ballot_sync(0xffffffffu, is_start);
-    // starts that can cover this pixel: those in [lane - L + 1, lane]
-    const int first = max(lane - L + 1, 0);
-    unsigned cand = starts & ((2u << lane) - 1u) & ~((1u << first) - 1u);
+    if (starts == 0u) continue;            // nothing in this row (uniform)
+    if (is_start) S.cell[cs] = kCellNone;  // for the next pass
     const float py = y_lo_f + small_i2f(ly);
-    while (__any_sync(0xffffffffu, cand != 0u)) {
-      const int s = cand ? 31 - __clz(cand) : lane;
-      const uint32_t sc = __shfl_sync(0xffffffffu, c, s);
-      const bool hit = cand != 0u && lane <= (int)((sc >> 8) & 31u);
-      cand &= ~(1u << s);
-      if (hit) {
-        const unsigned long long key = shade_key(S.rec + (sc & 0xFFu) * kRecF4, px, py);
-        best[r] = key < best[r] ? key : best[r];
+    // nearest span start at or left of this pixel, and the one before it
+    const unsigned left = starts & ((2u << lane) - 1u);
+    const int s1 = left ? 31 - __clz(left) : lane;
+    const uint32_t c1 = __shfl_sync(0xffffffffu, c, s1);
+    const bool hit1 = left != 0u && lane <= (int)((c1 >> 8) & 31u);
+    // Do spans of this row overlap (several surfaces)?  A start lane looks at the span that starts before it.
+    const unsigned before = starts & ((1u << lane) - 1u);
+    const int s0 = before ? 31 - __clz(before) : lane;
+    const uint32_t c0 = __shfl_sync(0xffffffffu, c, s0);
+    // running maximum of the span ends left of this start would be exact; the previous span's end is enough to
+    // detect "some overlap in this row", which selects the general loop below
+    const bool overlap = is_start && before != 0u && (int)((c0 >> 8) & 31u) >= lane;
+    if (hit1) {
+      const unsigned long long key = shade_key(S.rec + (c1 & 0xFFu) * kRecF4, px, py);
+      best[r] = key < best[r] ? key : best[r];
+    }
+    if (__any_sync(0xffffffffu, overlap)) {
+      // general case: every start within the longest span length to the left may cover this pixel
+      const int len = is_start ? (int)((c >> 8) & 31u) - lane + 1 : 0;
+      const int L = __reduce_max_sync(0xffffffffu, len);
+      const int first = max(lane - L + 1, 0);
+      unsigned cand = left & ~((1u << first) - 1u);
+      if (left) cand &= ~(1u << s1);  // already shaded above
+      while (__any_sync(0xffffffffu, cand != 0u)) {
+        const int s = cand ? 31 - __clz(cand) : lane;
+        const uint32_t sc = __shfl_sync(0xffffffffu, c, s);
+        const bool hit = cand != 0u && lane <= (int)((sc >> 8) & 31u);
+        cand &= ~(1u << s);
+        if (hit) {
+          const unsigned long long key = shade_key(S.rec + (sc & 0xFFu) * kRecF4, px, py);
+          best[r] = key < best[r] ? key : best[r];
+        }
       }
     }
   }
@@ -494,17 +513,21 @@ __global__ void __launch_bounds__(kRasterThreads, RV_MIN_CTAS) raster_tiles_kern
   // store is one full 128-byte line of index_img / depth_img.
   const int x = x_lo + lane;
   if (x > x_hi) return;
+  const int row0 = wid * kRowsPerWarp;
+  const int64_t o0 = ((int64_t)n * a.H + (y_lo + row0)) * a.W + x;
+  int32_t* ip = index_img + o0;
+  float* dp = depth_img + o0;
+  const int nrows = min(kRowsPerWarp, y_hi - (y_lo + row0) + 1);
 #pragma unroll
   for (int r = 0; r < kRowsPerWarp; ++r) {
-    const int ly = wid * kRowsPerWarp + r;
-    const int y = y_lo + ly;
-    if (y > y_hi) break;
-    const unsigned long long zb = S.zbuf[(ly << kTileLog) + lane];
+    if (r >= nrows) break;
+    const unsigned long long zb = S.zbuf[((row0 + r) << kTileLog) + lane];
     const unsigned long long k = zb < best[r] ? zb : best[r];
     const uint32_t d = (uint32_t)(k >> 32);
-    const int64_t o = (int64_t)n * a.H * a.W + (int64_t)y * a.W + x;
-    index_img[o] = (int)(uint32_t)k;
-    depth_img[o] = d == 0xFFFFFFFFu ? 0.f : __uint_as_float(d);
+    *ip = (int)(uint32_t)k;
+    *dp = d == 0xFFFFFFFFu ? 0.f : __uint_as_float(d);
+    ip += a.W;
+    dp += a.W;
   }
 }
 

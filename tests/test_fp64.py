@@ -12,6 +12,8 @@ from oracle import oracle as O
 from oracle import ref as R
 from tests.util import assert_close
 
+needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref/*.so (reference build) not present")
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
