@@ -323,9 +323,10 @@ constexpr int kStripPx = 256, kStripWarps = 8;
 
 // Also zero-fills grad_v_pix, which the strip kernel accumulates into (saves a memset launch per step).
 __global__ void __launch_bounds__(256) xy_table_kernel(EdgeArgs a, float4* __restrict__ table, float* __restrict__ zero,
-                                                       int64_t zero_count) {
+                                                       int64_t zero_count, unsigned long long* __restrict__ work_counter) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *work_counter = 0ull;  // the strip kernel's item counter
   {
     const int64_t gid = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * gridDim.y * blockDim.x;
@@ -389,13 +390,17 @@ __device__ __forceinline__ void pair_contribute(const EdgeArgs& a, const FusedAr
 
 // Work item of a warp: a block of kStripRows consecutive centre rows x 256 columns.  The row below a centre row is the
 // next centre row, so it stays in registers (one index-row load per row instead of two).
-constexpr int kStripRows = 4;
+#ifndef DRTK_EDGE_STRIP_ROWS
+#define DRTK_EDGE_STRIP_ROWS 4
+#endif
+constexpr int kStripRows = DRTK_EDGE_STRIP_ROWS;
 
 __global__ void __launch_bounds__(kStripWarps * 32, 4) edge_grad_strip_kernel(const __grid_constant__ EdgeArgs a,
                                                                            const __grid_constant__ FusedArgs fz,
                                                                            const float4* __restrict__ table,
                                                                            int strips_per_row, int row_blocks,
-                                                                           int64_t num_items) {
+                                                                           int64_t num_items,
+                                                                           unsigned long long* __restrict__ work_counter) {
   __shared__ int s_own[kStripWarps][kStripPx + 1];
   __shared__ int s_below[kStripWarps][kStripPx];
   __shared__ unsigned short s_jobs[kStripWarps][2 * kStripPx];
@@ -408,10 +413,15 @@ __global__ void __launch_bounds__(kStripWarps * 32, 4) edge_grad_strip_kernel(co
   unsigned short* keepq = s_keep[wid];
   if (lane == 0) n_keep[wid] = 0;
   __syncwarp();
-  const int64_t warp0 = (int64_t)blockIdx.x * kStripWarps + wid, nwarps = (int64_t)gridDim.x * kStripWarps;
   const int items_per_img = strips_per_row * row_blocks;
 
-  for (int64_t s = warp0; s < num_items; s += nwarps) {
+  // items are handed out dynamically (one atomic per warp and item): the jobs per item vary with the scene, and a
+  // static split left the last wave of warps half empty
+  for (;;) {
+    unsigned long long s = 0;
+    if (lane == 0) s = atomicAdd(work_counter, 1ull);
+    s = __shfl_sync(0xffffffffu, s, 0);
+    if (s >= (unsigned long long)num_items) break;
     const int n = (int)(s / items_per_img);
     const int r = (int)(s - (int64_t)n * items_per_img);
     const int yb = r / strips_per_row, sx = r - yb * strips_per_row;
@@ -565,16 +575,17 @@ static int edge_launch(const float* v_pix, const int64_t* v_strides, const float
   if (fused && F > 0 && W % 8 == 0 && H > 1 && a.is.s2 == 1 && a.is.s1 % 4 == 0 && a.is.s0 % 4 == 0 && al16(index_img) &&
       F <= 65535LL * 256) {
     const size_t tb = (size_t)(N * F) * 32;
-    if (!workspace || workspace_bytes < tb + 32) return DRTK_B200_EWORKSPACE;
+    if (!workspace || workspace_bytes < tb + 64) return DRTK_B200_EWORKSPACE;
     float4* table = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(workspace) + 31) & ~uintptr_t(31));
-    xy_table_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)N), 256, 0, stream>>>(a, table, grad_v_pix, N * V * 3);
+    unsigned long long* work_counter = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(table) + tb);
+    xy_table_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)N), 256, 0, stream>>>(a, table, grad_v_pix, N * V * 3, work_counter);
     const int strips_per_row = (int)((W + kStripPx - 1) / kStripPx);
     const int row_blocks = (int)((H - 1 + kStripRows - 1) / kStripRows);
     const int64_t num_items = N * (int64_t)row_blocks * strips_per_row;
     const int64_t need = (num_items + kStripWarps - 1) / kStripWarps;
-    const int64_t cap = (int64_t)num_sms() * 4 * 4;  // a few items per warp: short tail
+    const int64_t cap = (int64_t)num_sms() * 4;  // one resident wave; the warps pull items from a counter
     edge_grad_strip_kernel<<<(unsigned)(need < cap ? need : cap), kStripWarps * 32, 0, stream>>>(a, fz, table, strips_per_row,
-                                                                                          row_blocks, num_items);
+                                                                                          row_blocks, num_items, work_counter);
     DRTK_CHECK_LAUNCH();
     return 0;
   }
@@ -611,5 +622,5 @@ extern "C" int drtk_b200_edge_grad_backward_fused(
 }
 
 extern "C" size_t drtk_b200_edge_grad_backward_fused_workspace_bytes(int64_t N, int64_t F) {
-  return (N <= 0 || F <= 0) ? 0 : (size_t)(N * F) * 32 + 32;  // + slack to align the table to 32 B (256-bit loads)
+  return (N <= 0 || F <= 0) ? 0 : (size_t)(N * F) * 32 + 64;  // + slack to align the table to 32 B (256-bit loads) + item counter
 }

@@ -362,11 +362,12 @@ __device__ __forceinline__ void tile_pass(TileSmem& S, int m, int x_lo, int y_lo
         if (sample_covered(ox, ay, row, tl, (float)(x_lo + lx))) { lxs = min(lxs, lx); lxe = max(lxe, lx); }
     }
     if (lxs > lxe) continue;
+    // Register the span at its start cell.  If another span of this pass already starts on that pixel (overlapping
+    // surfaces), shade that ONE pixel here (64-bit minimum) and register the rest of the span one pixel further right.
     const uint32_t mine = (uint32_t)slot | ((uint32_t)lxe << 8);
-    if (atomicCAS(&S.cell[cell_slot(ly, lxs)], kCellNone, mine) != kCellNone) {
-      // another span of this pass starts on the same pixel (overlapping surfaces): shade this span here
-      for (int lx = lxs; lx <= lxe; ++lx)
-        atomicMin(&S.zbuf[(ly << kTileLog) + lx], shade_key(rec, x_lo_f + small_i2f(lx), py));
+    while (lxs <= lxe && atomicCAS(&S.cell[cell_slot(ly, lxs)], kCellNone, mine) != kCellNone) {
+      atomicMin(&S.zbuf[(ly << kTileLog) + lxs], shade_key(rec, x_lo_f + small_i2f(lxs), py));
+      ++lxs;
     }
   }
   __syncthreads();
@@ -395,27 +396,36 @@ __device__ __forceinline__ void tile_pass(TileSmem& S, int m, int x_lo, int y_lo
     // running maximum of the span ends left of this start would be exact; the previous span's end is enough to
     // detect "some overlap in this row", which selects the general loop below
     const bool overlap = is_start && before != 0u && (int)((c0 >> 8) & 31u) >= lane;
-    if (hit1) {
-      const unsigned long long key = shade_key(S.rec + (c1 & 0xFFu) * kRecF4, px, py);
-      best[r] = key < best[r] ? key : best[r];
-    }
+    // covering spans are first COLLECTED (up to four record slots per pixel, one byte each), then shaded together:
+    // all lanes shade their k-th span in the same step, whatever the order in which they found it
+    uint32_t hits = hit1 ? (0xFFFFFF00u | (c1 & 0xFFu)) : 0xFFFFFFFFu;
     if (__any_sync(0xffffffffu, overlap)) {
       // general case: every start within the longest span length to the left may cover this pixel
       const int len = is_start ? (int)((c >> 8) & 31u) - lane + 1 : 0;
       const int L = __reduce_max_sync(0xffffffffu, len);
       const int first = max(lane - L + 1, 0);
       unsigned cand = left & ~((1u << first) - 1u);
-      if (left) cand &= ~(1u << s1);  // already shaded above
+      if (left) cand &= ~(1u << s1);  // already collected
       while (__any_sync(0xffffffffu, cand != 0u)) {
         const int s = cand ? 31 - __clz(cand) : lane;
         const uint32_t sc = __shfl_sync(0xffffffffu, c, s);
         const bool hit = cand != 0u && lane <= (int)((sc >> 8) & 31u);
         cand &= ~(1u << s);
         if (hit) {
-          const unsigned long long key = shade_key(S.rec + (sc & 0xFFu) * kRecF4, px, py);
-          best[r] = key < best[r] ? key : best[r];
+          if ((hits >> 24) != 0xFFu) {  // a fifth span on this pixel (rare): make room by shading the oldest now
+            const unsigned long long key = shade_key(S.rec + (hits >> 24) * kRecF4, px, py);
+            best[r] = key < best[r] ? key : best[r];
+          }
+          hits = (hits << 8) | (sc & 0xFFu);
         }
       }
+    }
+    while (__any_sync(0xffffffffu, (hits & 0xFFu) != 0xFFu)) {
+      if ((hits & 0xFFu) != 0xFFu) {
+        const unsigned long long key = shade_key(S.rec + (hits & 0xFFu) * kRecF4, px, py);
+        best[r] = key < best[r] ? key : best[r];
+      }
+      hits = (hits >> 8) | 0xFF000000u;
     }
   }
   __syncthreads();  // S.rec may be overwritten now

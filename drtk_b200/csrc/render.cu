@@ -316,6 +316,9 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs b, float*
 // The per-pixel kernel above spends ~310 thread-instructions per pixel, two thirds of them in the segmented
 // shuffle reduction and in re-deriving the triangle for every pixel.
 constexpr int kWalkPx = 8;
+#ifndef DRTK_RENDER_BWD_CHUNKS
+#define DRTK_RENDER_BWD_CHUNKS 2  // 8-pixel chunks per thread (1 = the round-1 mapping)
+#endif
 
 struct RunSetup {  // per-triangle constants of the backward (:186-219 of the reference)
   float p0x, p0y, v01x, v01y, v02x, v02y, rden, d0, d1, d2, rz0, rz1, rz2;  // rzk = 1/zk^2 (0 when zk was clamped)
@@ -365,39 +368,17 @@ __device__ __forceinline__ void run_setup(const float4* __restrict__ row, RunSet
   r.i0 = __float_as_int(d.y); r.i1 = __float_as_int(d.z); r.i2 = __float_as_int(d.w);
 }
 
-template <bool HAS_GB, bool HAS_GD>
+// CHUNKS: consecutive 8-pixel chunks walked by one thread with the run state carried from chunk to chunk (a run cut
+// at a thread boundary costs an extra table fetch and an extra flush: 8 px per thread = 3 runs per 8 px on the
+// 100k-triangle mesh, 16 px per thread = 5 runs per 16 px).
+template <bool HAS_GB, bool HAS_GD, int CHUNKS>
 __global__ void __launch_bounds__(128) render_bwd_walk_kernel(RenderBwdArgs b, const float4* __restrict__ table,
                                                               float* __restrict__ gpad) {
   const RenderArgs& a = b.r;
   const int HW = a.H * a.W;
   const int n = blockIdx.y;
-  const int rem = (blockIdx.x * blockDim.x + threadIdx.x) * kWalkPx;
-  if (rem >= HW) return;
-  const int32_t* ip = a.index_img + (int64_t)n * HW + rem;
-  const int4 ia = ldg_stream_i4(ip), ib = ldg_stream_i4(ip + 4);
-  const int ids[kWalkPx] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
-  if ((ia.x & ia.y & ia.z & ia.w & ib.x & ib.y & ib.z & ib.w) == -1) return;  // all empty
-  float gb0[kWalkPx], gb1[kWalkPx], gb2[kWalkPx], gdp[kWalkPx];
-  if (HAS_GB) {
-    const float* gp = b.grad_bary + (int64_t)n * 3 * HW + rem;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const float4 x = ldg_stream_f4(gp + 4 * q), y = ldg_stream_f4(gp + HW + 4 * q),
-                   z = ldg_stream_f4(gp + 2 * (int64_t)HW + 4 * q);
-      gb0[4 * q] = x.x; gb0[4 * q + 1] = x.y; gb0[4 * q + 2] = x.z; gb0[4 * q + 3] = x.w;
-      gb1[4 * q] = y.x; gb1[4 * q + 1] = y.y; gb1[4 * q + 2] = y.z; gb1[4 * q + 3] = y.w;
-      gb2[4 * q] = z.x; gb2[4 * q + 1] = z.y; gb2[4 * q + 2] = z.z; gb2[4 * q + 3] = z.w;
-    }
-  }
-  if (HAS_GD) {
-    const float* gp = b.grad_depth + (int64_t)n * HW + rem;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const float4 x = ldg_stream_f4(gp + 4 * q);
-      gdp[4 * q] = x.x; gdp[4 * q + 1] = x.y; gdp[4 * q + 2] = x.z; gdp[4 * q + 3] = x.w;
-    }
-  }
-  const int h = rem / a.W, w0 = rem - h * a.W;  // W % 8 == 0: the eight pixels share the row
+  const int rem0 = (blockIdx.x * blockDim.x + threadIdx.x) * (kWalkPx * CHUNKS);
+  if (rem0 >= HW) return;
   const float4* tn = table + (int64_t)n * a.F * 4;
   float* gvn = gpad + (int64_t)n * a.V * 4;
 
@@ -409,42 +390,75 @@ __global__ void __launch_bounds__(128) render_bwd_walk_kernel(RenderBwdArgs b, c
     red_add_v4(gvn + (int64_t)r.i1 * 4, acc[3], acc[4], acc[5], 0.f);
     red_add_v4(gvn + (int64_t)r.i2 * 4, acc[6], acc[7], acc[8], 0.f);
   };
-#pragma unroll
-  for (int j = 0; j < kWalkPx; ++j) {
-    const int id = ids[j];
-    if (id == -1) continue;
-    if (id != cur) {
-      if (cur != -1) flush();
-      run_setup(tn + (int64_t)id * 4, r);
-      cur = id;
-#pragma unroll
-      for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+#pragma unroll 1
+  for (int ch = 0; ch < CHUNKS; ++ch) {
+    const int rem = rem0 + ch * kWalkPx;
+    if (rem >= HW) break;
+    const int32_t* ip = a.index_img + (int64_t)n * HW + rem;
+    const int4 ia = ldg_stream_i4(ip), ib = ldg_stream_i4(ip + 4);
+    const int ids[kWalkPx] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+    if ((ia.x & ia.y & ia.z & ia.w & ib.x & ib.y & ib.z & ib.w) == -1) {  // all empty: a run cannot continue through it
+      if (cur != -1) { flush(); cur = -1; }
+      continue;
     }
-    const float qx = (float)(w0 + j) - r.p0x, qy = (float)h - r.p0y;
-    const float b1 = (qx * r.v02y - qy * r.v02x) * r.rden;
-    const float b2 = (qy * r.v01x - qx * r.v01y) * r.rden;
-    const float b0 = 1.f - b1 - b2;
-    const float dinv = r.d0 * b0 + r.d1 * b1 + r.d2 * b2;
-    const float dinv_e = epsclamp(dinv);
-    const float depth = rcp_approx(dinv_e);
-    const float g0 = HAS_GB ? gb0[j] : 0.f, g1 = HAS_GB ? gb1[j] : 0.f, g2 = HAS_GB ? gb2[j] : 0.f;
-    const float gd = HAS_GD ? gdp[j] : 0.f;
-    const float dL_depth = gd + (g0 * r.d0 * b0 + g1 * r.d1 * b1 + g2 * r.d2 * b2);
-    const float dL_dinv = (dinv_e != dinv) ? 0.f : (-dL_depth * rcp_approx(dinv * dinv));
-    const float dLd0 = g0 * b0 * depth + dL_dinv * b0;
-    const float dLd1 = g1 * b1 * depth + dL_dinv * b1;
-    const float dLd2 = g2 * b2 * depth + dL_dinv * b2;
-    acc[2] += -dLd0 * r.rz0; acc[5] += -dLd1 * r.rz1; acc[8] += -dLd2 * r.rz2;
-    const float dLb0 = g0 * r.d0 * depth + dL_dinv * r.d0;
-    const float dLb1 = g1 * r.d1 * depth + dL_dinv * r.d1;
-    const float dLb2 = g2 * r.d2 * depth + dL_dinv * r.d2;
-    const float e1 = (-dLb0 + dLb1) * r.rden, e2 = (-dLb0 + dLb2) * r.rden;
-    const float dL_den = r.den_clamped ? 0.f : -(e1 * b1 + e2 * b2);
-    const float dqx = e1 * r.v02y - e2 * r.v01y, dqy = -e1 * r.v02x + e2 * r.v01x;
-    const float dv02x = -e1 * qy - dL_den * r.v01y, dv02y = e1 * qx + dL_den * r.v01x;
-    const float dv01x = e2 * qy + dL_den * r.v02y, dv01y = -e2 * qx - dL_den * r.v02x;
-    acc[0] += -dv02x - dv01x - dqx; acc[1] += -dv02y - dv01y - dqy;
-    acc[3] += dv01x; acc[4] += dv01y; acc[6] += dv02x; acc[7] += dv02y;
+    float gb0[kWalkPx], gb1[kWalkPx], gb2[kWalkPx], gdp[kWalkPx];
+    if (HAS_GB) {
+      const float* gp = b.grad_bary + (int64_t)n * 3 * HW + rem;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 x = ldg_stream_f4(gp + 4 * q), y = ldg_stream_f4(gp + HW + 4 * q),
+                     z = ldg_stream_f4(gp + 2 * (int64_t)HW + 4 * q);
+        gb0[4 * q] = x.x; gb0[4 * q + 1] = x.y; gb0[4 * q + 2] = x.z; gb0[4 * q + 3] = x.w;
+        gb1[4 * q] = y.x; gb1[4 * q + 1] = y.y; gb1[4 * q + 2] = y.z; gb1[4 * q + 3] = y.w;
+        gb2[4 * q] = z.x; gb2[4 * q + 1] = z.y; gb2[4 * q + 2] = z.z; gb2[4 * q + 3] = z.w;
+      }
+    }
+    if (HAS_GD) {
+      const float* gp = b.grad_depth + (int64_t)n * HW + rem;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 x = ldg_stream_f4(gp + 4 * q);
+        gdp[4 * q] = x.x; gdp[4 * q + 1] = x.y; gdp[4 * q + 2] = x.z; gdp[4 * q + 3] = x.w;
+      }
+    }
+    const int h = rem / a.W, w0 = rem - h * a.W;  // W % 8 == 0: the eight pixels share the row
+#pragma unroll
+    for (int j = 0; j < kWalkPx; ++j) {
+      const int id = ids[j];
+      if (id == -1) continue;
+      if (id != cur) {
+        if (cur != -1) flush();
+        run_setup(tn + (int64_t)id * 4, r);
+        cur = id;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+      }
+      const float qx = (float)(w0 + j) - r.p0x, qy = (float)h - r.p0y;
+      const float b1 = (qx * r.v02y - qy * r.v02x) * r.rden;
+      const float b2 = (qy * r.v01x - qx * r.v01y) * r.rden;
+      const float b0 = 1.f - b1 - b2;
+      const float dinv = r.d0 * b0 + r.d1 * b1 + r.d2 * b2;
+      const float dinv_e = epsclamp(dinv);
+      const float depth = rcp_approx(dinv_e);
+      const float g0 = HAS_GB ? gb0[j] : 0.f, g1 = HAS_GB ? gb1[j] : 0.f, g2 = HAS_GB ? gb2[j] : 0.f;
+      const float gd = HAS_GD ? gdp[j] : 0.f;
+      const float dL_depth = gd + (g0 * r.d0 * b0 + g1 * r.d1 * b1 + g2 * r.d2 * b2);
+      const float dL_dinv = (dinv_e != dinv) ? 0.f : (-dL_depth * rcp_approx(dinv * dinv));
+      const float dLd0 = g0 * b0 * depth + dL_dinv * b0;
+      const float dLd1 = g1 * b1 * depth + dL_dinv * b1;
+      const float dLd2 = g2 * b2 * depth + dL_dinv * b2;
+      acc[2] += -dLd0 * r.rz0; acc[5] += -dLd1 * r.rz1; acc[8] += -dLd2 * r.rz2;
+      const float dLb0 = g0 * r.d0 * depth + dL_dinv * r.d0;
+      const float dLb1 = g1 * r.d1 * depth + dL_dinv * r.d1;
+      const float dLb2 = g2 * r.d2 * depth + dL_dinv * r.d2;
+      const float e1 = (-dLb0 + dLb1) * r.rden, e2 = (-dLb0 + dLb2) * r.rden;
+      const float dL_den = r.den_clamped ? 0.f : -(e1 * b1 + e2 * b2);
+      const float dqx = e1 * r.v02y - e2 * r.v01y, dqy = -e1 * r.v02x + e2 * r.v01x;
+      const float dv02x = -e1 * qy - dL_den * r.v01y, dv02y = e1 * qx + dL_den * r.v01x;
+      const float dv01x = e2 * qy + dL_den * r.v02y, dv01y = -e2 * qx - dL_den * r.v02x;
+      acc[0] += -dv02x - dv01x - dqx; acc[1] += -dv02y - dv01y - dqy;
+      acc[3] += dv01x; acc[4] += dv01y; acc[6] += dv02x; acc[7] += dv02y;
+    }
   }
   if (cur != -1) flush();
 }
@@ -577,10 +591,11 @@ extern "C" int drtk_b200_render_backward(const float* v, const int64_t* v_stride
     float* gpad = reinterpret_cast<float*>(ws32 + tb);
     tri_table_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)N), 256, 0, stream>>>(
         b.r, table, reinterpret_cast<float4*>(gpad), (int64_t)(gb / sizeof(float4)));
-    const dim3 wgrid((unsigned)((H * W / kWalkPx + 127) / 128), (unsigned)N);
-    if (grad_bary && grad_depth) render_bwd_walk_kernel<true, true><<<wgrid, 128, 0, stream>>>(b, table, gpad);
-    else if (grad_bary) render_bwd_walk_kernel<true, false><<<wgrid, 128, 0, stream>>>(b, table, gpad);
-    else render_bwd_walk_kernel<false, true><<<wgrid, 128, 0, stream>>>(b, table, gpad);
+    constexpr int CH = DRTK_RENDER_BWD_CHUNKS;
+    const dim3 wgrid((unsigned)((H * W / (kWalkPx * CH) + 127) / 128 + 1), (unsigned)N);
+    if (grad_bary && grad_depth) render_bwd_walk_kernel<true, true, CH><<<wgrid, 128, 0, stream>>>(b, table, gpad);
+    else if (grad_bary) render_bwd_walk_kernel<true, false, CH><<<wgrid, 128, 0, stream>>>(b, table, gpad);
+    else render_bwd_walk_kernel<false, true, CH><<<wgrid, 128, 0, stream>>>(b, table, gpad);
     unpad_kernel<<<(unsigned)((N * V + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(gpad), grad_v, N * V);
     DRTK_CHECK_LAUNCH();
     return 0;
