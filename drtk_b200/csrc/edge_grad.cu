@@ -391,7 +391,7 @@ __device__ __forceinline__ void pair_contribute(const EdgeArgs& a, const FusedAr
 // Work item of a warp: a block of kStripRows consecutive centre rows x 256 columns.  The row below a centre row is the
 // next centre row, so it stays in registers (one index-row load per row instead of two).
 #ifndef DRTK_EDGE_STRIP_ROWS
-#define DRTK_EDGE_STRIP_ROWS 4
+#define DRTK_EDGE_STRIP_ROWS 2  // measured on B200 (config 3 / 4 / 5 / 4-overdraw, ms): 2 -> .090 / .279 / 1.09 / 1.41, 4 -> .110 / .291 / 1.05 / 1.51, 8 -> .130 / .276 / 1.02 / -; round-1 kernel .087 / .283 / 1.14 / 1.67
 #endif
 constexpr int kStripRows = DRTK_EDGE_STRIP_ROWS;
 

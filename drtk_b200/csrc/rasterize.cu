@@ -396,11 +396,18 @@ __device__ __forceinline__ void tile_pass(TileSmem& S, int m, int x_lo, int y_lo
     // running maximum of the span ends left of this start would be exact; the previous span's end is enough to
     // detect "some overlap in this row", which selects the general loop below
     const bool overlap = is_start && before != 0u && (int)((c0 >> 8) & 31u) >= lane;
-    // covering spans are first COLLECTED (up to four record slots per pixel, one byte each), then shaded together:
-    // all lanes shade their k-th span in the same step, whatever the order in which they found it
+    if (!__any_sync(0xffffffffu, overlap)) {  // one surface in this row: the nearest start is the only candidate
+      if (hit1) {
+        const unsigned long long key = shade_key(S.rec + (c1 & 0xFFu) * kRecF4, px, py);
+        best[r] = key < best[r] ? key : best[r];
+      }
+      continue;
+    }
+    // Several surfaces: every start within the longest span length to the left may cover this pixel.  The covering
+    // spans are first COLLECTED (up to four record slots per pixel, one byte each), then shaded together -- all lanes
+    // shade their k-th span in the same step, whatever the order in which they found it.
     uint32_t hits = hit1 ? (0xFFFFFF00u | (c1 & 0xFFu)) : 0xFFFFFFFFu;
-    if (__any_sync(0xffffffffu, overlap)) {
-      // general case: every start within the longest span length to the left may cover this pixel
+    {
       const int len = is_start ? (int)((c >> 8) & 31u) - lane + 1 : 0;
       const int L = __reduce_max_sync(0xffffffffu, len);
       const int first = max(lane - L + 1, 0);

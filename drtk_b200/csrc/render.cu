@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs b, float*
 // shuffle reduction and in re-deriving the triangle for every pixel.
 constexpr int kWalkPx = 8;
 #ifndef DRTK_RENDER_BWD_CHUNKS
-#define DRTK_RENDER_BWD_CHUNKS 2  // 8-pixel chunks per thread (1 = the round-1 mapping)
+#define DRTK_RENDER_BWD_CHUNKS 1  // 8-pixel chunks per thread; measured on B200: 1 -> 0.243 ms, 2 -> 0.271 ms, 4 -> 0.349 ms (config 4)
 #endif
 
 struct RunSetup {  // per-triangle constants of the backward (:186-219 of the reference)

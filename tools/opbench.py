@@ -23,7 +23,7 @@ v, vi, H, W = scenes.config_mesh(a.config, overdraw=a.overdraw, device=dev)
 N = v.shape[0]
 vi3 = vi[None].expand(N, -1, -1)
 attr = scenes.vertex_attributes(N, v.shape[1], a.C, seed=1, device=dev)
-w = th.rand((N, a.C, H, W), device=dev)
+w = th.rand((N, a.C, H, W), device=dev, generator=th.Generator(device=dev).manual_seed(2))  # seeded: --dump / --cmp runs see the same cotangent
 depth, index = _ops.rasterize(v, vi3, H, W)
 _, bary = _ops.render_forward(v, vi3, index)
 img = _ops.interpolate_forward(attr, vi3, index, bary)
