@@ -390,6 +390,9 @@ __device__ __forceinline__ void pair_contribute(const EdgeArgs& a, const FusedAr
 
 // Work item of a warp: a block of kStripRows consecutive centre rows x 256 columns.  The row below a centre row is the
 // next centre row, so it stays in registers (one index-row load per row instead of two).
+#ifndef DRTK_EDGE_PREFETCH
+#define DRTK_EDGE_PREFETCH 1
+#endif
 #ifndef DRTK_EDGE_STRIP_ROWS
 #define DRTK_EDGE_STRIP_ROWS 2  // measured on B200 (config 3 / 4 / 5 / 4-overdraw, ms): 2 -> .090 / .279 / 1.09 / 1.41, 4 -> .110 / .291 / 1.05 / 1.51, 8 -> .130 / .276 / 1.02 / -; round-1 kernel .087 / .283 / 1.14 / 1.67
 #endif
@@ -490,11 +493,27 @@ __global__ void __launch_bounds__(kStripWarps * 32, 4) edge_grad_strip_kernel(co
         jobs[off++] = (unsigned short)(((bit >> 3) << 8) | (lane * 8 + (bit & 7)));
       }
       __syncwarp();
+      // One job per lane and step.  The two table rows of the NEXT step's job are requested into L1 while this
+      // step's job is classified (the id -> table row -> inside test chain is what the kernel waits on).
+      int job = lane < total ? jobs[lane] : 0;
       for (int q = lane; q < total; q += 32) {
-        const int job = jobs[q];
         const int axis = job >> 8, lx = job & 0xff;
         const int ci = own[lx];
         const int ni = axis == 0 ? own[lx + 1] : below[lx];
+#if DRTK_EDGE_PREFETCH
+        int job_next = 0;
+        if (q + 32 < total) {
+          job_next = jobs[q + 32];
+          const int lxn = job_next & 0xff;
+          const int cn = own[lxn], nn = (job_next >> 8) == 0 ? own[lxn + 1] : below[lxn];
+          if (cn >= 0 && nn >= 0) {
+            prefetch_l1(fetch.tn + (int64_t)cn * 2);
+            prefetch_l1(fetch.tn + (int64_t)nn * 2);
+          }
+        }
+#else
+        const int job_next = q + 32 < total ? jobs[q + 32] : 0;
+#endif
         const int cx = sx * kStripPx + lx;
         bool c_in_n = false, n_in_c = false, keep = true;
         if (ci >= 0 && ni >= 0) {  // (:320-325) the bulk: two neighbouring triangles, neither covers the other's pixel
@@ -506,6 +525,7 @@ __global__ void __launch_bounds__(kStripWarps * 32, 4) edge_grad_strip_kernel(co
           keep = c_in_n || n_in_c;  // else adjacent (:338-341): no contribution
         }
         if (keep) keepq[atomicAdd(&n_keep[wid], 1)] = (unsigned short)(job | (c_in_n ? 0x4000 : 0) | (n_in_c ? 0x8000 : 0));
+        job = job_next;
       }
       __syncwarp();
       const int nk = n_keep[wid];
