@@ -305,6 +305,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the informational legs (cuda graph, with_loss, host paths)")
+    ap.add_argument("--dispatch", default="auto", choices=["auto", "torch", "ctypes"],
+                    help="host path of the public API: dispatcher ops (csrc/torch_shim.cpp) or ctypes; auto = the package default")
     args = ap.parse_args()
 
     # stdout carries exactly ONE line (the JSON): everything else that libraries print there (e.g. NCCL's
@@ -347,9 +349,12 @@ def main():
     th.cuda.set_device(local_rank)
     dev = th.device("cuda", local_rank)
     import drtk_b200
-    from drtk_b200 import _ops
+    from drtk_b200 import _ops, torch_ops
     from drtk_b200 import dist as ddist
     import torch.distributed as dist
+    if args.dispatch != "auto":
+        torch_ops.set_mode(args.dispatch)
+    host_path = "dispatcher ops (torch_shim, C++ autograd)" if torch_ops.enabled() else "ctypes (Python autograd)"
     numa_cpus = ddist.bind_to_gpu_numa_node(local_rank)  # before the pinned buffers are allocated
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -478,10 +483,18 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_device()
-    timing_on[0] = True
     dev_runs = [timed_region(step_device, args.steps) for _ in range(R)]
-    timing_on[0] = False
     ms_step = statistics.median(dev_runs)
+    # per-op CUDA events (roofline, per_op): one more region of the same K steps over the ctypes host path, whose Python
+    # launchers can be bracketed op by op (the dispatcher path runs its backward ops inside the C++ autograd engine);
+    # same kernels, same stream, same tensors
+    was_torch = torch_ops.enabled()
+    torch_ops.set_mode("ctypes")
+    step_device()
+    timing_on[0] = True
+    ms_step_per_op_region = timed_region(step_device, args.steps)
+    timing_on[0] = False
+    torch_ops.set_mode("torch" if was_torch else "ctypes")
 
     for _ in range(3):
         step_e2e()
@@ -550,6 +563,7 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "new",
         "ms_per_step_regions": [round(x, 4) for x in dev_runs], "ms_per_step_min": min(dev_runs),
+        "host_path": host_path, "per_op_region_ms_per_step": round(ms_step_per_op_region, 4),
         "config": {"workload": workload, "global_batch": N * world,
                    "parallelism": f"dp{world} (batch sharded; shared-parameter gradients batch-summed"
                                   + (f" and all-reduced, transport {reducer.transport})" if world > 1 else ")"),
@@ -688,7 +702,9 @@ def main():
                 th.cuda.synchronize()
                 return {"issue_us_per_step": round(t_issue / iters * 1e6, 1), "wall_us_per_step": round((time.perf_counter() - t0) / iters * 1e6, 1)}
             iters = 50 if cfg <= 3 else 10
+            torch_ops.set_mode("ctypes")
             hp = {"ctypes_python_autograd": wall(drtk_b200, iters)}
+            torch_ops.set_mode("torch" if was_torch else "ctypes")
             if torch_ops.available():
                 hp["dispatcher_ops_cpp_autograd"] = wall(_Shim, iters)
             if R_api is not None:

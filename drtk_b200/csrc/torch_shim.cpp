@@ -14,7 +14,8 @@
 // This file registers the SAME schemas under drtk_b200_<name>_ext (one process cannot hold two definitions of
 // rasterize_ext) with the same three dispatch keys; the CUDA implementations call the C ABI of
 // include/drtk_b200.h.  The reference's Python layer binds to it by changing one string per op.
-// There is deliberately no CPU key: a CPU tensor raises the dispatcher's "no kernel" error.
+// There is no CPU implementation: the CPU key maps to the same launchers, whose first TORCH_CHECK rejects a CPU tensor
+// with the reference's own wording ("...expected all inputs to be on same cuda device").
 //
 // Extra op (no counterpart in the reference): drtk_b200_edge_grad_ext::edge_grad_estimator_fused, the estimator
 // with its C = 3 conduit folded in (no [N,3,H,W] gradient image; used when no v_pix_img hook is registered).
@@ -464,11 +465,13 @@ TORCH_LIBRARY(drtk_b200_rasterize_ext, m) {
 TORCH_LIBRARY_IMPL(drtk_b200_rasterize_ext, Autograd, m) { m.impl("rasterize", &rasterize_autograd); }
 TORCH_LIBRARY_IMPL(drtk_b200_rasterize_ext, Autocast, m) { m.impl("rasterize", &rasterize_autocast); }
 TORCH_LIBRARY_IMPL(drtk_b200_rasterize_ext, CUDA, m) { m.impl("rasterize", &rasterize_cuda); }
+TORCH_LIBRARY_IMPL(drtk_b200_rasterize_ext, CPU, m) { m.impl("rasterize", &rasterize_cuda); }  // raises: no CPU path
 
 TORCH_LIBRARY(drtk_b200_render_ext, m) { m.def("render(Tensor v, Tensor vi, Tensor index_img) -> Tensor[]"); }
 TORCH_LIBRARY_IMPL(drtk_b200_render_ext, Autograd, m) { m.impl("render", &render_autograd); }
 TORCH_LIBRARY_IMPL(drtk_b200_render_ext, Autocast, m) { m.impl("render", &render_autocast); }
 TORCH_LIBRARY_IMPL(drtk_b200_render_ext, CUDA, m) { m.impl("render", &render_cuda); }
+TORCH_LIBRARY_IMPL(drtk_b200_render_ext, CPU, m) { m.impl("render", &render_cuda); }  // raises: no CPU path
 
 TORCH_LIBRARY(drtk_b200_interpolate_ext, m) {
   m.def("interpolate(Tensor vert_attributes, Tensor vi, Tensor index_img, Tensor bary_img) -> Tensor");
@@ -476,6 +479,7 @@ TORCH_LIBRARY(drtk_b200_interpolate_ext, m) {
 TORCH_LIBRARY_IMPL(drtk_b200_interpolate_ext, Autograd, m) { m.impl("interpolate", &interpolate_autograd); }
 TORCH_LIBRARY_IMPL(drtk_b200_interpolate_ext, Autocast, m) { m.impl("interpolate", &interpolate_autocast); }
 TORCH_LIBRARY_IMPL(drtk_b200_interpolate_ext, CUDA, m) { m.impl("interpolate", &interpolate_cuda); }
+TORCH_LIBRARY_IMPL(drtk_b200_interpolate_ext, CPU, m) { m.impl("interpolate", &interpolate_cuda); }  // raises: no CPU path
 
 TORCH_LIBRARY(drtk_b200_edge_grad_ext, m) {
   m.def("edge_grad_estimator(Tensor v_pix, Tensor v_pix_img, Tensor vi, Tensor img, Tensor index_img, float max_dp_dr=1e4) -> Tensor");
@@ -490,6 +494,10 @@ TORCH_LIBRARY_IMPL(drtk_b200_edge_grad_ext, Autocast, m) {
   m.impl("edge_grad_estimator_fused", &edge_grad_fused_autocast);
 }
 TORCH_LIBRARY_IMPL(drtk_b200_edge_grad_ext, CUDA, m) {
+  m.impl("edge_grad_estimator", &edge_grad_estimator_cuda_fwd);
+  m.impl("edge_grad_estimator_fused", &edge_grad_fused_cuda_fwd);
+}
+TORCH_LIBRARY_IMPL(drtk_b200_edge_grad_ext, CPU, m) {  // raise: no CPU path
   m.impl("edge_grad_estimator", &edge_grad_estimator_cuda_fwd);
   m.impl("edge_grad_estimator_fused", &edge_grad_fused_cuda_fwd);
 }

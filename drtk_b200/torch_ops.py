@@ -10,7 +10,9 @@ reference's `drtk/utils/load_torch_ops.py:14-28` loads its extensions.
 Which host path the public functions (`drtk_b200.rasterize`, ...) take is decided once per process:
   DRTK_B200_DISPATCH=torch   -> these dispatcher ops (C++ autograd functions, no ctypes marshalling)
   DRTK_B200_DISPATCH=ctypes  -> the Python autograd functions over ctypes (`_ops.py`)
-  unset                      -> ctypes
+  unset                      -> torch when `_torch_ops.so` is present (it is after `build()`), else ctypes
+`set_mode()` switches at run time (tools, tests).  Host cost of one forward + backward step on B200 (two-triangle 512^2
+scene, the size of the reference's tutorials): 473 us over ctypes, 166 us over the dispatcher ops, the kernels the same.
 Both end in the same C-ABI entry points and kernels.
 """
 import os
@@ -81,12 +83,22 @@ def enabled() -> bool:
         want = os.environ.get("DRTK_B200_DISPATCH", "").strip().lower()
         if want not in ("", "torch", "ctypes"):
             raise RuntimeError(f"DRTK_B200_DISPATCH={want!r}: expected 'torch' or 'ctypes'")
-        if want == "torch":
+        if want == "torch" or (want == "" and available()):
             load()
             _mode = "torch"
         else:
             _mode = "ctypes"
     return _mode == "torch"
+
+
+def set_mode(mode: str) -> None:
+    """Select the host path of the public functions for the rest of the process: "torch" or "ctypes"."""
+    global _mode
+    if mode not in ("torch", "ctypes"):
+        raise ValueError(mode)
+    if mode == "torch":
+        load()
+    _mode = mode
 
 
 def rasterize(v, vi, height, width, wireframe=False):
