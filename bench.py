@@ -483,6 +483,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_device()
+    timed_region(step_device, args.steps)  # one more untimed pass of K steps: allocator pools and clocks settle
     dev_runs = [timed_region(step_device, args.steps) for _ in range(R)]
     ms_step = statistics.median(dev_runs)
     # per-op CUDA events (roofline, per_op): one more region of the same K steps over the ctypes host path, whose Python
