@@ -286,6 +286,7 @@ struct __align__(16) TileSmem {
   int warp_tot[kRasterThreads / 32];
   uint32_t mlist[kPassRecs];               // large triangles that touch this tile (ids), current round
   int nmatch;
+  int collided;                            // some span took the collision path: zbuf holds keys to merge at the end
   unsigned long long bar;                  // mbarrier of the record copy
 };
 
@@ -367,6 +368,7 @@ __device__ __forceinline__ void tile_pass(TileSmem& S, int m, int x_lo, int y_lo
     const uint32_t mine = (uint32_t)slot | ((uint32_t)lxe << 8);
     while (lxs <= lxe && atomicCAS(&S.cell[cell_slot(ly, lxs)], kCellNone, mine) != kCellNone) {
       atomicMin(&S.zbuf[(ly << kTileLog) + lxs], shade_key(rec, x_lo_f + small_i2f(lxs), py));
+      S.collided = 1;
       ++lxs;
     }
   }
@@ -457,6 +459,7 @@ __global__ void __launch_bounds__(kRasterThreads, RV_MIN_CTAS) raster_tiles_kern
     mbar_init(bar, 1);
     mbar_fence_init();
     S.nmatch = 0;
+    S.collided = 0;
     if (cnt) {  // first pass in flight while the CTA initialises its pixel state
       const uint32_t bytes = min(cnt, (uint32_t)kPassRecs) * (uint32_t)(kRecF4 * 16);
       mbar_arrive_expect_tx(bar, bytes);
@@ -535,11 +538,15 @@ __global__ void __launch_bounds__(kRasterThreads, RV_MIN_CTAS) raster_tiles_kern
   int32_t* ip = index_img + o0;
   float* dp = depth_img + o0;
   const int nrows = min(kRowsPerWarp, y_hi - (y_lo + row0) + 1);
+  const bool merge = S.collided != 0;  // uniform over the CTA (every pass ends with a barrier)
 #pragma unroll
   for (int r = 0; r < kRowsPerWarp; ++r) {
     if (r >= nrows) break;
-    const unsigned long long zb = S.zbuf[((row0 + r) << kTileLog) + lane];
-    const unsigned long long k = zb < best[r] ? zb : best[r];
+    unsigned long long k = best[r];
+    if (merge) {
+      const unsigned long long zb = S.zbuf[((row0 + r) << kTileLog) + lane];
+      k = zb < k ? zb : k;
+    }
     const uint32_t d = (uint32_t)(k >> 32);
     *ip = (int)(uint32_t)k;
     *dp = d == 0xFFFFFFFFu ? 0.f : __uint_as_float(d);

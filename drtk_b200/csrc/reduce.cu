@@ -8,8 +8,8 @@
 //   drtk_b200_batch_sum           out[m] = sum_n x[n * batch_stride + m]                 (one launch, 128-bit accesses)
 //   drtk_b200_batch_sum_allreduce the same, then summed over all ranks IN THE SAME KERNEL through NVSwitch multicast
 //                                 memory: every rank adds its local sums into every rank's bucket with
-//                                 multimem.red.add.f32 (the switch fans the reduction out), bracketed by flag
-//                                 barriers over peer memory.  No NCCL call on this path.
+//                                 multimem.red.add.f32 (the switch fans the reduction out), followed by one flag
+//                                 barrier over peer memory (double-buffered bucket).  No NCCL call on this path.
 #include "common.cuh"
 
 namespace drtk {
@@ -82,22 +82,21 @@ __device__ __forceinline__ void rank_barrier(uint32_t* const* peer_flags, int ra
 
 struct PeerFlags { uint32_t* p[16]; };
 
-// Persistent one-wave grid.  bucket_mc: multicast address of the bucket (one physical copy per rank); bucket_local:
-// this rank's copy.  Protocol per call (epoch e = 3 * call_index):
-//   1. zero the local copy of the bucket;                barrier(e+1)   -- every rank's copy is zero
-//   2. local batch sum, multimem.red.add into ALL copies; barrier(e+2)   -- every copy holds the sum over ranks
-//   (the next call's step 1 must not start before every rank has READ its copy: the caller consumes the bucket on
-//    the same stream before the next call, and barrier(e'+1) of the next call orders the zeroing across ranks)
+// One co-resident wave.  The bucket has TWO halves used alternately (`half` = 0 / 1, flipped by the caller once per
+// backward pass): this call accumulates into half `half` and zero-fills this rank's copy of the OTHER half for the next
+// pass, so ONE barrier per call suffices:
+//   * every rank's copy of half `half` was zeroed by that rank's previous call, which ended with a barrier;
+//   * local batch sum, multimem.red.add into ALL copies of half `half`; zero the local copy of the other half;
+//   * barrier: every copy of half `half` now holds the sum over ranks, and nobody will add into the half just zeroed
+//     before the next call (whose reductions start after the peers passed this barrier).
+// The caller consumes half `half` (stream order) before its next call on the SAME half, i.e. two passes later.
 template <bool VEC>
 __global__ void __launch_bounds__(256) batch_sum_allreduce_kernel(const float* __restrict__ x, int N, int64_t M, int64_t stride,
-                                                                  float* __restrict__ bucket_local, float* bucket_mc,
+                                                                  float* __restrict__ zero_local, float* acc_mc,
                                                                   PeerFlags flags, int rank, int world, uint32_t epoch,
                                                                   int* timeout_flag) {
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
   const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (VEC) for (int64_t q = t0; q < M / 4; q += step) *reinterpret_cast<float4*>(bucket_local + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-  else for (int64_t m = t0; m < M; m += step) bucket_local[m] = 0.f;
-  rank_barrier(flags.p, rank, world, epoch + 1, timeout_flag);
   if (VEC) {
     for (int64_t q = t0; q < M / 4; q += step) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -106,16 +105,18 @@ __global__ void __launch_bounds__(256) batch_sum_allreduce_kernel(const float* _
         const float4 t = ldg_stream_f4(x + (int64_t)n * stride + q * 4);
         acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
       }
-      multimem_red_add_v4(bucket_mc + q * 4, acc.x, acc.y, acc.z, acc.w);
+      multimem_red_add_v4(acc_mc + q * 4, acc.x, acc.y, acc.z, acc.w);
+      *reinterpret_cast<float4*>(zero_local + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else {
     for (int64_t m = t0; m < M; m += step) {
       float acc = 0.f;
       for (int n = 0; n < N; ++n) acc += x[(int64_t)n * stride + m];
-      multimem_red_add(bucket_mc + m, acc);
+      multimem_red_add(acc_mc + m, acc);
+      zero_local[m] = 0.f;
     }
   }
-  rank_barrier(flags.p, rank, world, epoch + 2, timeout_flag);
+  rank_barrier(flags.p, rank, world, epoch + 1, timeout_flag);
 }
 
 inline bool vec_ok(const float* x, int64_t M, int64_t stride, const float* out) {
@@ -151,11 +152,13 @@ extern "C" int drtk_b200_batch_sum_allreduce_grid(void) {
 }
 
 extern "C" int drtk_b200_batch_sum_allreduce(const float* x, int64_t N, int64_t M, int64_t batch_stride,
-                                             float* bucket_local, float* bucket_multicast, void* const* peer_flags,
+                                             float* zero_local, float* acc_multicast, void* const* peer_flags,
                                              int rank, int world, uint32_t epoch, int* timeout_flag, void* stream_) {
   if (N < 0 || M < 0 || world < 1 || world > 16 || rank < 0 || rank >= world) return DRTK_B200_EINVAL;
   if (M == 0) return 0;
-  if (!bucket_local || !bucket_multicast || !peer_flags || (N > 0 && !x)) return DRTK_B200_EINVAL;
+  if (!zero_local || !acc_multicast || !peer_flags || (N > 0 && !x)) return DRTK_B200_EINVAL;
+  float* bucket_local = zero_local;
+  float* bucket_multicast = acc_multicast;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PeerFlags fl;
   for (int i = 0; i < 16; ++i) fl.p[i] = i < world ? static_cast<uint32_t*>(peer_flags[i]) : nullptr;

@@ -78,7 +78,8 @@ def allreduce_shared_grads(grads: Iterable[Optional[th.Tensor]], group=None, asy
 
 
 class _MultimemBucket:
-    """A symmetric-memory bucket of `numel` floats plus the flag array of the in-kernel rank barrier."""
+    """A symmetric-memory bucket of 2 x `numel` floats (two halves used by alternate backward passes) plus the flag
+    array of the in-kernel rank barrier."""
 
     def __init__(self, numel: int, device: th.device, group):
         import torch.distributed._symmetric_memory as symm_mem
@@ -87,29 +88,43 @@ class _MultimemBucket:
         self._lib = _lib
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.numel = numel
         grid = int(self.lib.drtk_b200_batch_sum_allreduce_grid())
-        self.bucket = symm_mem.empty(numel, dtype=th.float32, device=device)
+        self.bucket2 = symm_mem.empty(2 * numel, dtype=th.float32, device=device)
+        self.bucket2.zero_()
         self.flags = symm_mem.empty(self.world * grid, dtype=th.int32, device=device)
         self.flags.zero_()
-        self.h_bucket = symm_mem.rendezvous(self.bucket, self.group)
+        self.h_bucket = symm_mem.rendezvous(self.bucket2, self.group)
         self.h_flags = symm_mem.rendezvous(self.flags, self.group)
         if not getattr(self.h_bucket, "multicast_ptr", 0):
             raise RuntimeError("symmetric memory has no multicast address on this system (NVLS unavailable)")
         self.peer_flags = (ctypes.c_void_p * self.world)(*[int(p) for p in self.h_flags.buffer_ptrs])
         self.timeout = th.zeros((1,), dtype=th.int32, device=device)
         self.epoch = 0
+        self.half = 0
         th.cuda.synchronize(device)
-        dist.barrier(self.group)  # every rank's flags are zero before anybody raises one
+        dist.barrier(self.group)  # every rank's flags and buckets are zero before anybody touches a peer's
+
+    @property
+    def bucket(self) -> th.Tensor:
+        """The half that holds (or is receiving) the current pass's sums."""
+        return self.bucket2[self.half * self.numel:(self.half + 1) * self.numel]
 
     def reduce(self, x: th.Tensor, offset: int, numel: int, stream: th.cuda.Stream) -> None:
-        """bucket[offset : offset+numel] = sum over ranks of sum_n x[n] (one kernel)."""
+        """current half[offset : offset+numel] = sum over ranks of sum_n x[n]; the same range of the other half of
+        THIS rank is zero-filled for the next pass (one kernel, one cross-rank barrier)."""
         N = x.shape[0]
+        acc = self.half * self.numel + offset
+        zero = (1 - self.half) * self.numel + offset
         rc = self.lib.drtk_b200_batch_sum_allreduce(
-            self._lib.ptr(x), N, numel, x.stride(0) if N > 1 else numel, self.bucket.data_ptr() + 4 * offset,
-            int(self.h_bucket.multicast_ptr) + 4 * offset, self.peer_flags, self.rank, self.world, self.epoch,
+            self._lib.ptr(x), N, numel, x.stride(0) if N > 1 else numel, self.bucket2.data_ptr() + 4 * zero,
+            int(self.h_bucket.multicast_ptr) + 4 * acc, self.peer_flags, self.rank, self.world, self.epoch,
             self.timeout.data_ptr(), stream.cuda_stream)
         self._lib.check(rc, "batch_sum_allreduce()")
-        self.epoch = (self.epoch + 3) & 0xFFFFFFFF
+        self.epoch = (self.epoch + 1) & 0xFFFFFFFF
+
+    def next_pass(self) -> None:
+        self.half ^= 1
 
     def check(self) -> None:
         if int(self.timeout.item()) != 0:
@@ -129,7 +144,8 @@ class SharedGradReducer:
     a multicast address, else nccl; "auto" never raises).  On CUDA the work is issued on a side stream (ordered after
     the gradient's producer through an event; the caller's stream only waits in `finish()`).  Without an initialised
     process group it degenerates to the local batch sums.  The returned tensors are views into the reducer's bucket:
-    consume (or copy) them before the next backward pass."""
+    consume (or copy) them before the next backward pass, and call `finish()` once per backward pass (the multimem
+    transport alternates between two bucket halves per pass)."""
 
     def __init__(self, params: Sequence[th.Tensor], group=None, transport: str = "auto"):
         self.params = list(params)
@@ -159,7 +175,8 @@ class SharedGradReducer:
                     if transport == "multimem":
                         raise
                     self.fallback_reason = repr(ex)[:200]
-        self.bucket = self.mm.bucket if self.mm is not None else th.zeros((self.total,), dtype=self.params[0].dtype, device=dev)
+        self._bucket = None if self.mm is not None else th.zeros((self.total,), dtype=self.params[0].dtype, device=dev)
+        self._last = None  # the bucket (half) that holds the results of the last finished pass
         self._pending = {}
         self._side = th.cuda.Stream(dev) if self.cuda else None
         self._handles = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
@@ -167,8 +184,19 @@ class SharedGradReducer:
     def _distributed(self) -> bool:
         return _world(self.group) > 1
 
-    def _segment(self, i: int) -> th.Tensor:
-        return self.bucket[self.offsets[i]:self.offsets[i] + self.sizes[i]].view(self.params[i].shape[1:])
+    @property
+    def bucket(self) -> th.Tensor:
+        """Flat bucket holding the results of the last finished pass (before the first `finish()`: the current one)."""
+        if self._last is not None:
+            return self._last
+        return self.mm.bucket if self.mm is not None else self._bucket
+
+    def _current(self) -> th.Tensor:
+        return self.mm.bucket if self.mm is not None else self._bucket
+
+    def _segment(self, i: int, flat: Optional[th.Tensor] = None) -> th.Tensor:
+        flat = self._current() if flat is None else flat
+        return flat[self.offsets[i]:self.offsets[i] + self.sizes[i]].view(self.params[i].shape[1:])
 
     def _make_hook(self, i):
         def hook(p):
@@ -197,6 +225,7 @@ class SharedGradReducer:
         """Wait for the exchanges of this backward pass; returns the reduced gradients in parameter order (None for a
         parameter that received no gradient)."""
         out: List[Optional[th.Tensor]] = []
+        flat = self._current()
         for i in range(len(self.params)):
             if i not in self._pending:
                 out.append(None)
@@ -204,9 +233,12 @@ class SharedGradReducer:
             work = self._pending.pop(i)
             if work is not None:
                 work.wait()  # on CUDA: the current stream waits for the collective, the host does not block
-            out.append(self._segment(i))
+            out.append(self._segment(i, flat))
         if self.cuda:
             th.cuda.current_stream(self.params[0].device).wait_stream(self._side)
+        self._last = flat
+        if self.mm is not None:
+            self.mm.next_pass()
         return out
 
     def close(self) -> None:

@@ -293,20 +293,22 @@ int drtk_b200_grid_scatter_backward(const float* grad_out, const int64_t* grad_o
  * batch_sum: out[m] = sum_n x[n * batch_stride + m], m < M  -- the local batch reduction, written straight into the
  *   communication bucket.
  * batch_sum_allreduce: the same followed, IN THE SAME KERNEL, by the sum over all ranks through NVSwitch multicast
- *   memory (multimem.red.add.f32 into every rank's copy of the bucket, flag barriers over peer memory); no NCCL
- *   call.  bucket_local / bucket_multicast: this rank's copy and the multicast address of a symmetric buffer of M
- *   floats; peer_flags[r]: rank r's flag array (world * drtk_b200_batch_sum_allreduce_grid() zero-initialised
- *   uint32) as mapped into this process; epoch: 3 * (number of earlier calls on these flags).  Every rank must
- *   make the same sequence of calls.  On return (stream order) bucket_local holds the sum over ranks.
- *   timeout_flag (device int, may be NULL) is set to 1 when a peer did not arrive within ~2 s (the wait then gives
- *   up instead of hanging the GPU; the bucket is invalid).
+ *   memory (multimem.red.add.f32 into every rank's copy of the bucket, one flag barrier over peer memory); no NCCL
+ *   call.  The bucket is double buffered: acc_multicast = multicast address of the half that receives this call's sums
+ *   (every rank's copy of it must be zero: it was zero_local of that rank's previous call, or freshly zeroed memory),
+ *   zero_local = THIS rank's copy of the other half, zero-filled by this call for the next one (M floats each).
+ *   peer_flags[r]: rank r's flag array (world * drtk_b200_batch_sum_allreduce_grid() zero-initialised uint32) as mapped
+ *   into this process; epoch: number of earlier calls on these flags.  Every rank must make the same sequence of
+ *   calls.  On return (stream order) this rank's copy of the accumulated half holds the sum over ranks; consume it
+ *   before the call after next (which zero-fills it).  timeout_flag (device int, may be NULL) is set to 1 when a peer
+ *   did not arrive within ~2 s (the wait then gives up instead of hanging the GPU; the bucket is invalid).
  * ------------------------------------------------------------------------------------- */
 int drtk_b200_batch_sum(const float* x, int64_t N, int64_t M, int64_t batch_stride, float* out, void* stream);
 
 int drtk_b200_batch_sum_allreduce_grid(void);
 
-int drtk_b200_batch_sum_allreduce(const float* x, int64_t N, int64_t M, int64_t batch_stride, float* bucket_local,
-                                  float* bucket_multicast, void* const* peer_flags, int rank, int world,
+int drtk_b200_batch_sum_allreduce(const float* x, int64_t N, int64_t M, int64_t batch_stride, float* zero_local,
+                                  float* acc_multicast, void* const* peer_flags, int rank, int world,
                                   uint32_t epoch, int* timeout_flag, void* stream);
 
 /* ---------------------------------------------------------------------------------------
