@@ -183,28 +183,45 @@ __global__ void __launch_bounds__(256) bin_kernel(RasterArgs a, int64_t total, u
                                                   uint32_t* large_count, uint32_t* __restrict__ large_id,
                                                   int4* __restrict__ large_bbox) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int n = (int)(idx / a.F);
-  const int f = (int)(idx - (int64_t)n * a.F);
+  const int lane = threadIdx.x & 31;
+  // every lane of the warp stays in the kernel (the fill pass uses warp-wide MATCH / SHFL); `valid` carries the culling
+  const bool in_range = idx < total;
+  const int n = in_range ? (int)(idx / a.F) : 0;
+  const int f = in_range ? (int)(idx - (int64_t)n * a.F) : 0;
   TriFull s;
-  if (!tri_full(a, n, f, s)) return;
-  if (s.bx0 > s.bx1 || s.by0 > s.by1) return;
-  const int tx0 = s.bx0 >> kTileLog, tx1 = s.bx1 >> kTileLog;
-  const int ty0 = s.by0 >> kTileLog, ty1 = s.by1 >> kTileLog;
+  bool valid = in_range && tri_full(a, n, f, s);
+  valid = valid && s.bx0 <= s.bx1 && s.by0 <= s.by1;
+  const int tx0 = valid ? s.bx0 >> kTileLog : 0, tx1 = valid ? s.bx1 >> kTileLog : 0;
+  const int ty0 = valid ? s.by0 >> kTileLog : 0, ty1 = valid ? s.by1 >> kTileLog : 0;
   const int64_t tbase = (int64_t)n * a.tilesX * a.tilesY;
-  if (tx1 - tx0 <= 1 && ty1 - ty0 <= 1) {
-    for (int ty = ty0; ty <= ty1; ++ty)
-      for (int tx = tx0; tx <= tx1; ++tx) {
-        const int64_t t = tbase + (int64_t)ty * a.tilesX + tx;
-        const uint32_t k = atomicAdd(&tile_count[t], 1u);
-        if (FILL) {
-          const int x_lo = tx << kTileLog, y_lo = ty << kTileLog;
-          const int meta = record_meta(s, x_lo, y_lo, min(x_lo + kTile - 1, a.W - 1), min(y_lo + kTile - 1, a.H - 1), a.W);
-          float4* dst = recs + (size_t)(tile_offset[t] + k) * kRecF4;
-          write_record(s, f, meta, [&](int q, float4 val) { dst[q] = val; });
-        }
-      }
-  } else if (FILL) {
+  const bool small = valid && tx1 - tx0 <= 1 && ty1 - ty0 <= 1;
+  // Neighbouring triangles of a mesh are neighbouring threads and fall into the same few tiles: in the fill pass the
+  // lanes that append to the same tile are grouped (MATCH.ANY) and ONE of them takes a range of slots for all of them
+  // -- a returning atomic per lane on the same counter serialises in L2 (the fill kernel ran at 27 % issue).
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int tx = tx0 + (q & 1), ty = ty0 + (q >> 1);
+    const bool mine = small && tx <= tx1 && ty <= ty1;
+    const int64_t t = tbase + (int64_t)ty * a.tilesX + tx;
+    if (!FILL) {
+      if (mine) atomicAdd(&tile_count[t], 1u);  // no return value: a fire-and-forget reduction
+      continue;
+    }
+    // key: the tile for participating lanes (t < 2^31, host check), a private value for the others
+    const unsigned peers = __match_any_sync(0xffffffffu, mine ? (unsigned)t : (0x80000000u | (unsigned)lane));
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (mine && lane == leader) base = atomicAdd(&tile_count[t], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (mine) {
+      const uint32_t k = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+      const int x_lo = tx << kTileLog, y_lo = ty << kTileLog;
+      const int meta = record_meta(s, x_lo, y_lo, min(x_lo + kTile - 1, a.W - 1), min(y_lo + kTile - 1, a.H - 1), a.W);
+      float4* dst = recs + (size_t)(tile_offset[t] + k) * kRecF4;
+      write_record(s, f, meta, [&](int q2, float4 val) { dst[q2] = val; });
+    }
+  }
+  if (FILL && valid && !small) {
     const uint32_t k = atomicAdd(&large_count[n], 1u);
     large_id[(int64_t)n * a.F + k] = (uint32_t)f;
     large_bbox[(int64_t)n * a.F + k] = make_int4(s.bx0, s.by0, s.bx1, s.by1);

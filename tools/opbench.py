@@ -39,8 +39,21 @@ def timeit(fn):
     ts = sorted(x.elapsed_time(y) for x, y in evs)
     return ts[len(ts) // 2], ts[0], out
 
+vi_wire = vi3.clone()
+vi_wire[..., 0] |= (7 << 28)  # all edges visible (wireframe mode, src/rasterize/rasterize_kernel.cu:293-303)
+
+
+def _ref_op(name, *args):
+    from oracle import ref as R
+    R.load()
+    return getattr(getattr(th.ops, name + "_ext"), {"rasterize": "rasterize", "render": "render", "interpolate": "interpolate"}[name])(*args)
+
+
 OPS = {
     "rasterize": lambda: _ops.rasterize(v, vi3, H, W),
+    "wireframe": lambda: _ops.rasterize(v, vi_wire, H, W, wireframe=True),
+    "wireframe_ref": lambda: tuple(_ref_op("rasterize", v, vi_wire, H, W, True)),
+    "rasterize_ref": lambda: tuple(_ref_op("rasterize", v, vi3, H, W, False)),
     "render_fwd": lambda: _ops.render_forward(v, vi3, index),
     "interp_fwd": lambda: _ops.interpolate_forward(attr, vi3, index, bary),
     "interp_bwd": lambda: _ops.interpolate_backward(w, attr, vi3, index, bary, True, True),

@@ -52,6 +52,9 @@ vv[..., :2] = vv[..., :2].round()
 check("integer coordinates 128", vv, vii, 128, 128)
 v2, vi2, H2, W2 = scenes.two_triangles()
 check("two triangles 512 (config 2)", v2, vi2, H2, W2)
+if "--small" in sys.argv:  # under compute-sanitizer: the small scenes only
+    print("elapsed", round(time.time() - t0, 1), "s;", "ALL OK" if ok else "FAILED")
+    sys.exit(0 if ok else 1)
 for cfg, N, od in ((3, 8, False), (3, 2, True), (4, 8, False), (4, 2, True), (5, 1, False)):
     v, vi, H, W = scenes.config_mesh(cfg, N=N, overdraw=od)
     check(f"config {cfg} N={N} overdraw={od}", v, vi, H, W)
