@@ -237,7 +237,9 @@ def _f32(t, name):
 def project_points(v, campos, camrot, focal, princpt, distortion_mode=None, distortion_coeff=None, fov=None,
                    lut_vector_field=None, lut_spacing=None) -> Tuple[th.Tensor, th.Tensor]:
     """-> (v_pix, v_cam), both [N,V,3]; v_pix = (x_pixels, y_pixels, z_camera).  `drtk/utils/projection.py:486-646`."""
-    if not v.is_cuda:
+    if not v.is_cuda or v.dtype == th.float64:
+        # CPU tensors (no kernel in the reference either) and float64 (the reference's torch-op chain works in any dtype;
+        # the fused kernel is float32): stock torch ops
         return project_points_ref(v, campos, camrot, focal, princpt, distortion_mode, distortion_coeff, fov,
                                   lut_vector_field, lut_spacing)
     mode, modes = _resolve_modes(distortion_mode, distortion_coeff)
