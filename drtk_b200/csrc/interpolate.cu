@@ -567,6 +567,18 @@ constexpr int kQCh = 16;        // channels per pass over a tile
 constexpr int kQUnit = 128;     // pixels per warp: 8 walkers x kQSeg (phase A) = 2 x 32 lanes x 2 px (phase B)
 constexpr int kQProducers = 2;  // 20 bulk copies per tile at ~0.145 us each per issuing thread
 constexpr int kQChunk = 8;      // tiles per scheduling chunk (see the tile order comment in the kernel)
+// tile pixels / pipeline stages per CTA / co-resident CTAs per SM of the quad kernel (A/B knobs, tools/build_variants.sh)
+#ifndef DRTK_INTERP_BWD_TP
+#define DRTK_INTERP_BWD_TP 512
+#endif
+#ifndef DRTK_INTERP_BWD_STAGES
+#define DRTK_INTERP_BWD_STAGES 2
+#endif
+#ifndef DRTK_INTERP_BWD_CTAS
+#define DRTK_INTERP_BWD_CTAS 2
+#endif
+constexpr int kQStages = DRTK_INTERP_BWD_STAGES;
+constexpr int kQCtas = DRTK_INTERP_BWD_CTAS;
 
 template <int TP>
 struct QStage {
@@ -576,9 +588,9 @@ struct QStage {
 };
 template <int TP>
 struct QSmem {
-  QStage<TP> st[kBwdStages];
-  unsigned long long full[kBwdStages];
-  unsigned long long empty[kBwdStages];
+  QStage<TP> st[kQStages];
+  unsigned long long full[kQStages];
+  unsigned long long empty[kQStages];
 };
 
 // Also zero-fills the vertex-gradient table the walkers reduce into (saves a memset launch per step).
@@ -714,7 +726,7 @@ __device__ __forceinline__ void bary_grad_pair(const float* __restrict__ gq_base
 
 // MULTI: C > 16, i.e. several channel passes per tile (phase-B sums are then carried between passes)
 template <int TP, bool NEED_VERT, bool NEED_BARY, bool AVEC, bool MULTI>
-__global__ void __launch_bounds__(32 * (TP / kQUnit * 2 + kQProducers), (TP <= 512) ? 2 : 1)
+__global__ void __launch_bounds__(32 * (TP / kQUnit * 2 + kQProducers), kQCtas)
 interp_bwd_quad_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __restrict__ bary_grad,
                        const int4* __restrict__ tab, int tab_img_stride, int tiles_per_img, int num_tiles, bool v8) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -725,7 +737,7 @@ interp_bwd_quad_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
   const int tid = threadIdx.x, lane = tid & 31;
   const int HW = a.H * a.W;
   if (tid == 0) {
-    for (int s = 0; s < kBwdStages; ++s) {
+    for (int s = 0; s < kQStages; ++s) {
       mbar_init(reinterpret_cast<uint64_t*>(&S.full[s]), kQProducers);
       mbar_init(reinterpret_cast<uint64_t*>(&S.empty[s]), CONSUMERS);
     }
@@ -753,9 +765,9 @@ interp_bwd_quad_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
         const int p0 = tl * TP;
         const uint32_t bytes = (uint32_t)min(TP, HW - p0) * 4u;
         for (int chunk = 0; chunk < nchunks; ++chunk, ++item) {
-          const int s = item & 1;
-          if (item >= kBwdStages)
-            mbar_wait_backoff(reinterpret_cast<uint64_t*>(&S.empty[s]), (uint32_t)((item / kBwdStages - 1) & 1), 100);
+          const int s = item % kQStages;
+          if (item >= kQStages)
+            mbar_wait_backoff(reinterpret_cast<uint64_t*>(&S.empty[s]), (uint32_t)((item / kQStages - 1) & 1), 100);
           const int c0 = chunk * kQCh, nc = min(kQCh, a.C - c0);
           const int ncopies = nc + (NEED_VERT ? 3 : 0) + 1;
           uint64_t* bar = reinterpret_cast<uint64_t*>(&S.full[s]);
@@ -798,7 +810,7 @@ interp_bwd_quad_kernel(InterpBwdArgs b, float* __restrict__ vert_grad, float* __
     const bool a_team = ((team ^ seq) & 1) == 0;  // the teams swap roles every tile
     const int4* tabn = tab + (size_t)((unsigned)n * (unsigned)tab_img_stride);
     for (int chunk = 0; chunk < nchunks; ++chunk, ++item) {
-      const int s = item & 1;
+      const int s = item % kQStages;
       const int c0 = chunk * kQCh, nc = min(kQCh, a.C - c0);
       QStage<TP>& st = S.st[s];
       mbar_wait_backoff(reinterpret_cast<uint64_t*>(&S.full[s]), (phase_bits >> s) & 1u, 32);
@@ -1032,7 +1044,7 @@ extern "C" int drtk_b200_interpolate_backward(
                       (V * (b.f.as.s1 > 0 ? b.f.as.s1 : 1) + C < (int64_t)0x7FFFFFF0) && b.f.as.s1 >= 0;
     int rc2 = 0;
     // v5: quad-lane walkers + packed triangle table (needs whole groups of four channels)
-    constexpr int QTP = 512;
+    constexpr int QTP = DRTK_INTERP_BWD_TP;
     const int64_t tiles_q = N * ((H * W + QTP - 1) / QTP);
     const int64_t tab_imgs = (b.f.vis.s0 == 0) ? 1 : N;
     if ((C % 4 == 0) && tiles_q < (int64_t)0x7FFFFFF0 && tab_imgs * F < (int64_t)0x0FFFFFFF &&
@@ -1051,7 +1063,7 @@ extern "C" int drtk_b200_interpolate_backward(
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { rc2 = (int)e; return; }
         const int tiles_per_img = (int)((H * W + QTP - 1) / QTP);
-        const int64_t ctas = 2 * num_sms();  // two co-resident CTAs per SM
+        const int64_t ctas = (int64_t)kQCtas * num_sms();  // co-resident CTAs per SM
         const int64_t chunks = (tiles_q + kQChunk - 1) / kQChunk;
         const unsigned grid = (unsigned)(chunks < ctas ? chunks : ctas);
         kern<<<grid, 32 * (QTP / kQUnit * 2 + kQProducers), smem, stream>>>(
