@@ -302,6 +302,9 @@ def main():
     ap.add_argument("--overdraw", action="store_true", help="two sheets, the second rotated 7 degrees (occlusion + intersections)")
     ap.add_argument("--regions", type=int, default=3, help="how many times the K-step region is timed (median reported)")
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "multimem"])
+    ap.add_argument("--bg-ctas", type=int, default=None,
+                    help="multimem transport: CTAs of the exchanges that overlap the backward (default: a quarter of the SMs; "
+                         "0 = full wave for every exchange)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the informational legs (cuda graph, with_loss, host paths)")
@@ -394,7 +397,7 @@ def main():
         wrap(name, key)
 
     # shared-parameter gradients: batch-summed (and all-reduced over ranks) per parameter, from post-accumulate-grad hooks
-    reducer = ddist.SharedGradReducer([v_d, attr_d], transport=args.transport)
+    reducer = ddist.SharedGradReducer([v_d, attr_d], transport=args.transport, background_ctas=args.bg_ctas)
     exchange = {"on": True}
 
     def step_device():
@@ -419,7 +422,7 @@ def main():
         bv = th.empty_like(v_h, device=dev).requires_grad_(True)
         ba = th.empty_like(attr_h, device=dev).requires_grad_(True)
         ebuf.append(dict(v=bv, a=ba, ready=th.cuda.Event(), free=th.cuda.Event(), out_done=th.cuda.Event(),
-                         red=ddist.SharedGradReducer([bv, ba], transport=args.transport)))
+                         red=ddist.SharedGradReducer([bv, ba], transport=args.transport, background_ctas=args.bg_ctas)))
     estate = {"k": 0, "primed": False}
 
     def e2e_prefetch(k):
@@ -578,7 +581,7 @@ def main():
                         "region; copies double-buffered on side streams; topology (vi) stays resident; median of the regions"},
         "gpu_launches": (sum(KERNELS.values()) + REDUCE_KERNELS) * args.steps,
         "clocks": clocks, "roofline": roofline, "per_op": breakdown, "pcie": pcie,
-        "shared_grad_exchange": {"transport": reducer.transport, "ms_isolated": round(ms_exchange, 4),
+        "shared_grad_exchange": {"transport": reducer.transport, "background_ctas": args.bg_ctas, "ms_isolated": round(ms_exchange, 4),
                                  "bytes": reducer.total * 4, "fallback_reason": getattr(reducer, "fallback_reason", None)},
         "numa_cpus": (f"{numa_cpus[0]}-{numa_cpus[-1]} ({len(numa_cpus)})" if numa_cpus else None),
         "pipeline_algorithmic_GB_per_step": round(sum(ALGO_BYTES_PER_PX[k](C) for k in KERNELS) * npx_rank / 1e9, 3),

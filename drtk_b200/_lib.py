@@ -89,7 +89,7 @@ PROTOTYPES = {
         _INT, [_P, _P, _P, _P, _INT, _INT, _P, _P, _P, _P, _I64, _I64, _P, _P, _P]),
     "drtk_b200_batch_sum": (_INT, [_P, _I64, _I64, _I64, _P, _P]),
     "drtk_b200_batch_sum_allreduce_grid": (_INT, []),
-    "drtk_b200_batch_sum_allreduce": (_INT, [_P, _I64, _I64, _I64, _P, _P, _P, _INT, _INT, ctypes.c_uint32, _P, _P]),
+    "drtk_b200_batch_sum_allreduce": (_INT, [_P, _I64, _I64, _I64, _P, _P, _P, _INT, _INT, ctypes.c_uint32, _P, _INT, _P]),
     "drtk_b200_edge_grad_backward_fused": (
         _INT,
         [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _F32, _P, _P, _SZ, _P],

@@ -131,7 +131,7 @@ __device__ __forceinline__ float2 dp_dr(float nvx, float nvy, float nfx, float n
 }
 
 #ifndef DRTK_EDGE_DOT_BATCH
-#define DRTK_EDGE_DOT_BATCH 4
+#define DRTK_EDGE_DOT_BATCH 8  // measured (config 3 / 4 / 5 / 4-overdraw, ms): 1 -> .0886 / .2771 / 1.082 / 1.422, 4 -> same, 8 -> .0825 / .2628 / 1.065 / 1.381, 16 -> .0874 / .2695 / 1.071 / 1.424
 #endif
 // sum_c (img[nb] - img[c]) * 0.5 * (g[nb] + g[c])   (:351-380)
 __device__ __forceinline__ float grad_dot(const EdgeArgs& a, int n, int xc, int yc, int xn, int yn) {

@@ -629,6 +629,9 @@ __global__ void __launch_bounds__(256) unpack_kernel(const unsigned long long* _
 //   d  = fma(a1, b2, -rn(b1 * a2));  r = MUFU.RCP(d)
 //   cx = rn(fma(b1, c2, -rn(c1 * b2)) * r);  cy = rn(fma(c1, a2, -rn(a1 * c2)) * r)       (:193-203)
 //   d == 0  ->  (FLT_MAX, 0)
+#ifndef DRTK_LINES_MINCTAS
+#define DRTK_LINES_MINCTAS 3
+#endif
 struct Line { float a, b, c; };
 __device__ __forceinline__ Line line_through(float p1x, float p1y, float p2x, float p2y) {
   Line l;
@@ -699,7 +702,7 @@ __device__ __forceinline__ float canon_edge_fn(int ia, int ib, float pax, float 
   return -edge_fn(pbx, pby, pax, pay, px, py);
 }
 
-__global__ void __launch_bounds__(256) raster_lines_kernel(RasterArgs a, int64_t total,
+__global__ void __launch_bounds__(256, DRTK_LINES_MINCTAS) raster_lines_kernel(RasterArgs a, int64_t total,
                                                            unsigned long long* __restrict__ packed_img) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -746,20 +749,35 @@ __global__ void __launch_bounds__(256) raster_lines_kernel(RasterArgs a, int64_t
     const Line l01 = line_through(p0x, p0y, p1x, p1y), l12 = line_through(p1x, p1y, p2x, p2y),
                l02 = line_through(p0x, p0y, p2x, p2y);
     unsigned long long* img = packed_img + (int64_t)n * a.H * a.W;
-    // Work split: lane = (row within a block of 16 rows, left / right half of the row).
-    const int bw = bx1 - bx0 + 1, rows = by1 - by0 + 1, half = (bw + 1) >> 1;
-    const int xa = bx0 + (lane & 1) * half, xb = min(bx1, xa + half - 1);
-    for (int ry = lane >> 1; ry < rows; ry += 16) {
-      const int y = by0 + ry;
+    // Work split: the padded bounding box is walked in row-major order, 32 consecutive samples per step (a 9 x 9 box
+    // of a 4-px triangle keeps 27 of 32 lanes busy; the previous (row, half-row) split kept 18).
+    const int bw = bx1 - bx0 + 1, rows = by1 - by0 + 1;
+    const uint64_t area = (uint64_t)bw * (uint64_t)rows;
+    for (uint64_t s0 = 0; s0 < area; s0 += 0x40000000ull) {  // one pass unless the box holds > 2^30 samples: 32-bit index math inside
+      const uint32_t cnt = (uint32_t)min((unsigned long long)(area - s0), 0x40000000ull);
+      const uint32_t row0 = s0 ? (uint32_t)(s0 / (uint32_t)bw) : 0u;
+      const uint32_t rem0 = s0 ? (uint32_t)(s0 - (uint64_t)row0 * (uint32_t)bw) : 0u;
+      for (uint32_t s = (uint32_t)lane; s < cnt; s += 32u) {
+      const uint32_t t = s + rem0;
+      const uint32_t ry = t / (uint32_t)bw;
+      const int y = by0 + (int)(row0 + ry), x = bx0 + (int)(t - ry * (uint32_t)bw);
       const float py = (float)y;
-      for (int x = xa; x <= xb; ++x) {
+      {
       const float px = (float)x;
       DiamondSides ds;
       diamond_sides(px, py, ds);
+      // An edge can only be hit through an intersection point c that lies `within` a diamond side AND `within` the
+      // edge: c.x in [xl, xh] and in [min, max] of the edge's x (same for y).  When those closed ranges are disjoint
+      // no value of c passes both tests, whatever the rounding of c -- the edge is skipped for this sample (exact,
+      // not a tolerance).  xl / xh / yl / yh are the very values the sides are built from.
+      const float xl = ds.s0x[3], xh = ds.s0x[1], yl = ds.s0y[0], yh = ds.s0y[2];
+      auto reach = [&](float ax, float ay, float bx, float by) {
+        return !(xh < fminf(ax, bx) || xl > fmaxf(ax, bx) || yh < fminf(ay, by) || yl > fmaxf(ay, by));
+      };
       bool hit = false;  // (:343-346)
-      hit |= crosses_diamond(l01, p0x, p0y, p1x, p1y, ds) && vis0;
-      hit |= crosses_diamond(l12, p1x, p1y, p2x, p2y, ds) && vis1;
-      hit |= crosses_diamond(l02, p0x, p0y, p2x, p2y, ds) && vis2;
+      if (vis0 && reach(p0x, p0y, p1x, p1y)) hit |= crosses_diamond(l01, p0x, p0y, p1x, p1y, ds);
+      if (vis1 && reach(p1x, p1y, p2x, p2y)) hit |= crosses_diamond(l12, p1x, p1y, p2x, p2y, ds);
+      if (vis2 && reach(p0x, p0y, p2x, p2y)) hit |= crosses_diamond(l02, p0x, p0y, p2x, p2y, ds);
       float b0 = canon_edge_fn<true>(i1, i2, p1x, p1y, p2x, p2y, px, py);  // (:348-353)
       float b1 = canon_edge_fn<false>(i2, i0, p2x, p2y, p0x, p0y, px, py);
       float b2 = canon_edge_fn<false>(i0, i1, p0x, p0y, p1x, p1y, px, py);
@@ -778,6 +796,7 @@ __global__ void __launch_bounds__(256) raster_lines_kernel(RasterArgs a, int64_t
         const unsigned long long val = ((unsigned long long)__float_as_uint(depth) << 32) |
                                        (hit ? (unsigned long long)(uint32_t)f : 0xFFFFFFFFull);
         atomicMin(img + (int64_t)y * a.W + x, val);
+      }
       }
       }
     }

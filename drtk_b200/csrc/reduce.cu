@@ -58,16 +58,17 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 // Barrier over all ranks, entered by every CTA of the (co-resident) grid: CTA b of rank r raises flag
 // [r][b] on every peer (peer_flags[p] = base of rank p's flag array, world * gridDim.x words) to the epoch value and
 // waits until its own array shows the epoch for (every rank, b).  Epochs grow monotonically (one per call and
-// barrier), so flags are never reset.
+// barrier), so flags are never reset.  flag_stride = words per rank in a flag array (the full-wave grid): a call may
+// run on fewer CTAs than that (every rank the same number) and then simply leaves the upper slots of a row alone.
 // A rank that never arrives (crashed peer) must not hang the GPU: after ~4e9 SM cycles (about two seconds) the
 // wait gives up and raises *timeout_flag; the caller treats the bucket as invalid.
-__device__ __forceinline__ void rank_barrier(uint32_t* const* peer_flags, int rank, int world, uint32_t epoch,
+__device__ __forceinline__ void rank_barrier(uint32_t* const* peer_flags, int flag_stride, int rank, int world, uint32_t epoch,
                                              int* timeout_flag) {
   __syncthreads();
   if (threadIdx.x < world) {
     __threadfence_system();
-    st_release_sys(peer_flags[threadIdx.x] + (size_t)rank * gridDim.x + blockIdx.x, epoch);
-    const uint32_t* mine = peer_flags[rank] + (size_t)threadIdx.x * gridDim.x + blockIdx.x;
+    st_release_sys(peer_flags[threadIdx.x] + (size_t)rank * flag_stride + blockIdx.x, epoch);
+    const uint32_t* mine = peer_flags[rank] + (size_t)threadIdx.x * flag_stride + blockIdx.x;
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
       __nanosleep(40);
@@ -93,8 +94,8 @@ struct PeerFlags { uint32_t* p[16]; };
 template <bool VEC>
 __global__ void __launch_bounds__(256) batch_sum_allreduce_kernel(const float* __restrict__ x, int N, int64_t M, int64_t stride,
                                                                   float* __restrict__ zero_local, float* acc_mc,
-                                                                  PeerFlags flags, int rank, int world, uint32_t epoch,
-                                                                  int* timeout_flag) {
+                                                                  PeerFlags flags, int flag_stride, int rank, int world,
+                                                                  uint32_t epoch, int* timeout_flag) {
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
   const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (VEC) {
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(256) batch_sum_allreduce_kernel(const float* _
       zero_local[m] = 0.f;
     }
   }
-  rank_barrier(flags.p, rank, world, epoch + 1, timeout_flag);
+  rank_barrier(flags.p, flag_stride, rank, world, epoch + 1, timeout_flag);
 }
 
 inline bool vec_ok(const float* x, int64_t M, int64_t stride, const float* out) {
@@ -153,8 +154,9 @@ extern "C" int drtk_b200_batch_sum_allreduce_grid(void) {
 
 extern "C" int drtk_b200_batch_sum_allreduce(const float* x, int64_t N, int64_t M, int64_t batch_stride,
                                              float* zero_local, float* acc_multicast, void* const* peer_flags,
-                                             int rank, int world, uint32_t epoch, int* timeout_flag, void* stream_) {
-  if (N < 0 || M < 0 || world < 1 || world > 16 || rank < 0 || rank >= world) return DRTK_B200_EINVAL;
+                                             int rank, int world, uint32_t epoch, int* timeout_flag, int max_ctas,
+                                             void* stream_) {
+  if (N < 0 || M < 0 || world < 1 || world > 16 || rank < 0 || rank >= world || max_ctas < 0) return DRTK_B200_EINVAL;
   if (M == 0) return 0;
   if (!zero_local || !acc_multicast || !peer_flags || (N > 0 && !x)) return DRTK_B200_EINVAL;
   float* bucket_local = zero_local;
@@ -163,9 +165,12 @@ extern "C" int drtk_b200_batch_sum_allreduce(const float* x, int64_t N, int64_t 
   PeerFlags fl;
   for (int i = 0; i < 16; ++i) fl.p[i] = i < world ? static_cast<uint32_t*>(peer_flags[i]) : nullptr;
   const bool vec = vec_ok(x, M, batch_stride, bucket_local) && (reinterpret_cast<uintptr_t>(bucket_multicast) % 16 == 0);
-  const unsigned grid = (unsigned)num_sms();
-  if (vec) batch_sum_allreduce_kernel<true><<<grid, 256, 0, stream>>>(x, (int)N, M, batch_stride, bucket_local, bucket_multicast, fl, rank, world, epoch, timeout_flag);
-  else batch_sum_allreduce_kernel<false><<<grid, 256, 0, stream>>>(x, (int)N, M, batch_stride, bucket_local, bucket_multicast, fl, rank, world, epoch, timeout_flag);
+  // max_ctas: 0 = the full wave (an exchange on the critical path); a smaller grid for an exchange that overlaps
+  // other kernels -- its CTAs wait at the rank barrier for the slowest rank and should not hold every SM meanwhile
+  const int wave = num_sms();
+  const unsigned grid = (unsigned)((max_ctas > 0 && max_ctas < wave) ? max_ctas : wave);
+  if (vec) batch_sum_allreduce_kernel<true><<<grid, 256, 0, stream>>>(x, (int)N, M, batch_stride, bucket_local, bucket_multicast, fl, wave, rank, world, epoch, timeout_flag);
+  else batch_sum_allreduce_kernel<false><<<grid, 256, 0, stream>>>(x, (int)N, M, batch_stride, bucket_local, bucket_multicast, fl, wave, rank, world, epoch, timeout_flag);
   DRTK_CHECK_LAUNCH();
   return 0;
 }

@@ -16,11 +16,6 @@
 // config, many more on large triangles.
 #include "common.cuh"
 
-// A/B knob (tools/build_variants.sh): 0 = load a quad's ids at the point of use (round-1 form)
-#ifndef DRTK_RENDER_FWD_PIPELINE
-#define DRTK_RENDER_FWD_PIPELINE 1
-#endif
-
 namespace drtk {
 namespace {
 
@@ -177,22 +172,10 @@ __global__ void __launch_bounds__(256) render_fwd_dense_kernel(RenderArgs a, flo
   const float* vn = a.v + (int64_t)n * a.vs.s0;
   float* bbase = bary_img + (int64_t)n * 3 * HW;
   float* dbase = depth_img + (int64_t)n * HW;
-  // The ids of the NEXT grid-stride iteration are requested before this iteration's gathers: the id load is a DRAM
-  // round trip at the head of a three-level dependent chain (id -> vi row -> vertex rows), 30 % of the stall samples.
-  const int stride = gridDim.x * blockDim.x;
-  auto load_ids = [&](int q) {
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < HW / 4; q += gridDim.x * blockDim.x) {
     const int rem = q * 4;
     const int h = rem / a.W, w = rem - h * a.W;
-    return ldg_stream_i4(ibase + (int64_t)h * a.is.s1 + w);
-  };
-  int q = blockIdx.x * blockDim.x + threadIdx.x;
-  int4 id_next = make_int4(-1, -1, -1, -1);
-  if (DRTK_RENDER_FWD_PIPELINE && q < HW / 4) id_next = load_ids(q);
-  for (; q < HW / 4; q += stride) {
-    const int rem = q * 4;
-    const int h = rem / a.W, w = rem - h * a.W;
-    const int4 id = DRTK_RENDER_FWD_PIPELINE ? id_next : load_ids(q);
-    if (DRTK_RENDER_FWD_PIPELINE && q + stride < HW / 4) id_next = load_ids(q + stride);
+    const int4 id = ldg_stream_i4(ibase + (int64_t)h * a.is.s1 + w);
     const int ids[4] = {id.x, id.y, id.z, id.w};
     float o0[4], o1[4], o2[4], od[4];
     TriSetupFwd ts;
@@ -333,15 +316,6 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(RenderBwdArgs b, float*
 // The per-pixel kernel above spends ~310 thread-instructions per pixel, two thirds of them in the segmented
 // shuffle reduction and in re-deriving the triangle for every pixel.
 constexpr int kWalkPx = 8;
-#ifndef DRTK_RENDER_BWD_MINCTAS
-#define DRTK_RENDER_BWD_MINCTAS 1
-#endif
-#ifndef DRTK_RENDER_BWD_PREFETCH
-#define DRTK_RENDER_BWD_PREFETCH 0  // L1 prefetch (CCTL.PF1) of the later runs' table rows: measured 0.271 vs 0.244 ms, off
-#endif
-#ifndef DRTK_RENDER_BWD_MERGE
-#define DRTK_RENDER_BWD_MERGE 0  // warp-level merge of runs cut at the 8-pixel thread boundary (see the kernel)
-#endif
 #ifndef DRTK_RENDER_BWD_CHUNKS
 #define DRTK_RENDER_BWD_CHUNKS 1  // 8-pixel chunks per thread; measured on B200: 1 -> 0.243 ms, 2 -> 0.271 ms, 4 -> 0.349 ms (config 4)
 #endif
@@ -394,53 +368,35 @@ __device__ __forceinline__ void run_setup(const float4* __restrict__ row, RunSet
   r.i0 = __float_as_int(d.y); r.i1 = __float_as_int(d.z); r.i2 = __float_as_int(d.w);
 }
 
+// Measured and NOT adopted in round 2 (config 4, B200, profiles/r02_opbench_render_bwd_*.txt; baseline 0.244-0.252 ms):
+//   * merging the runs cut at a thread's 8-pixel boundary with the neighbouring thread's run (first run parked in
+//     shared memory, added by the left neighbour): 28 % fewer reductions, but 0.289 ms with a CTA barrier and
+//     0.302 ms warp-synchronous -- the kernel is not bound by the number of REDs;
+//   * vertex carry (the next triangle of a row shares an edge: keep the shared vertices' sums, reduce one row instead
+//     of three per run): 0.291 ms, the 9 compares + 27 selects per run boundary cost more than the REDs they save;
+//   * L1 prefetch (CCTL.PF1) of the later runs' table rows at the head of the thread: 0.271 ms;
+//   * 7 / 8 CTAs per SM through launch bounds (spills): 0.270 / 0.273 ms.
 // CHUNKS: consecutive 8-pixel chunks walked by one thread with the run state carried from chunk to chunk (a run cut
 // at a thread boundary costs an extra table fetch and an extra flush: 8 px per thread = 3 runs per 8 px on the
 // 100k-triangle mesh, 16 px per thread = 5 runs per 16 px).
 template <bool HAS_GB, bool HAS_GD, int CHUNKS>
-__global__ void __launch_bounds__(128, DRTK_RENDER_BWD_MINCTAS) render_bwd_walk_kernel(RenderBwdArgs b, const float4* __restrict__ table,
+__global__ void __launch_bounds__(128) render_bwd_walk_kernel(RenderBwdArgs b, const float4* __restrict__ table,
                                                               float* __restrict__ gpad) {
-#if DRTK_RENDER_BWD_MERGE
-  // A third of the runs exist only because a triangle's row span is cut at the 8-pixel boundary between two lanes.
-  // A lane parks its FIRST run in (warp-private) shared memory instead of flushing it; at the end the lane to its
-  // left adds it to its own LAST run when the ids agree (the accumulators are sums in vertex-gradient space).
-  __shared__ float s_acc[9][128];
-  __shared__ int s_vtx[3][128];
-  __shared__ int s_first[128], s_last[128];
-  const int tid = threadIdx.x, lane = tid & 31;
-  int first = -1;
-  bool first_open = true;
-#endif
   const RenderArgs& a = b.r;
   const int HW = a.H * a.W;
   const int n = blockIdx.y;
   const int rem0 = (blockIdx.x * blockDim.x + threadIdx.x) * (kWalkPx * CHUNKS);
-#if !DRTK_RENDER_BWD_MERGE
   if (rem0 >= HW) return;
-#endif
   const float4* tn = table + (int64_t)n * a.F * 4;
   float* gvn = gpad + (int64_t)n * a.V * 4;
 
   RunSetup r;
   int cur = -1;
   float acc[9];
-  auto flush_now = [&]() {
+  auto flush = [&]() {
     red_add_v4(gvn + (int64_t)r.i0 * 4, acc[0], acc[1], acc[2], 0.f);
     red_add_v4(gvn + (int64_t)r.i1 * 4, acc[3], acc[4], acc[5], 0.f);
     red_add_v4(gvn + (int64_t)r.i2 * 4, acc[6], acc[7], acc[8], 0.f);
-  };
-  auto flush = [&]() {  // the run (cur, r, acc) has ended inside this thread's pixels
-#if DRTK_RENDER_BWD_MERGE
-    if (first_open) {
-      first_open = false;
-      first = cur;
-#pragma unroll
-      for (int i = 0; i < 9; ++i) s_acc[i][tid] = acc[i];
-      s_vtx[0][tid] = r.i0; s_vtx[1][tid] = r.i1; s_vtx[2][tid] = r.i2;
-      return;
-    }
-#endif
-    flush_now();
   };
 #pragma unroll 1
   for (int ch = 0; ch < CHUNKS; ++ch) {
@@ -453,18 +409,6 @@ __global__ void __launch_bounds__(128, DRTK_RENDER_BWD_MINCTAS) render_bwd_walk_
       if (cur != -1) { flush(); cur = -1; }
       continue;
     }
-#if DRTK_RENDER_BWD_PREFETCH
-    // the table row of a run is needed at the run's first pixel: an exposed L2 round trip per run (47 % of the
-    // kernel's stall samples).  The ids are all known here, so the rows of the later runs are requested into L1
-    // now and their latency overlaps the gradient loads and the first run.
-#pragma unroll
-    for (int j = 1; j < kWalkPx; ++j) {
-      if (ids[j] != ids[j - 1] && ids[j] >= 0) {
-        prefetch_l1(tn + (int64_t)ids[j] * 4);
-        prefetch_l1(tn + (int64_t)ids[j] * 4 + 2);
-      }
-    }
-#endif
     float gb0[kWalkPx], gb1[kWalkPx], gb2[kWalkPx], gdp[kWalkPx];
     if (HAS_GB) {
       const float* gp = b.grad_bary + (int64_t)n * 3 * HW + rem;
@@ -524,26 +468,7 @@ __global__ void __launch_bounds__(128, DRTK_RENDER_BWD_MINCTAS) render_bwd_walk_
       acc[3] += dv01x; acc[4] += dv01y; acc[6] += dv02x; acc[7] += dv02y;
     }
   }
-#if DRTK_RENDER_BWD_MERGE
-  // a thread with a single run keeps it in registers as its LAST run (nothing parked): it may receive, never gives
-  s_first[tid] = first;
-  s_last[tid] = cur;
-  __syncwarp();
-  if (first != -1 && !(lane > 0 && s_last[tid - 1] == first)) {  // nobody took the parked run
-    red_add_v4(gvn + (int64_t)s_vtx[0][tid] * 4, s_acc[0][tid], s_acc[1][tid], s_acc[2][tid], 0.f);
-    red_add_v4(gvn + (int64_t)s_vtx[1][tid] * 4, s_acc[3][tid], s_acc[4][tid], s_acc[5][tid], 0.f);
-    red_add_v4(gvn + (int64_t)s_vtx[2][tid] * 4, s_acc[6][tid], s_acc[7][tid], s_acc[8][tid], 0.f);
-  }
-  if (cur != -1) {
-    if (lane < 31 && s_first[tid + 1] == cur) {
-#pragma unroll
-      for (int i = 0; i < 9; ++i) acc[i] += s_acc[i][tid + 1];
-    }
-    flush_now();
-  }
-#else
   if (cur != -1) flush();
-#endif
 }
 
 __global__ void __launch_bounds__(256) unpad_kernel(const float4* __restrict__ gpad, float* __restrict__ grad_v, int64_t rows) {

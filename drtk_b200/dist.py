@@ -90,6 +90,7 @@ class _MultimemBucket:
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         self.numel = numel
         grid = int(self.lib.drtk_b200_batch_sum_allreduce_grid())
+        self.grid = grid
         self.bucket2 = symm_mem.empty(2 * numel, dtype=th.float32, device=device)
         self.bucket2.zero_()
         self.flags = symm_mem.empty(self.world * grid, dtype=th.int32, device=device)
@@ -110,16 +111,17 @@ class _MultimemBucket:
         """The half that holds (or is receiving) the current pass's sums."""
         return self.bucket2[self.half * self.numel:(self.half + 1) * self.numel]
 
-    def reduce(self, x: th.Tensor, offset: int, numel: int, stream: th.cuda.Stream) -> None:
+    def reduce(self, x: th.Tensor, offset: int, numel: int, stream: th.cuda.Stream, max_ctas: int = 0) -> None:
         """current half[offset : offset+numel] = sum over ranks of sum_n x[n]; the same range of the other half of
-        THIS rank is zero-filled for the next pass (one kernel, one cross-rank barrier)."""
+        THIS rank is zero-filled for the next pass (one kernel, one cross-rank barrier).  max_ctas > 0 caps the grid
+        (an exchange that overlaps other kernels); every rank must pass the same value."""
         N = x.shape[0]
         acc = self.half * self.numel + offset
         zero = (1 - self.half) * self.numel + offset
         rc = self.lib.drtk_b200_batch_sum_allreduce(
             self._lib.ptr(x), N, numel, x.stride(0) if N > 1 else numel, self.bucket2.data_ptr() + 4 * zero,
             int(self.h_bucket.multicast_ptr) + 4 * acc, self.peer_flags, self.rank, self.world, self.epoch,
-            self.timeout.data_ptr(), stream.cuda_stream)
+            self.timeout.data_ptr(), int(max_ctas), stream.cuda_stream)
         self._lib.check(rc, "batch_sum_allreduce()")
         self.epoch = (self.epoch + 1) & 0xFFFFFFFF
 
@@ -147,9 +149,18 @@ class SharedGradReducer:
     consume (or copy) them before the next backward pass, and call `finish()` once per backward pass (the multimem
     transport alternates between two bucket halves per pass)."""
 
-    def __init__(self, params: Sequence[th.Tensor], group=None, transport: str = "auto"):
+    def __init__(self, params: Sequence[th.Tensor], group=None, transport: str = "auto",
+                 background_ctas: Optional[int] = None):
         self.params = list(params)
         self.group = group
+        # multimem transport: the exchange of the parameter whose gradient arrives LAST in a backward pass is on the
+        # critical path and runs on a full wave of CTAs; the earlier ones overlap the rest of the backward and run on
+        # `background_ctas` CTAs (default: a quarter of the SMs), because their CTAs sit at the rank barrier until the
+        # slowest rank arrives and would otherwise take registers and issue slots from the kernels they overlap.
+        # The order is learned from the previous pass (identical on every rank: same autograd graph).
+        self.background_ctas = background_ctas
+        self._fired: List[int] = []
+        self._last_fired: Optional[int] = None
         self.sizes = [p[0].numel() for p in self.params]
         self.offsets = [sum(self.sizes[:i]) for i in range(len(self.sizes))]
         # segments start on 16-byte boundaries so that every one takes the 128-bit path
@@ -214,7 +225,11 @@ class SharedGradReducer:
     def _exchange(self, i: int, g: th.Tensor):
         seg = self._segment(i)
         if self.mm is not None:
-            self.mm.reduce(g, self.offsets[i], self.sizes[i], th.cuda.current_stream(g.device))
+            self._fired.append(i)
+            bg = 0
+            if self._last_fired is not None and i != self._last_fired:
+                bg = self.background_ctas if self.background_ctas is not None else max(1, self.mm.grid // 4)
+            self.mm.reduce(g, self.offsets[i], self.sizes[i], th.cuda.current_stream(g.device), max_ctas=bg)
             return None
         batch_sum(g, seg)
         if self._distributed():
@@ -239,6 +254,9 @@ class SharedGradReducer:
         self._last = flat
         if self.mm is not None:
             self.mm.next_pass()
+            if self._fired:
+                self._last_fired = self._fired[-1]
+            self._fired = []
         return out
 
     def close(self) -> None:

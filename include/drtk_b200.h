@@ -302,6 +302,9 @@ int drtk_b200_grid_scatter_backward(const float* grad_out, const int64_t* grad_o
  *   calls.  On return (stream order) this rank's copy of the accumulated half holds the sum over ranks; consume it
  *   before the call after next (which zero-fills it).  timeout_flag (device int, may be NULL) is set to 1 when a peer
  *   did not arrive within ~2 s (the wait then gives up instead of hanging the GPU; the bucket is invalid).
+ *   max_ctas: 0 = one full co-resident wave (drtk_b200_batch_sum_allreduce_grid() CTAs; for an exchange on the critical
+ *   path); > 0 caps the grid for an exchange that overlaps other kernels (its CTAs wait at the barrier for the slowest
+ *   rank).  Every rank must pass the same value.
  * ------------------------------------------------------------------------------------- */
 int drtk_b200_batch_sum(const float* x, int64_t N, int64_t M, int64_t batch_stride, float* out, void* stream);
 
@@ -309,7 +312,7 @@ int drtk_b200_batch_sum_allreduce_grid(void);
 
 int drtk_b200_batch_sum_allreduce(const float* x, int64_t N, int64_t M, int64_t batch_stride, float* zero_local,
                                   float* acc_multicast, void* const* peer_flags, int rank, int world,
-                                  uint32_t epoch, int* timeout_flag, void* stream);
+                                  uint32_t epoch, int* timeout_flag, int max_ctas, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * float64 dispatch of the six hot-path launchers (the reference instantiates every kernel for float and double,
