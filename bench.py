@@ -28,7 +28,7 @@ the same per-GPU workload on its own items (weak scaling, no data-path collectiv
 each parameter as soon as autograd has finished it (drtk_b200.dist.SharedGradReducer: one fused batch-sum +
 multimem all-reduce kernel over NVSwitch multicast memory, or batch-sum kernel + NCCL).
 
-The K-step region is timed R times (--regions, default 3); `ms_per_step` / `value` are the MEDIAN region, all regions
+The K-step region is timed R times (--regions, default 5); `ms_per_step` / `value` are the MEDIAN region, all regions
 are listed.  `parity_check` compares the tensors of one step with the reference CUDA kernels run on the same inputs.
 """
 import argparse
@@ -300,7 +300,7 @@ def main():
     ap.add_argument("--impl", default="new", choices=["new", "reference"])
     ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5])
     ap.add_argument("--overdraw", action="store_true", help="two sheets, the second rotated 7 degrees (occlusion + intersections)")
-    ap.add_argument("--regions", type=int, default=3, help="how many times the K-step region is timed (median reported)")
+    ap.add_argument("--regions", type=int, default=5, help="how many times the K-step region is timed (median reported)")
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "multimem"])
     ap.add_argument("--bg-ctas", type=int, default=None,
                     help="multimem transport: CTAs of the exchanges that overlap the backward (default: a quarter of the SMs; "
@@ -483,6 +483,11 @@ def main():
         return float(ms) / steps
 
     R = max(args.regions, 1)
+    # no collector pauses on the issuing thread inside the timed regions (one region in ~20 showed a 35-ms host hiccup;
+    # the median over R regions is the second guard)
+    import gc
+    gc.collect()
+    gc.disable()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -506,6 +511,7 @@ def main():
     e2e_runs = [timed_region(step_e2e, args.steps, e2e_finish) for _ in range(R)]
     ms_e2e = statistics.median(e2e_runs)
     clocks = sampler.stop() if sampler else None
+    gc.enable()
 
     # the exchange alone (batch sums + all-reduce of both parameters on gradients already in place)
     def exchange_only():

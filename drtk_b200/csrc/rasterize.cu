@@ -69,8 +69,12 @@ constexpr int kRasterThreads = RV_THREADS;  // 128 or 256
 constexpr int kPassRecs = RV_PASS;          // records per pass (<= 248, <= threads): slot ids are bytes, 0xFF = "no owner"
 constexpr int kRecF4 = 5;                   // a record is 5 x 16 B
 constexpr uint32_t kOwnEmpty = 0xFFFFFFFFu;
-constexpr int kLargeBlock = 64;             // large-list entries examined per round of a tile CTA
+constexpr int kLargeBlock = 64;             // large-list entries examined per round of a tile CTA (narrow form)
+constexpr int kScanPerThread = 4;           // ... and per thread in an optimistic wide round
+constexpr int kScanBlock = kScanPerThread * kRasterThreads;
 static_assert(kPassRecs <= kRasterThreads && kPassRecs <= 248 && kPassRecs > kLargeBlock, "pass size");
+
+constexpr int kSuperLog = 3;                // a super-tile is 8 x 8 tiles (256 x 256 pixels): the bins of the "medium" triangles
 
 struct RasterArgs {
   const float* v;
@@ -79,6 +83,28 @@ struct RasterArgs {
   Strides3 vis;
   int N, V, F, H, W;
   int tilesX, tilesY;
+  int superX, superY;  // super-tiles per image
+};
+
+// Triangle lists built by the bin kernels.  Three classes by the extent of the clamped bounding box:
+//   small  (<= 2 x 2 tiles):        one 80-B RECORD per (triangle, tile) in the tile's own contiguous list;
+//   medium (<= 2 x 2 super-tiles):  one (id, bbox) entry per (triangle, super-tile); a tile CTA scans the list of ITS
+//                                   super-tile only (a few hundred boxes at most for any mesh that is not pathological);
+//   large  (the rest):              one (id, bbox) entry in the per-image list every tile CTA scans; a triangle in it
+//                                   spans more than 256 pixels, so an image holds few of them that are visible.
+// (Round 2 first shipped small + large only: a 4 096^2 image of 50-px triangles then put 11 000 boxes in front of each of
+// its 16 384 tile CTAs -- O(tiles x triangles).)
+struct BinLists {
+  uint32_t* tile_count;        // per tile: entries (count pass) / fill cursor (fill pass) / entries (tile kernel)
+  const uint32_t* tile_offset; // per tile: first record of its list
+  float4* recs;
+  uint32_t* med_count;         // per super-tile, same protocol
+  const uint32_t* med_offset;
+  uint32_t* med_id;
+  int4* med_bbox;
+  uint32_t* large_count;       // per image
+  uint32_t* large_id;
+  int4* large_bbox;
 };
 
 // Everything a sample needs, derived once per triangle.
@@ -178,10 +204,10 @@ __device__ __forceinline__ void write_record(const TriFull& s, int f, int meta, 
 // FILL = false: count the list entries of every tile.  FILL = true: append the records (small triangles) and the
 // bounding boxes (large triangles).  Both passes take the same decisions from the same arithmetic.
 template <bool FILL>
-__global__ void __launch_bounds__(256) bin_kernel(RasterArgs a, int64_t total, uint32_t* tile_count,
-                                                  const uint32_t* __restrict__ tile_offset, float4* __restrict__ recs,
-                                                  uint32_t* large_count, uint32_t* __restrict__ large_id,
-                                                  int4* __restrict__ large_bbox) {
+__global__ void __launch_bounds__(256) bin_kernel(RasterArgs a, int64_t total, BinLists L) {
+  uint32_t* tile_count = L.tile_count;
+  const uint32_t* __restrict__ tile_offset = L.tile_offset;
+  float4* __restrict__ recs = L.recs;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   // every lane of the warp stays in the kernel (the fill pass uses warp-wide MATCH / SHFL); `valid` carries the culling
@@ -221,23 +247,42 @@ __global__ void __launch_bounds__(256) bin_kernel(RasterArgs a, int64_t total, u
       write_record(s, f, meta, [&](int q2, float4 val) { dst[q2] = val; });
     }
   }
-  if (FILL && valid && !small) {
-    const uint32_t k = atomicAdd(&large_count[n], 1u);
-    large_id[(int64_t)n * a.F + k] = (uint32_t)f;
-    large_bbox[(int64_t)n * a.F + k] = make_int4(s.bx0, s.by0, s.bx1, s.by1);
+  if (!valid || small) return;  // (after the last warp-wide operation)
+  const int sx0 = tx0 >> kSuperLog, sx1 = tx1 >> kSuperLog, sy0 = ty0 >> kSuperLog, sy1 = ty1 >> kSuperLog;
+  if (sx1 - sx0 <= 1 && sy1 - sy0 <= 1) {  // medium: an entry in each super-tile it touches
+    const int64_t sbase = (int64_t)n * a.superX * a.superY;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int sx = sx0 + (q & 1), sy = sy0 + (q >> 1);
+      if (sx > sx1 || sy > sy1) continue;
+      const int64_t st = sbase + (int64_t)sy * a.superX + sx;
+      if (!FILL) {
+        atomicAdd(&L.med_count[st], 1u);
+      } else {
+        const uint32_t pos = L.med_offset[st] + atomicAdd(&L.med_count[st], 1u);
+        L.med_id[pos] = (uint32_t)f;
+        L.med_bbox[pos] = make_int4(s.bx0, s.by0, s.bx1, s.by1);
+      }
+    }
+  } else if (FILL) {  // large
+    const uint32_t k = atomicAdd(&L.large_count[n], 1u);
+    L.large_id[(int64_t)n * a.F + k] = (uint32_t)f;
+    L.large_bbox[(int64_t)n * a.F + k] = make_int4(s.bx0, s.by0, s.bx1, s.by1);
   }
 }
 
-// Per-image exclusive scan of the tile counts into list offsets, zeroing `count` so that bin_kernel<true> can
-// reuse it as the per-tile cursor.  One CTA of 1024 threads per IMAGE (a small triangle adds at most four list
+// Per-image exclusive scan of the tile counts (blockIdx.y == 0) and of the super-tile counts (blockIdx.y == 1) into
+// list offsets, zeroing `count` so that bin_kernel<true> can reuse it as the fill cursor.  One CTA of 1024 threads per IMAGE (a small triangle adds at most four list
 // entries, so image n owns the fixed list region [n * 4F, (n + 1) * 4F) and the images scan independently):
 // T tiles in coalesced slabs of 4096 entries (uint4 per thread) carrying the running total -- one slab at
 // config 4, four at config 5.  (A single CTA over all N * T counters took 13.6 us at config 4.)
-__global__ void __launch_bounds__(1024) scan_kernel(uint32_t* count, uint32_t* offset, int64_t M,
-                                                    uint32_t list_stride, bool vec) {
+__global__ void __launch_bounds__(1024) scan_kernel(uint32_t* count, uint32_t* offset, int64_t M, bool vec,
+                                                    uint32_t* count2, uint32_t* offset2, int64_t M2, bool vec2,
+                                                    uint32_t list_stride) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (blockIdx.y == 1) { count = count2; offset = offset2; M = M2; vec = vec2; }  // the super-tile (medium) lists
   count += (int64_t)blockIdx.x * M;
   offset += (int64_t)blockIdx.x * M;
   if (tid == 0) carry_s = blockIdx.x * list_stride;
@@ -458,9 +503,10 @@ __device__ __forceinline__ void tile_pass(TileSmem& S, int m, int x_lo, int y_lo
 }
 
 __global__ void __launch_bounds__(kRasterThreads, RV_MIN_CTAS) raster_tiles_kernel(
-    RasterArgs a, const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_offset,
-    const float4* __restrict__ recs, const uint32_t* __restrict__ large_count, const uint32_t* __restrict__ large_id,
-    const int4* __restrict__ large_bbox, float* __restrict__ depth_img, int32_t* __restrict__ index_img) {
+    RasterArgs a, const BinLists L, float* __restrict__ depth_img, int32_t* __restrict__ index_img) {
+  const uint32_t* __restrict__ tile_count = L.tile_count;
+  const uint32_t* __restrict__ tile_offset = L.tile_offset;
+  const float4* __restrict__ recs = L.recs;
   __shared__ TileSmem S;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y, n = blockIdx.z;
@@ -472,6 +518,10 @@ __global__ void __launch_bounds__(kRasterThreads, RV_MIN_CTAS) raster_tiles_kern
 
   const uint32_t cnt = a.F > 0 ? tile_count[t] : 0u;  // after bin_kernel<true>: entries of this tile
   const uint32_t off = a.F > 0 ? tile_offset[t] : 0u;
+  const int64_t st = ((int64_t)n * a.superY + (tile_y >> kSuperLog)) * a.superX + (tile_x >> kSuperLog);
+  const uint32_t nmed = a.F > 0 ? L.med_count[st] : 0u;
+  const uint32_t med_off = a.F > 0 ? L.med_offset[st] : 0u;
+  const uint32_t nlarge_img = a.F > 0 ? L.large_count[n] : 0u;
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
@@ -507,44 +557,74 @@ __global__ void __launch_bounds__(kRasterThreads, RV_MIN_CTAS) raster_tiles_kern
     tile_pass(S, m, x_lo, y_lo, x_lo_f, y_lo_f, best);
   }
 
-  // (2) large triangles of this image: scan the bounding boxes, build the records of those touching the tile
-  const uint32_t nlarge = a.F > 0 ? large_count[n] : 0u;
-  const uint32_t* lid = large_id + (int64_t)n * a.F;
-  const int4* lbb = large_bbox + (int64_t)n * a.F;
-  for (uint32_t base = 0; base < nlarge; base += kLargeBlock) {
-    bool hit = false;
-    uint32_t f = 0;
-    if (tid < kLargeBlock && base + tid < nlarge) {
-      const int4 bb = lbb[base + tid];
-      hit = bb.x <= x_hi && bb.z >= x_lo && bb.y <= y_hi && bb.w >= y_lo;
-      f = lid[base + tid];
-    }
-    const unsigned bm = __ballot_sync(0xffffffffu, hit);
-    if (bm) {
-      int wbase = 0;
-      if (lane == 0) wbase = atomicAdd(&S.nmatch, __popc(bm));
-      wbase = __shfl_sync(0xffffffffu, wbase, 0);
-      if (hit) S.mlist[wbase + __popc(bm & ((1u << lane) - 1u))] = f;
+  // (2) medium triangles (the list of this tile's super-tile), then large triangles (the list of the image): scan the
+  // bounding boxes, build the records of those touching the tile.
+  // The scan is optimistic: every thread tests kScanPerThread boxes per round (kScanBlock boxes between two barriers).
+  // Matches are appended to S.mlist; should a wide round find more than the list can hold, it is undone, the matches
+  // gathered so far are rasterised, and the round is redone in steps of kLargeBlock, which always fit.
+  auto flush_matches = [&](int m) {  // uniform over the CTA, after a barrier; m <= kPassRecs
+    if (tid < m) {
+      TriFull s;
+      float4* dst = S.rec + tid * kRecF4;
+      if (tri_full(a, n, (int)S.mlist[tid], s) && max(s.bx0, x_lo) <= min(s.bx1, x_hi) && max(s.by0, y_lo) <= min(s.by1, y_hi)) {
+        write_record(s, (int)S.mlist[tid], record_meta(s, x_lo, y_lo, x_hi, y_hi, a.W), [&](int q, float4 val) { dst[q] = val; });
+      } else {  // cannot happen for a listed triangle; an empty record keeps the pass well defined
+        dst[0] = dst[1] = dst[2] = dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[4] = make_float4(0.f, __int_as_float((1 << RASTER_META_BY0) | (0 << RASTER_META_BY1)), 0.f, 0.f);
+      }
     }
     __syncthreads();
-    const int m = S.nmatch;
-    if (m > kPassRecs - kLargeBlock || (base + kLargeBlock >= nlarge && m > 0)) {  // uniform over the CTA
-      if (tid < m) {
-        TriFull s;
-        float4* dst = S.rec + tid * kRecF4;
-        if (tri_full(a, n, (int)S.mlist[tid], s) && max(s.bx0, x_lo) <= min(s.bx1, x_hi) && max(s.by0, y_lo) <= min(s.by1, y_hi)) {
-          write_record(s, (int)S.mlist[tid], record_meta(s, x_lo, y_lo, x_hi, y_hi, a.W), [&](int q, float4 val) { dst[q] = val; });
-        } else {  // cannot happen for a listed triangle; an empty record keeps the pass well defined
-          dst[0] = dst[1] = dst[2] = dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
-          dst[4] = make_float4(0.f, __int_as_float((1 << RASTER_META_BY0) | (0 << RASTER_META_BY1)), 0.f, 0.f);
-        }
+    tile_pass(S, m, x_lo, y_lo, x_lo_f, y_lo_f, best);
+    if (tid == 0) S.nmatch = 0;
+    __syncthreads();
+  };
+  auto scan_list = [&](const uint32_t* __restrict__ lid, const int4* __restrict__ lbb, uint32_t count) {
+    auto test_append = [&](uint32_t idx, bool active) {  // convergent: called by whole warps
+      bool hit = false;
+      uint32_t f = 0;
+      if (active) {
+        const int4 bb = lbb[idx];
+        hit = bb.x <= x_hi && bb.z >= x_lo && bb.y <= y_hi && bb.w >= y_lo;
+        f = lid[idx];
+      }
+      const unsigned bm = __ballot_sync(0xffffffffu, hit);
+      if (bm) {
+        int wbase = 0;
+        if (lane == 0) wbase = atomicAdd(&S.nmatch, __popc(bm));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        const int pos = wbase + __popc(bm & ((1u << lane) - 1u));
+        if (hit && pos < kPassRecs) S.mlist[pos] = f;  // beyond the list: dropped, the round is redone (see below)
+      }
+    };
+    for (uint32_t base = 0; base < count; base += kScanBlock) {
+      const uint32_t end = min(base + (uint32_t)kScanBlock, count);
+      const bool last = end == count;
+      const int m0 = S.nmatch;  // stable: written before the last barrier
+#pragma unroll
+      for (int k = 0; k < kScanPerThread; ++k) {
+        const uint32_t idx = base + (uint32_t)(k * kRasterThreads + tid);
+        test_append(idx, idx < end);
       }
       __syncthreads();
-      tile_pass(S, m, x_lo, y_lo, x_lo_f, y_lo_f, best);
-      if (tid == 0) S.nmatch = 0;
-      __syncthreads();
+      const int m = S.nmatch;
+      if (m > kPassRecs) {  // (uniform) the wide round overflowed the list
+        __syncthreads();    // everybody has read m
+        if (tid == 0) S.nmatch = m0;
+        __syncthreads();
+        if (m0 > 0) flush_matches(m0);
+        for (uint32_t b2 = base; b2 < end; b2 += kLargeBlock) {  // the always-fitting form: kLargeBlock boxes per barrier
+          if (wid < kLargeBlock / 32) test_append(b2 + tid, b2 + tid < end);
+          __syncthreads();
+          const int m2 = S.nmatch;
+          if (m2 > kPassRecs - kLargeBlock || (last && b2 + kLargeBlock >= end && m2 > 0)) flush_matches(m2);
+        }
+      } else if (m > 0 && (last || m > kPassRecs - kLargeBlock)) {
+        flush_matches(m);
+      }
     }
-  }
+  };
+  scan_list(L.med_id + med_off, L.med_bbox + med_off, nmed);
+  scan_list(L.large_id + (int64_t)n * a.F, L.large_bbox + (int64_t)n * a.F, nlarge_img);
 
   // (3) resolve + store (:402-415): empty -> index -1 (low word all ones), depth 0.  Lane = pixel of a row: every warp
   // store is one full 128-byte line of index_img / depth_img.
@@ -629,6 +709,9 @@ __global__ void __launch_bounds__(256) unpack_kernel(const unsigned long long* _
 //   d  = fma(a1, b2, -rn(b1 * a2));  r = MUFU.RCP(d)
 //   cx = rn(fma(b1, c2, -rn(c1 * b2)) * r);  cy = rn(fma(c1, a2, -rn(a1 * c2)) * r)       (:193-203)
 //   d == 0  ->  (FLT_MAX, 0)
+#ifndef DRTK_LINES_CHUNK
+#define DRTK_LINES_CHUNK 0x40000000ull  // samples per pass of a triangle's padded box (a test build uses 96 to exercise the multi-pass path)
+#endif
 #ifndef DRTK_LINES_MINCTAS
 #define DRTK_LINES_MINCTAS 3
 #endif
@@ -753,8 +836,8 @@ __global__ void __launch_bounds__(256, DRTK_LINES_MINCTAS) raster_lines_kernel(R
     // of a 4-px triangle keeps 27 of 32 lanes busy; the previous (row, half-row) split kept 18).
     const int bw = bx1 - bx0 + 1, rows = by1 - by0 + 1;
     const uint64_t area = (uint64_t)bw * (uint64_t)rows;
-    for (uint64_t s0 = 0; s0 < area; s0 += 0x40000000ull) {  // one pass unless the box holds > 2^30 samples: 32-bit index math inside
-      const uint32_t cnt = (uint32_t)min((unsigned long long)(area - s0), 0x40000000ull);
+    for (uint64_t s0 = 0; s0 < area; s0 += DRTK_LINES_CHUNK) {  // one pass unless the box holds > 2^30 samples: 32-bit index math inside
+      const uint32_t cnt = (uint32_t)min((unsigned long long)(area - s0), (unsigned long long)DRTK_LINES_CHUNK);
       const uint32_t row0 = s0 ? (uint32_t)(s0 / (uint32_t)bw) : 0u;
       const uint32_t rem0 = s0 ? (uint32_t)(s0 - (uint64_t)row0 * (uint32_t)bw) : 0u;
       for (uint32_t s = (uint32_t)lane; s < cnt; s += 32u) {
@@ -806,19 +889,27 @@ __global__ void __launch_bounds__(256, DRTK_LINES_MINCTAS) raster_lines_kernel(R
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct TiledWorkspace {
-  size_t off_count, off_large_count, zero_bytes, off_offset, off_large_id, off_large_bbox, off_recs, total;
-  int64_t M;
+  size_t off_count, off_med_count, off_large_count, zero_bytes, off_offset, off_med_offset, off_med_id, off_med_bbox,
+      off_large_id, off_large_bbox, off_recs, total;
+  int64_t M;   // tiles of the batch
+  int64_t MS;  // super-tiles of the batch
 };
 
 inline TiledWorkspace tiled_layout(int64_t N, int64_t F, int64_t H, int64_t W) {
   TiledWorkspace w;
   const int64_t tilesX = (W + kTile - 1) >> kTileLog, tilesY = (H + kTile - 1) >> kTileLog;
+  const int64_t superX = (tilesX + (1 << kSuperLog) - 1) >> kSuperLog, superY = (tilesY + (1 << kSuperLog) - 1) >> kSuperLog;
   w.M = N * tilesX * tilesY;
+  w.MS = N * superX * superY;
   size_t o = 0;
   w.off_count = o;       o = align_up(o + sizeof(uint32_t) * (size_t)w.M, 256);
+  w.off_med_count = o;   o = align_up(o + sizeof(uint32_t) * (size_t)w.MS, 256);
   w.off_large_count = o; o = align_up(o + sizeof(uint32_t) * (size_t)N, 256);
   w.zero_bytes = o;      // [0, zero_bytes) is memset to 0 per call
   w.off_offset = o;      o = align_up(o + sizeof(uint32_t) * (size_t)w.M, 256);
+  w.off_med_offset = o;  o = align_up(o + sizeof(uint32_t) * (size_t)w.MS, 256);
+  w.off_med_id = o;      o = align_up(o + sizeof(uint32_t) * (size_t)(4 * N * F), 256);  // a medium triangle: <= 4 super-tiles
+  w.off_med_bbox = o;    o = align_up(o + sizeof(int4) * (size_t)(4 * N * F), 256);
   w.off_large_id = o;    o = align_up(o + sizeof(uint32_t) * (size_t)(N * F), 256);
   w.off_large_bbox = o;  o = align_up(o + sizeof(int4) * (size_t)(N * F), 256);
   w.off_recs = o;        o = align_up(o + (size_t)(kRecF4 * 16) * (size_t)(4 * N * F), 256);
@@ -872,6 +963,8 @@ extern "C" int drtk_b200_rasterize(const float* v, const int64_t* v_strides, con
   a.N = (int)N; a.V = (int)V; a.F = (int)F; a.H = (int)H; a.W = (int)W;
   a.tilesX = (int)((W + kTile - 1) >> kTileLog);
   a.tilesY = (int)((H + kTile - 1) >> kTileLog);
+  a.superX = (a.tilesX + (1 << kSuperLog) - 1) >> kSuperLog;
+  a.superY = (a.tilesY + (1 << kSuperLog) - 1) >> kSuperLog;
   const int64_t total = N * F;
   char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
 
@@ -906,27 +999,34 @@ extern "C" int drtk_b200_rasterize(const float* v, const int64_t* v_strides, con
   if (use_v1()) return rasterize_v1(v, v_strides, vi, vi_strides, N, V, F, H, W, depth_img, index_img, workspace, stream);
   const TiledWorkspace w = tiled_layout(N, F, H, W);
   if (w.M > 0x7FFFFFFFLL || a.tilesY > 65535) return DRTK_B200_EUNSUPPORTED;
-  uint32_t* tile_count = reinterpret_cast<uint32_t*>(ws + w.off_count);
-  uint32_t* large_count = reinterpret_cast<uint32_t*>(ws + w.off_large_count);
-  uint32_t* tile_offset = reinterpret_cast<uint32_t*>(ws + w.off_offset);
-  uint32_t* large_id = reinterpret_cast<uint32_t*>(ws + w.off_large_id);
-  int4* large_bbox = reinterpret_cast<int4*>(ws + w.off_large_bbox);
-  float4* recs = reinterpret_cast<float4*>(ws + w.off_recs);
+  BinLists L;
+  L.tile_count = reinterpret_cast<uint32_t*>(ws + w.off_count);
+  L.tile_offset = reinterpret_cast<uint32_t*>(ws + w.off_offset);
+  L.recs = reinterpret_cast<float4*>(ws + w.off_recs);
+  L.med_count = reinterpret_cast<uint32_t*>(ws + w.off_med_count);
+  L.med_offset = reinterpret_cast<uint32_t*>(ws + w.off_med_offset);
+  L.med_id = reinterpret_cast<uint32_t*>(ws + w.off_med_id);
+  L.med_bbox = reinterpret_cast<int4*>(ws + w.off_med_bbox);
+  L.large_count = reinterpret_cast<uint32_t*>(ws + w.off_large_count);
+  L.large_id = reinterpret_cast<uint32_t*>(ws + w.off_large_id);
+  L.large_bbox = reinterpret_cast<int4*>(ws + w.off_large_bbox);
 
-  DRTK_CUDA(cudaMemsetAsync(ws, 0, w.zero_bytes, stream));  // tile_count + large_count
+  DRTK_CUDA(cudaMemsetAsync(ws, 0, w.zero_bytes, stream));  // tile_count + med_count + large_count
   if (total > 0) {
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    bin_kernel<false><<<blocks, 256, 0, stream>>>(a, total, tile_count, nullptr, nullptr, nullptr, nullptr, nullptr);
+    bin_kernel<false><<<blocks, 256, 0, stream>>>(a, total, L);
     DRTK_CHECK_LAUNCH();
-    const int64_t T = w.M / N;  // tiles per image; 16-B aligned per-image segments allow the uint4 path
+    const int64_t T = w.M / N, TS = w.MS / N;  // tiles / super-tiles per image; 16-B aligned per-image segments allow the uint4 path
     if (4 * F * N > 0xFFFFFFFFLL) return DRTK_B200_EUNSUPPORTED;
-    scan_kernel<<<(unsigned)N, 1024, 0, stream>>>(tile_count, tile_offset, T, (uint32_t)(4 * F), (T & 3) == 0);
+    scan_kernel<<<dim3((unsigned)N, 2u), 1024, 0, stream>>>(L.tile_count, const_cast<uint32_t*>(L.tile_offset), T, (T & 3) == 0,
+                                                            L.med_count, const_cast<uint32_t*>(L.med_offset), TS, (TS & 3) == 0,
+                                                            (uint32_t)(4 * F));
     DRTK_CHECK_LAUNCH();
-    bin_kernel<true><<<blocks, 256, 0, stream>>>(a, total, tile_count, tile_offset, recs, large_count, large_id, large_bbox);
+    bin_kernel<true><<<blocks, 256, 0, stream>>>(a, total, L);
     DRTK_CHECK_LAUNCH();
   }
   raster_tiles_kernel<<<dim3((unsigned)a.tilesX, (unsigned)a.tilesY, (unsigned)N), kRasterThreads, 0, stream>>>(
-      a, tile_count, tile_offset, recs, large_count, large_id, large_bbox, depth_img, index_img);
+      a, L, depth_img, index_img);
   DRTK_CHECK_LAUNCH();
   return 0;
 }

@@ -46,9 +46,12 @@ def batch_sum(x: th.Tensor, out: Optional[th.Tensor] = None) -> th.Tensor:
         lib = _lib.load()
         N = x.shape[0]
         M = out.numel()
-        with th.cuda.device(x.device):
-            rc = lib.drtk_b200_batch_sum(_lib.ptr(x), N, M, x.stride(0) if N > 1 else M, _lib.ptr(out),
-                                         th.cuda.current_stream(x.device).cuda_stream)
+        args = (_lib.ptr(x), N, M, x.stride(0) if N > 1 else M, _lib.ptr(out), th.cuda.current_stream(x.device).cuda_stream)
+        if th.cuda.current_device() == x.device.index:  # the common case: no device-guard round trip on the host path
+            rc = lib.drtk_b200_batch_sum(*args)
+        else:
+            with th.cuda.device(x.device):
+                rc = lib.drtk_b200_batch_sum(*args)
         _lib.check(rc, "batch_sum()")
     else:
         th.sum(x, dim=0, out=out)
@@ -189,7 +192,10 @@ class SharedGradReducer:
         self._bucket = None if self.mm is not None else th.zeros((self.total,), dtype=self.params[0].dtype, device=dev)
         self._last = None  # the bucket (half) that holds the results of the last finished pass
         self._pending = {}
-        self._side = th.cuda.Stream(dev) if self.cuda else None
+        # the side stream only pays when there is a cross-rank exchange to hide; without one its three extra stream
+        # calls per parameter are pure host overhead (they dominate the step of a 512^2 demo scene)
+        self._overlap = self.cuda and self._distributed()
+        self._side = th.cuda.Stream(dev) if self._overlap else None
         self._handles = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
 
     def _distributed(self) -> bool:
@@ -212,7 +218,9 @@ class SharedGradReducer:
     def _make_hook(self, i):
         def hook(p):
             g = p.grad
-            if self.cuda:
+            if self.cuda and not self._overlap:  # single process: the local sums run in stream order, no side stream
+                work = self._exchange(i, g)
+            elif self.cuda:
                 self._side.wait_stream(th.cuda.current_stream(p.device))
                 with th.cuda.stream(self._side):
                     work = self._exchange(i, g)
@@ -249,7 +257,7 @@ class SharedGradReducer:
             if work is not None:
                 work.wait()  # on CUDA: the current stream waits for the collective, the host does not block
             out.append(self._segment(i, flat))
-        if self.cuda:
+        if self._overlap:
             th.cuda.current_stream(self.params[0].device).wait_stream(self._side)
         self._last = flat
         if self.mm is not None:

@@ -169,6 +169,45 @@ def test_rasterize_bit_exact_vs_reference_cuda_baseline_sizes(cfg, N, overdraw):
     assert th.equal(d.view(th.int32), d_ref.view(th.int32))
 
 
+def mixed_size_scene():
+    """One 1280 x 1536 image holding all three bin classes of the tiler: a fine mesh (small: <= 2x2 tiles), a 70-px mesh
+    (medium: super-tile lists) and a 3x3 mesh of ~600-px cells plus two canvas-sized triangles (large: per-image list),
+    interleaved in depth so that every class wins some pixels."""
+    H, W = 1280, 1536
+    parts, faces, off = [], [], 0
+    for nx, ny, z0, z1, seed in ((120, 100, 1.8, 3.2, 31), (22, 18, 1.5, 3.5, 32), (3, 3, 1.2, 3.8, 33)):
+        v, vi = scenes.grid_mesh(nx, ny, H, W, 1, seed=seed)
+        g = th.Generator().manual_seed(seed)
+        v[0, :, 2] = z0 + (z1 - z0) * th.rand((v.shape[1],), generator=g)
+        parts.append(v[0]); faces.append(vi + off); off += v.shape[1]
+    big = th.tensor([[-200.0, -100.0, 2.5], [1700.0, 30.0, 2.6], [700.0, 1500.0, 2.4],
+                     [40.0, 1200.0, 2.2], [1500.0, 1250.0, 3.0], [800.0, -300.0, 2.0]])
+    parts.append(big); faces.append(th.tensor([[0, 1, 2], [3, 4, 5]], dtype=th.int32) + off)
+    return th.cat(parts)[None].contiguous(), th.cat(faces).contiguous(), H, W
+
+
+def test_rasterize_triangle_size_classes_agree_bitwise():
+    v, vi, H, W = mixed_size_scene()
+    vi_b = cu(vi)[None]
+    d0, i0 = _ops.rasterize(cu(v), vi_b, H, W, algo=0)
+    d1, i1 = _ops.rasterize(cu(v), vi_b, H, W, algo=1)
+    assert th.equal(i0, i1) and th.equal(d0.view(th.int32), d1.view(th.int32))
+    nf = [2 * 119 * 99, 2 * 21 * 17, 2 * 2 * 2, 2]  # faces per class, in list order
+    lo = 0
+    for k, n in enumerate(nf):  # every class owns pixels in the result
+        assert int(((i0 >= lo) & (i0 < lo + n)).sum()) > 1000, f"class {k} invisible"
+        lo += n
+
+
+@needs_ref
+def test_rasterize_triangle_size_classes_vs_reference_cuda():
+    v, vi, H, W = mixed_size_scene()
+    d_ref, i_ref = R.rasterize_with_depth(cu(v), cu(vi), H, W)
+    d, i = drtk_b200.rasterize_with_depth(cu(v), cu(vi), H, W)
+    assert th.equal(i, i_ref), f"{int((i != i_ref).sum())} index mismatches"
+    assert th.equal(d.view(th.int32), d_ref.view(th.int32)), "depth bits differ"
+
+
 def test_rasterize_known_answers():
     with open(os.path.join(GOLDEN, "known_answers.json")) as f:
         ka = json.load(f)
