@@ -406,6 +406,13 @@ __device__ __forceinline__ void pair_contribute(const EdgeArgs& a, const FusedAr
   scatter_pixel(a, fz, n, ni, nx, ny, axis, -r.z, -r.w);
 }
 
+// Measured and NOT adopted (profiles/r02_opbench_edge_split_classify_contribute.txt): splitting this kernel into a
+// classification kernel (48-64 registers, survivors written as 6 bits per pixel into a byte image) and a contribution
+// kernel (80 registers, scans the byte image and evaluates the marked pairs with full warps).  Unconstrained the fused
+// kernel wants 158 registers, nearly all for the contribution code, so the split looked like the way to un-spill the
+// classification loop -- but config 3 / 4 / 5 ran at 0.091 / 0.295 / 1.26 ms against 0.082 / 0.264 / 1.06 ms fused (the
+// classification is bound by its id -> table row -> inside-test latency chain, not by the spills, and the second
+// kernel's 1 B/px scan costs 30 us), and the overdraw scene gained only 5-10 % (1.24-1.31 against 1.385 ms).
 // Work item of a warp: a block of kStripRows consecutive centre rows x 256 columns.  The row below a centre row is the
 // next centre row, so it stays in registers (one index-row load per row instead of two).
 #ifndef DRTK_EDGE_PREFETCH

@@ -1,10 +1,19 @@
 #!/bin/bash
-mkdir -p gpurun_out; T=${TAG:-r2q}
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/raster_sanity.py 2>&1 | tail -13 | tee gpurun_out/${T}_raster_sanity.txt
-python tools/raster_sweep.py 2>&1 | tee gpurun_out/${T}_raster_sweep.txt
-python tools/raster_sweep.py --H 4096 --N 2 2>&1 | tee -a gpurun_out/${T}_raster_sweep.txt
-python tools/raster_sweep.py --H 8192 --N 1 --iters 4 2>&1 | tee -a gpurun_out/${T}_raster_sweep.txt
-for c in 4 3 5; do python tools/opbench.py --config $c --ops rasterize 2>&1 | tee -a gpurun_out/${T}_opbench.txt; done
-timeout 600 compute-sanitizer --tool memcheck python tools/raster_sanity.py --small > gpurun_out/${T}_sanitizer_memcheck.txt 2>&1; tail -3 gpurun_out/${T}_sanitizer_memcheck.txt
-timeout 600 compute-sanitizer --tool racecheck python tools/raster_sanity.py --small > gpurun_out/${T}_sanitizer_racecheck.txt 2>&1; tail -3 gpurun_out/${T}_sanitizer_racecheck.txt
+mkdir -p gpurun_out; T=${TAG:-r2r}
+V=drtk_b200/variants
+python -m pytest tests -m gpu -x -q -k "edge or pipeline or raster" 2>&1 | tail -3
+{
+for cfg in 4 3 5; do
+  echo "== config $cfg"
+  DRTK_B200_LIB=$V/lib_eg_single.so python tools/opbench.py --config $cfg --ops edge_fused --dump /tmp/eg_$cfg.pt | sed "s/^/eg_single /"
+  for x in eg_split_a5 eg_split_a4 eg_split_a6 eg_split_a4_b4 eg_split_a4_b2; do
+    DRTK_B200_LIB=$V/lib_$x.so python tools/opbench.py --config $cfg --ops edge_fused --cmp /tmp/eg_$cfg.pt | sed "s/^/$x /"
+  done
+done
+echo "== config 4 overdraw"
+DRTK_B200_LIB=$V/lib_eg_single.so python tools/opbench.py --config 4 --overdraw --ops edge_fused --dump /tmp/eg_o.pt | sed "s/^/eg_single /"
+for x in eg_split_a5 eg_split_a4 eg_split_a6 eg_split_a4_b4 eg_split_a4_b2; do
+  DRTK_B200_LIB=$V/lib_$x.so python tools/opbench.py --config 4 --overdraw --ops edge_fused --cmp /tmp/eg_o.pt | sed "s/^/$x /"
+done
+} > gpurun_out/${T}_opbench.txt 2>&1
+cat gpurun_out/${T}_opbench.txt
