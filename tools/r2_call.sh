@@ -1,19 +1,8 @@
 #!/bin/bash
-mkdir -p gpurun_out; T=${TAG:-r2r}
-V=drtk_b200/variants
-python -m pytest tests -m gpu -x -q -k "edge or pipeline or raster" 2>&1 | tail -3
-{
-for cfg in 4 3 5; do
-  echo "== config $cfg"
-  DRTK_B200_LIB=$V/lib_eg_single.so python tools/opbench.py --config $cfg --ops edge_fused --dump /tmp/eg_$cfg.pt | sed "s/^/eg_single /"
-  for x in eg_split_a5 eg_split_a4 eg_split_a6 eg_split_a4_b4 eg_split_a4_b2; do
-    DRTK_B200_LIB=$V/lib_$x.so python tools/opbench.py --config $cfg --ops edge_fused --cmp /tmp/eg_$cfg.pt | sed "s/^/$x /"
-  done
-done
-echo "== config 4 overdraw"
-DRTK_B200_LIB=$V/lib_eg_single.so python tools/opbench.py --config 4 --overdraw --ops edge_fused --dump /tmp/eg_o.pt | sed "s/^/eg_single /"
-for x in eg_split_a5 eg_split_a4 eg_split_a6 eg_split_a4_b4 eg_split_a4_b2; do
-  DRTK_B200_LIB=$V/lib_$x.so python tools/opbench.py --config 4 --overdraw --ops edge_fused --cmp /tmp/eg_o.pt | sed "s/^/$x /"
-done
-} > gpurun_out/${T}_opbench.txt 2>&1
-cat gpurun_out/${T}_opbench.txt
+# final single-GPU validation of the round: GPU tests, smoke, bench (+ launch list under ncu, not a bench value)
+mkdir -p gpurun_out; T=${TAG:-r2t}
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/${T}_pytest_gpu.txt
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke OK')" 2>&1 | tail -1
+python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; cut -c1-500 gpurun_out/${T}_bench.json; tail -2 gpurun_out/${T}_bench.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${T}_bench_reference_arm.json 2>/dev/null; cut -c1-300 gpurun_out/${T}_bench_reference_arm.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 3 --regions 1 --no-extras --no-cpu-baseline --no-ref-cuda > gpurun_out/${T}_ncu_bench.log 2>&1; wc -l gpurun_out/${T}_launches.csv
