@@ -345,6 +345,10 @@ struct RasterizeFn : torch::autograd::Function<RasterizeFn> {
 // render: gradient to v only, and only when v required grad at forward time (src/render/render_module.cpp:27-72)
 struct RenderFn : torch::autograd::Function<RenderFn> {
   static tensor_list forward(AutogradContext* ctx, const Tensor& v, const Tensor& vi, const Tensor& index_img) {
+    // an output nobody differentiates (usually depth_img) arrives as an UNDEFINED gradient and is passed to the
+    // launcher as a null pointer; the reference lets autograd materialise it (render_module.cpp:46-64): a zero-fill of
+    // [N,H,W] plus a kernel that reads those zeros -- same result, 134 MB + 134 MB of traffic per step at config 4
+    ctx->set_materialize_grads(false);
     ctx->save_for_backward({v, vi, index_img});
     ctx->saved_data["v_requires_grad"] = v.requires_grad();
     at::AutoDispatchBelowADInplaceOrView below;
@@ -353,6 +357,7 @@ struct RenderFn : torch::autograd::Function<RenderFn> {
   static tensor_list backward(AutogradContext* ctx, const tensor_list& grads) {
     if (!ctx->saved_data["v_requires_grad"].toBool()) return tensor_list(3);
     const auto saved = ctx->get_saved_variables();
+    if (!grads[0].defined() && !grads[1].defined()) return {at::zeros_like(saved[0]), Tensor(), Tensor()};
     return {render_cuda_backward(saved[0], saved[1], saved[2], grads[0], grads[1]), Tensor(), Tensor()};
   }
 };
