@@ -112,6 +112,19 @@ SMALL = list(small_scenes())
 SMALL_IDS = [s[0] for s in SMALL]
 
 
+def deep_scene():
+    """300 big triangles over one another: every tile matches more boxes than one pass of the tiler holds (the overflow /
+    redo path of the box-list scan, several passes per tile, deep z-order).  Rasterize tests only."""
+    g = th.Generator().manual_seed(29)
+    v = th.rand((1, 900, 3), generator=g) * th.tensor([360.0, 360.0, 3.0]) + th.tensor([-50.0, -50.0, 0.5])
+    vi = th.arange(900, dtype=th.int32).view(300, 3)
+    return "deep_300_tris_256", v, vi, 256, 256
+
+
+RASTER = SMALL + [deep_scene()]
+RASTER_IDS = [s[0] for s in RASTER]
+
+
 # ------------------------------------------------------------------------------------------------
 # rasterize
 # ------------------------------------------------------------------------------------------------
@@ -140,7 +153,7 @@ def test_rasterize_vs_oracle(scene):
         assert ulp_diff(npy(depth)[~mism], d_o[~mism]).max() <= 16
 
 
-@pytest.mark.parametrize("scene", SMALL, ids=SMALL_IDS)
+@pytest.mark.parametrize("scene", RASTER, ids=RASTER_IDS)
 def test_rasterize_algorithms_agree_bitwise(scene):
     _, v, vi, H, W = scene
     vi_b = cu(vi)[None].expand(v.shape[0], -1, -1)
@@ -150,7 +163,7 @@ def test_rasterize_algorithms_agree_bitwise(scene):
 
 
 @needs_ref
-@pytest.mark.parametrize("scene", SMALL, ids=SMALL_IDS)
+@pytest.mark.parametrize("scene", RASTER, ids=RASTER_IDS)
 def test_rasterize_bit_exact_vs_reference_cuda(scene):
     _, v, vi, H, W = scene
     d_ref, i_ref = R.rasterize_with_depth(cu(v), cu(vi), H, W)
