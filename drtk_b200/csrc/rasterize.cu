@@ -522,6 +522,19 @@ __global__ void __launch_bounds__(kRasterThreads, RV_MIN_CTAS) raster_tiles_kern
   const uint32_t nmed = a.F > 0 ? L.med_count[st] : 0u;
   const uint32_t med_off = a.F > 0 ? L.med_offset[st] : 0u;
   const uint32_t nlarge_img = a.F > 0 ? L.large_count[n] : 0u;
+  if (cnt == 0u && nmed == 0u && nlarge_img == 0u) {
+    // nothing can touch this tile (uniform over the CTA): write the background and leave -- an object in front of an
+    // empty background leaves most tiles here, and the full tile prologue + resolve cost ~8 us per tile
+    const int x = x_lo + lane;
+    if (x <= x_hi) {
+      for (int y = y_lo + wid; y <= y_hi; y += kRasterThreads / 32) {
+        const int64_t o = ((int64_t)n * a.H + y) * a.W + x;
+        index_img[o] = -1;
+        depth_img[o] = 0.f;
+      }
+    }
+    return;
+  }
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();

@@ -1,6 +1,8 @@
 #!/bin/bash
-mkdir -p gpurun_out; T=${TAG:-r2x}
-python bench.py --config 3 > gpurun_out/${T}_bench_c3.json 2> gpurun_out/${T}_bench_c3.err; cut -c1-300 gpurun_out/${T}_bench_c3.json
-python bench.py --config 2 > gpurun_out/${T}_bench_c2.json 2> gpurun_out/${T}_bench_c2.err; cut -c1-300 gpurun_out/${T}_bench_c2.json
-python bench.py --overdraw > gpurun_out/${T}_bench_c4o.json 2> gpurun_out/${T}_bench_c4o.err; cut -c1-300 gpurun_out/${T}_bench_c4o.json
-python bench.py --config 5 --steps 5 --no-cpu-baseline > gpurun_out/${T}_bench_c5.json 2> gpurun_out/${T}_bench_c5.err; cut -c1-300 gpurun_out/${T}_bench_c5.json; tail -2 gpurun_out/${T}_bench_c5.err
+mkdir -p gpurun_out; T=${TAG:-r2y}
+python -m pytest tests -m gpu -x -q -k "rasterize or pipeline or smoke" 2>&1 | tail -2
+python tools/raster_sanity.py 2>&1 | tail -4
+python tools/raster_sweep.py 2>&1 | tee gpurun_out/${T}_raster_sweep.txt
+python tools/opbench.py --config 4 --ops rasterize 2>&1 | tee gpurun_out/${T}_opbench.txt
+python tools/opbench.py --config 3 --ops rasterize 2>&1 | tee -a gpurun_out/${T}_opbench.txt
+python bench.py --no-extras --no-cpu-baseline --regions 3 2>/dev/null | cut -c1-330
