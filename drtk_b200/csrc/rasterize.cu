@@ -609,10 +609,15 @@ __global__ void __launch_bounds__(kRasterThreads, RV_MIN_CTAS) raster_tiles_kern
         if (hit && pos < kPassRecs) S.mlist[pos] = f;  // beyond the list: dropped, the round is redone (see below)
       }
     };
+    // `pending` = matches gathered and not yet rasterised.  It mirrors S.nmatch at the start of every round but lives in
+    // a register: S.nmatch is only ever READ between two barriers that no atomicAdd / reset can cross, so that all
+    // threads see the same value and take the same flush / no-flush branch (the barriers inside the flush would fall
+    // out of step otherwise -- racecheck found exactly that on a scene with 300 overlapping triangles).
+    int pending = 0;
     for (uint32_t base = 0; base < count; base += kScanBlock) {
       const uint32_t end = min(base + (uint32_t)kScanBlock, count);
       const bool last = end == count;
-      const int m0 = S.nmatch;  // stable: written before the last barrier
+      const int m0 = pending;
 #pragma unroll
       for (int k = 0; k < kScanPerThread; ++k) {
         const uint32_t idx = base + (uint32_t)(k * kRasterThreads + tid);
@@ -620,19 +625,28 @@ __global__ void __launch_bounds__(kRasterThreads, RV_MIN_CTAS) raster_tiles_kern
       }
       __syncthreads();
       const int m = S.nmatch;
-      if (m > kPassRecs) {  // (uniform) the wide round overflowed the list
-        __syncthreads();    // everybody has read m
+      __syncthreads();  // every thread has read the counter before anybody changes it again
+      if (m > kPassRecs) {  // (uniform) the wide round overflowed the list: undo it
         if (tid == 0) S.nmatch = m0;
         __syncthreads();
         if (m0 > 0) flush_matches(m0);
+        pending = 0;
         for (uint32_t b2 = base; b2 < end; b2 += kLargeBlock) {  // the always-fitting form: kLargeBlock boxes per barrier
           if (wid < kLargeBlock / 32) test_append(b2 + tid, b2 + tid < end);
           __syncthreads();
           const int m2 = S.nmatch;
-          if (m2 > kPassRecs - kLargeBlock || (last && b2 + kLargeBlock >= end && m2 > 0)) flush_matches(m2);
+          __syncthreads();
+          pending = m2;
+          if (m2 > kPassRecs - kLargeBlock || (last && b2 + kLargeBlock >= end && m2 > 0)) {
+            flush_matches(m2);
+            pending = 0;
+          }
         }
       } else if (m > 0 && (last || m > kPassRecs - kLargeBlock)) {
         flush_matches(m);
+        pending = 0;
+      } else {
+        pending = m;
       }
     }
   };

@@ -1,8 +1,5 @@
 #!/bin/bash
-mkdir -p gpurun_out; T=${TAG:-r2y}
-python -m pytest tests -m gpu -x -q -k "rasterize or pipeline or smoke" 2>&1 | tail -2
-python tools/raster_sanity.py 2>&1 | tail -4
-python tools/raster_sweep.py 2>&1 | tee gpurun_out/${T}_raster_sweep.txt
-python tools/opbench.py --config 4 --ops rasterize 2>&1 | tee gpurun_out/${T}_opbench.txt
-python tools/opbench.py --config 3 --ops rasterize 2>&1 | tee -a gpurun_out/${T}_opbench.txt
-python bench.py --no-extras --no-cpu-baseline --regions 3 2>/dev/null | cut -c1-330
+mkdir -p gpurun_out; T=${TAG:-r2ab}
+timeout 70 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "(algorithms_agree and deep_300) or size_classes_agree" > gpurun_out/${T}_sanitizer_racecheck_deep.txt 2>&1; tail -3 gpurun_out/${T}_sanitizer_racecheck_deep.txt
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2 | tee gpurun_out/${T}_pytest_gpu.txt
+python tools/opbench.py --config 4 --ops rasterize --iters 10 2>&1 | tail -1 | tee gpurun_out/${T}_opbench.txt
