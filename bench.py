@@ -2,7 +2,8 @@
 """bench.py -- the DRTK rasterisation hot path on B200: Mpixels/s, forward + backward.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl new|reference] [--config 2|3|4|5] [--overdraw]
-                    [--regions R] [--transport auto|nccl|multimem]
+                    [--regions R] [--transport auto|nccl|multimem] [--bg-ctas B] [--dispatch auto|torch|ctypes]
+                    [--no-extras] [--no-cpu-baseline] [--no-ref-cuda]
 
 One step = one pass of the hot path over one batch of synthetic input (BASELINE.json):
 
@@ -15,7 +16,8 @@ attributes (the configuration the metric is quoted on).  Prints ONE JSON line (r
 
   value          whole-job Mpix/s with inputs resident in HBM, CUDA-event timed, max over ranks
   e2e            same metric through the public API with HOST (pinned) inputs: every step copies
-                 v_pix / attr / vi to the device and reads both gradients back
+                 v_pix / attr to the device (the topology vi stays resident) and reads the step's result
+                 back (the gradients summed over the batch and the ranks), copies double-buffered
   roofline       the dominant kernel of the step: algorithmic bytes / its event-timed duration,
                  against the measured HBM copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline   the reference's own CPU kernels (oracle/_ref, built from the unmodified reference
