@@ -64,3 +64,52 @@ def test_overlapped_reducer_without_process_group():
     red.close()
     assert th.equal(g, w.sum(0))
     assert red.finish() == [None]
+
+
+def test_reducer_background_grid_follows_the_firing_order(monkeypatch):
+    """multimem transport, host logic only (a stub stands in for the symmetric-memory bucket): the exchange of the parameter
+    whose gradient arrived LAST in the previous pass runs on a full wave (max_ctas 0), the earlier ones on the background
+    grid; the first pass, whose order is unknown, runs everything on a full wave.  Every rank derives the same values from
+    the same autograd graph -- a mismatch would leave the ranks' in-kernel barriers with different grids."""
+    import torch as th
+    from drtk_b200 import dist as ddist
+
+    calls = []
+
+    class StubBucket:
+        grid = 148
+
+        def __init__(self, numel):
+            self.flat = th.zeros((numel,))
+
+        @property
+        def bucket(self):
+            return self.flat
+
+        def reduce(self, x, offset, numel, stream, max_ctas=0):
+            calls.append((offset, max_ctas))
+            self.flat[offset:offset + numel] = x.sum(0).reshape(-1)
+
+        def next_pass(self):
+            pass
+
+    monkeypatch.setattr(ddist.th.cuda, "current_stream", lambda device=None: None)
+    for background, expect in ((None, 148 // 4), (16, 16), (0, 0)):
+        v = th.zeros((2, 5, 3), requires_grad=True)
+        a = th.zeros((2, 5, 4), requires_grad=True)
+        red = ddist.SharedGradReducer([v, a], background_ctas=background)
+        red.mm = StubBucket(red.total)
+        for it in range(3):
+            calls.clear()
+            v.grad = None
+            a.grad = None
+            (a * 2.0).sum().backward()   # a fires first ...
+            (v * 3.0).sum().backward()   # ... v last
+            gv, ga = red.finish()
+            assert th.allclose(gv, th.full((5, 3), 6.0)) and th.allclose(ga, th.full((5, 4), 4.0))
+            off_v, off_a = red.offsets
+            if it == 0:
+                assert calls == [(off_a, 0), (off_v, 0)]
+            else:
+                assert calls == [(off_a, expect), (off_v, 0)]
+        red.close()
