@@ -82,3 +82,22 @@ def test_dispatcher_boundary_registers_the_reference_schemas():
     with pytest.raises(RuntimeError, match="same cuda device"):
         torch.ops.drtk_b200_render_ext.render(torch.zeros(1, 3, 3), torch.zeros(1, 1, 3, dtype=torch.int32),
                                               torch.zeros(1, 4, 4, dtype=torch.int32))
+
+
+def test_rasterize_workspace_covers_its_lists():
+    """No GPU: the workspace query must cover every list the bin kernels may fill in the worst case (records of small
+    triangles: 4 per triangle x 80 B; medium entries: 4 per triangle x 20 B; large entries: 1 per triangle x 20 B; two
+    uint32 per tile and per 256-px super-tile) and the packed 64-bit image of the wireframe / validation paths, and grow
+    with the batch."""
+    from drtk_b200 import _lib
+    lib = _lib.load()
+    for N, F, H, W in ((1, 2, 512, 512), (8, 100352, 2048, 2048), (3, 7, 33, 65), (1, 0, 16, 16)):
+        tiles = ((H + 31) // 32) * ((W + 31) // 32)
+        supers = ((H + 255) // 256) * ((W + 255) // 256)
+        need = N * F * (4 * 80 + 4 * 20 + 20) + N * (tiles + supers) * 8 + N * 4
+        got = lib.drtk_b200_rasterize_workspace_bytes(N, F, H, W, 0)
+        assert got >= need, (N, F, H, W, got, need)
+        assert got >= 8 * N * H * W  # wireframe mode shares the buffer
+        assert lib.drtk_b200_rasterize_workspace_bytes(N, F, H, W, 1) >= 8 * N * H * W
+        assert lib.drtk_b200_rasterize_workspace_bytes(N + 1, F, H, W, 0) >= got
+    assert lib.drtk_b200_rasterize_workspace_bytes(0, 5, 64, 64, 0) == 0
